@@ -1,0 +1,153 @@
+/* libttk -- B200 (sm_100a) kernels for the UpliftingTableTennis inference hot path.
+ *
+ * C ABI.  The reference (KieDani/UpliftingTableTennis) is pure Python/PyTorch and has no
+ * FFI of its own; each entry point below therefore replaces one
+ * Python call seam of the reference and cites it.  Host code (Python, ctypes) owns every
+ * activation/input/output buffer and passes raw device pointers plus the CUDA stream to
+ * launch on; the library never synchronises the device and never allocates on the forward
+ * path.  Handles own only their pre-packed weights.
+ *
+ * Conventions
+ *   - return value: 0 = ok, negative = error; ttk_last_error() gives the message of the last
+ *     failing call on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - pointers named *_dev are device pointers, *_host host pointers.
+ *   - activations are NHWC ("pixels x channels"), C padded to a multiple of 16.
+ */
+#ifndef TTK_H
+#define TTK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTK_VERSION 100          /* 0.1.0 */
+#define TTK_API __attribute__((visibility("default")))
+
+enum { TTK_OK = 0, TTK_ERR_ARG = -1, TTK_ERR_CUDA = -2, TTK_ERR_STATE = -3, TTK_ERR_UNSUPPORTED = -4 };
+enum { TTK_F32 = 0, TTK_BF16 = 1 };                 /* arithmetic/storage type of a path */
+enum { TTK_DECODE_TABLE = 0, TTK_DECODE_BALL = 1 }; /* the two live sub-pixel variants */
+enum { TTK_LAYOUT_NCHW_F32 = 0, TTK_LAYOUT_NHWC16 = 1 };
+
+TTK_API int ttk_version(void);
+TTK_API const char* ttk_last_error(void);
+/* 1 when a CUDA device with compute capability 10.x is present, else 0 (never raises). */
+TTK_API int ttk_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Frame pre-processing: cv2.resize (uint8, INTER_LINEAR, bit exact) + ImageNet normalise
+ * (3x256 LUT) + stack [prev, cur, next] + HWC->CHW.
+ * Replaces balldetection/transforms.py:17-52 (Resize), :379-402 (NormalizeImage) and
+ * interface.py:110-112 (concat / rearrange / astype / H2D); tabledetection/transforms.py:9-40.
+ *
+ * frames_dev : n_frames x src_h x src_w x 3 uint8 (HWC, channel order as stored: BGR from the
+ *              hub API).  Stack s reads frames s*stack_stride + {0..frames_per_stack-1}.
+ * lut_dev    : 3 x 256 float32, lut[c][v] = float32((v/255 - mean[c]) / std[c]) (host float64).
+ * out_dev    : layout NCHW_F32: n_stacks x (3*fps) x dst_h x dst_w float32 (the reference tensor)
+ *              layout NHWC16  : n_stacks x dst_h x dst_w x 16, dtype f32 or bf16, channels
+ *              3*fps..15 zero -- the detector input.
+ */
+TTK_API int ttk_preprocess_stacks(const uint8_t* frames_dev, int n_frames, int src_h, int src_w,
+                          int frames_per_stack, int stack_stride, int n_stacks,
+                          int dst_h, int dst_w, const float* lut_dev,
+                          void* out_dev, int layout, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HRNet-W18-small heatmap network (WASB ball detector / HRNet table detector).
+ * Replaces WASBNet.forward (balldetection/models/wasb.py:596-608), HRNet.forward (:445-486)
+ * and MyHRNet.forward (tabledetection/models/hrnet.py:588-590); weights come from the
+ * reference checkpoint through load_model (inference/inference_balldetection.py:40-61).
+ */
+typedef struct ttk_hrnet ttk_hrnet;
+
+/* in_ch: 9 (WASB, 3 stacked frames) or 3 (table); out_ch: 3 or 13 = channels of the final
+ * 1x1 conv; out_first/out_count: the slice of them that is materialised (WASB returns
+ * channel 1 only: out_first=1, out_count=1). */
+TTK_API int ttk_hrnet_create(int in_ch, int out_ch, int out_first, int out_count, ttk_hrnet** out);
+TTK_API void ttk_hrnet_destroy(ttk_hrnet* h);
+TTK_API int ttk_hrnet_num_convs(const ttk_hrnet* h);
+/* name: state-dict key of the conv weight without ".weight"; bn: state-dict prefix of its
+ * batch norm ("" = none, the conv has a bias).  Buffers must hold 128 chars. */
+TTK_API int ttk_hrnet_conv_info(const ttk_hrnet* h, int i, char* name, char* bn, int* cin, int* cout,
+                        int* k, int* stride);
+/* BN-folded weights of conv i: w_host[cout][cin][k][k] float32, b_host[cout] float32.
+ * The library re-packs them for both arithmetic paths and uploads them. */
+TTK_API int ttk_hrnet_set_conv(ttk_hrnet* h, int i, const float* w_host, const float* b_host);
+TTK_API size_t ttk_hrnet_workspace_bytes(const ttk_hrnet* h, int batch, int height, int width, int dtype);
+/* x_dev: batch x H x W x 16 (NHWC16, dtype); heatmaps_dev: batch x out_count x H x W float32.
+ * H and W must be multiples of 8.  dtype TTK_F32: fp32 SIMT path (parity with the CPU
+ * reference); TTK_BF16: tcgen05 tensor-core path (bf16 storage, fp32 accumulate). */
+TTK_API int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int height, int width, int dtype,
+                      float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* kernels launched by the last ttk_hrnet_forward on this handle (for bench accounting) */
+TTK_API int ttk_hrnet_last_launches(const ttk_hrnet* h);
+
+/* ---------------------------------------------------------------------------------------
+ * Heatmap decode: first-max argmax + 3x3 zero-padded window + bounded Gaussian fit +
+ * heatmap->image rescale.  Replaces extract_position_torch_gaussian,
+ * tabledetection/helper_tabledetection.py:50-156 (variant TABLE; interface.py:116,169) and
+ * balldetection/helper_balldetection.py:29-110 (variant BALL; inference/utils.py:59).
+ *
+ * heatmaps_dev : n_maps x H x W float32 (any (B,C) flattening)
+ * out_xyv_dev  : n_maps x 3 float64  [x_img, y_img, 1.0]
+ * out_idx_dev  : n_maps int32 flat argmax index            (may be NULL)
+ * out_win_dev  : n_maps x 9 float32 window, row major      (may be NULL)
+ * workspace    : ttk_decode_workspace_bytes(n_maps, H, W)
+ */
+TTK_API size_t ttk_decode_workspace_bytes(int n_maps, int height, int width);
+TTK_API int ttk_heatmap_decode(const float* heatmaps_dev, int n_maps, int height, int width, int variant,
+                       int image_width, int image_height, double* out_xyv_dev, int32_t* out_idx_dev,
+                       float* out_win_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Trajectory packing: pixel -> [0,1] normalisation, pad/crop to seq_len, mask.
+ * Replaces _uplifting_transform (inference/utils.py:268-309), batched over clips.
+ * ball_xy_dev: sum(lengths) x 2 float64 (concatenated clips), times_dev: sum(lengths) float64,
+ * offsets_dev: n_clips+1 int32 prefix sums, table_dev: n_clips x 13 x 3 float64.
+ * Outputs float32: ball n x seq x 2, table n x 13 x 3, times n x seq, mask n x seq.
+ */
+TTK_API int ttk_trajectory_pack(const double* ball_xy_dev, const double* times_dev, const int32_t* offsets_dev,
+                        const double* table_dev, int n_clips, int seq_len, double img_w, double img_h,
+                        float* ball_out, float* table_out, float* times_out, float* mask_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Uplifting transformer (MultiStageModel 'multistage' / 'connectstage', size 'large',
+ * tabletoken_mode 'dynamic', time_rotation 'new').
+ * Replaces MultiStageModel.forward (uplifting/model.py:529-571) incl. FirstStage (:335-390),
+ * SimpleStaticLayer (:278-300), rotary attention (:186-229, :56-102), embeddings, heads; weights
+ * from inference/inference_uplifting.py:33-58.
+ */
+typedef struct ttk_uplift ttk_uplift;
+TTK_API int ttk_uplift_create(int dim, int heads, int depth, int use_skipconnection, ttk_uplift** out);
+TTK_API void ttk_uplift_destroy(ttk_uplift* h);
+TTK_API int ttk_uplift_num_params(const ttk_uplift* h);
+/* name: state-dict key; numel: element count (row-major, as stored by torch). */
+TTK_API int ttk_uplift_param_info(const ttk_uplift* h, int i, char* name, int* numel);
+TTK_API int ttk_uplift_set_param(ttk_uplift* h, int i, const float* data_host, int numel);
+TTK_API size_t ttk_uplift_workspace_bytes(const ttk_uplift* h, int batch, int seq_len, int dtype);
+/* ball B x T x 2, table B x 13 x 3 (x, y, visibility), mask B x T in {0,1}, times B x T (s);
+ * rot_out B x 3 (global axes), pos_out B x T x 3.  All float32 device pointers.
+ * The caller validates the mask (the reference raises ValueError on an all-ones mask). */
+TTK_API int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const float* table_dev, const float* mask_dev,
+                       const float* times_dev, int batch, int seq_len, int dtype, float* rot_out_dev,
+                       float* pos_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+TTK_API int ttk_uplift_last_launches(const ttk_uplift* h);
+
+/* Spin global -> local axes.  Replaces transform_rotationaxes (uplifting/helper.py:394-420).
+ * rot B x 3, pos B x T x 3 -> out B x 3, float32. */
+TTK_API int ttk_rotation_local(const float* rot_dev, const float* pos_dev, int batch, int seq_len,
+                       float* out_dev, void* stream);
+
+/* Camera projection cam2img(world2cam(p)).  Replaces uplifting/helper.py:137-204 and
+ * TableTennisPipeline.reproject (interface.py:301-312).  points n x 3, mext 4x4 row major,
+ * mint 3x3 row major (the leading 3x3 of Mint), out n x 2.  dtype_f64 != 0: float64 (the numpy
+ * path of the reference), else float32 (its torch path). */
+TTK_API int ttk_project(const void* points_dev, const void* mext_dev, const void* mint_dev, int n,
+                int dtype_f64, void* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTK_H */

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference-generated golden
+files.  Needs a B200: run with `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode as odec
+from oracle import hrnet as ohr
+from oracle import preprocess as opre
+from oracle import tails as otl
+from oracle import uplift as oup
+from oracle.gen_golden import synthetic_frames, synthetic_heatmaps, synthetic_trajectories
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'gpu tests need a CUDA device'
+    from upliftingtabletennis_b200 import _lib
+    _lib.require_device()
+    return torch.device('cuda:0')
+
+
+# ------------------------------------------------------------------------------------------------
+# pre-processing: bit exact
+# ------------------------------------------------------------------------------------------------
+def test_preprocess_golden_bit_exact(dev, golden):
+    from upliftingtabletennis_b200 import ops
+    g = golden('preprocess')
+    w, h = (int(v) for v in g['res'])
+    frames = torch.from_numpy(g['frames']).to(dev)
+    ball = ops.preprocess_stacks(frames, 3, 1, 1, w, h, layout='nchw')
+    assert np.array_equal(ball[0].cpu().numpy(), g['ball_stack'])
+    tab = ops.preprocess_stacks(frames[1:2], 1, 1, 1, w, h, layout='nchw')
+    assert np.array_equal(tab[0].cpu().numpy(), g['table_stack'])
+
+
+@pytest.mark.parametrize('res', [(1280, 704), (1600, 896), (1152, 640), (1920, 1088), (1920, 1080)])
+def test_preprocess_1080p_bit_exact(dev, res):
+    from upliftingtabletennis_b200 import ops
+    rng = np.random.default_rng(7)
+    frames = synthetic_frames(rng, 4, 1080, 1920)
+    w, h = res
+    fd = torch.from_numpy(np.stack(frames)).to(dev)
+    out = ops.preprocess_stacks(fd, 3, 1, 2, w, h, layout='nchw').cpu().numpy()
+    for s in range(2):
+        assert np.array_equal(out[s], opre.preprocess_stack(frames[s:s + 3], w, h)), (res, s)
+    # detector layouts hold the same numbers (channels 9..15 zero; bf16 = round-to-nearest of the fp32 value)
+    nhwc = ops.preprocess_stacks(fd, 3, 1, 2, w, h, layout='nhwc16', dtype=torch.float32)
+    assert torch.equal(nhwc[..., :9].permute(0, 3, 1, 2).cpu(), torch.from_numpy(out))
+    assert float(nhwc[..., 9:].abs().max()) == 0.0
+    nb = ops.preprocess_stacks(fd, 3, 1, 2, w, h, layout='nhwc16', dtype=torch.bfloat16)
+    assert torch.equal(nb, nhwc.to(torch.bfloat16))
+    # stride-3 addressing (BallDetector.predict gets independent triples)
+    o3 = ops.preprocess_stacks(fd[:3], 3, 3, 1, w, h, layout='nchw').cpu().numpy()
+    assert np.array_equal(o3[0], out[0])
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+DECODE_TOL_PX = 5e-3    # image pixels; SciPy's own stopping error (pgtol 1e-5) is ~1e-3 px, see DESIGN.md
+
+
+def _decode_both(dev, hm, variant):
+    from upliftingtabletennis_b200 import ops
+    out, idx, win = ops.decode_heatmaps(torch.from_numpy(hm).to(dev), 1920, 1080, variant, return_debug=True)
+    ref, ridx, rwin = odec.decode_heatmaps(hm, 1920, 1080, odec.TABLE if variant == 'table' else odec.BALL)
+    return out.cpu().numpy(), idx.cpu().numpy(), win.cpu().numpy(), ref, ridx, rwin
+
+
+@pytest.mark.parametrize('variant', ['table', 'ball'])
+def test_decode_golden(dev, golden, variant):
+    g = golden('decode')
+    hm = g['heatmaps']
+    out, idx, win, ref, ridx, rwin = _decode_both(dev, hm, variant)
+    assert np.array_equal(idx, ridx)                       # integer work: identical
+    assert np.array_equal(win, rwin)
+    gold = g['table'] if variant == 'table' else g['ball']
+    ok = np.ones(len(hm), bool) if variant == 'table' else g['ball_ok']
+    assert np.all(out[:, 2] == 1.0)
+    err = np.abs(out[ok, :2] - gold[ok, :2]).max(axis=1)
+    # well-conditioned windows (a real peak) agree to SciPy's stopping error; report the rest
+    assert np.median(err) < 2e-4, np.median(err)
+    assert np.mean(err < DECODE_TOL_PX) >= 0.9, np.sort(err)[-8:]
+
+
+def test_decode_full_size_and_properties(dev):
+    """704x1280 maps (BASELINE config 2): argmax identity incl. ties/NaN, translation covariance of the fit."""
+    from upliftingtabletennis_b200 import ops
+    rng = np.random.default_rng(11)
+    H, W = 704, 1280
+    hm = (rng.standard_normal((6, H, W)) * 0.05).astype(np.float32)
+    yy, xx = np.mgrid[0:H, 0:W]
+    centres = [(100.3, 200.6), (0.2, 0.4), (W - 1.0, H - 1.3), (640.5, 352.5), (17.0, 600.0), (1279.0, 0.0)]
+    for i, (cx, cy) in enumerate(centres):
+        hm[i] += np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * 1.5 ** 2)).astype(np.float32)
+    hm[4, 10, 10] = hm[4].max() + 1           # two exact ties: first index wins
+    hm[4, 500, 77] = hm[4, 10, 10]
+    hm[5, 300, 300] = np.nan                  # NaN counts as the maximum (torch.argmax)
+    t = torch.from_numpy(hm).to(dev)
+    out, idx, win = ops.decode_heatmaps(t, 1920, 1080, 'table', return_debug=True)
+    ref_idx = torch.argmax(t.view(6, -1), dim=1).cpu().numpy()
+    assert np.array_equal(idx.cpu().numpy(), ref_idx)
+    assert idx[4].item() == 10 * W + 10 and idx[5].item() == 300 * W + 300
+    ref, _, _ = odec.decode_heatmaps(hm[:4], 1920, 1080, odec.TABLE)
+    np.testing.assert_allclose(out[:4].cpu().numpy(), ref, rtol=0, atol=DECODE_TOL_PX)
+    assert np.isnan(out[5, 0].item())
+    # shifting the map by whole pixels shifts the answer by exactly that many heatmap pixels
+    sh = torch.roll(t[0:1], shifts=(5, 9), dims=(1, 2))
+    o2 = ops.decode_heatmaps(sh, W, H, 'table')
+    o1 = ops.decode_heatmaps(t[0:1], W, H, 'table')
+    np.testing.assert_allclose((o2 - o1)[0, :2].cpu().numpy(), [9.0, 5.0], atol=1e-9)
+
+
+def test_decode_shapes_and_ragged(dev):
+    from upliftingtabletennis_b200 import ops
+    rng = np.random.default_rng(5)
+    hm = synthetic_heatmaps(rng, 26, 37, 53)            # odd sizes: scalar load path
+    out = ops.decode_heatmaps(torch.from_numpy(hm).to(dev).view(2, 13, 37, 53), 1920, 1080, 'table')
+    assert out.shape == (2, 13, 3) and out.dtype == torch.float64
+    ref, _, _ = odec.decode_heatmaps(hm, 1920, 1080, odec.TABLE)
+    err = np.abs(out.view(26, 3).cpu().numpy() - ref)[:, :2].max(axis=1)
+    assert np.mean(err < DECODE_TOL_PX) >= 0.9
+    empty = ops.decode_heatmaps(torch.zeros((0, 8, 8), device=dev), 1920, 1080, 'ball')
+    assert empty.shape == (0, 3)
+
+
+# ------------------------------------------------------------------------------------------------
+# heatmap networks
+# ------------------------------------------------------------------------------------------------
+HEATMAP_RTOL = 1e-4      # |d| <= 1e-4 * max|h| + 1e-5
+
+
+def _heat_tol(ref):
+    return HEATMAP_RTOL * float(np.abs(ref).max()) + 1e-5
+
+
+def test_wasb_fp32_golden(dev, golden):
+    from upliftingtabletennis_b200.detector import WASBNet
+    g = golden('hrnet')
+    m = WASBNet().to(dev).eval()
+    m.load_state_dict(ohr.random_state_dict(9, 3, seed=int(g['wasb_seed'])))
+    y, none = m(torch.from_numpy(g['wasb_x']).to(dev))
+    assert none is None and y.shape == (2, 1, 64, 96)
+    np.testing.assert_allclose(y.cpu().numpy(), g['wasb_y'], rtol=0, atol=_heat_tol(g['wasb_y']))
+
+
+def test_table_hrnet_fp32_golden(dev, golden):
+    from upliftingtabletennis_b200.detector import MyHRNet
+    g = golden('hrnet')
+    m = MyHRNet().to(dev).eval()
+    m.load_state_dict(ohr.random_state_dict(3, 13, seed=int(g['table_seed'])))
+    y = m(torch.from_numpy(g['table_x']).to(dev))
+    assert y.shape == (1, 13, 64, 96)
+    np.testing.assert_allclose(y.cpu().numpy(), g['table_y'], rtol=0, atol=_heat_tol(g['table_y']))
+
+
+@pytest.mark.parametrize('shape', [(1, 88, 160), (3, 40, 72), (2, 8, 8)])
+def test_wasb_fp32_vs_oracle_shapes(dev, shape):
+    from upliftingtabletennis_b200.detector import WASBNet
+    B, H, W = shape
+    rng = np.random.default_rng(B * 1000 + H)
+    sd = ohr.random_state_dict(9, 3, seed=77)
+    x = rng.standard_normal((B, 9, H, W)).astype(np.float32)
+    ref = ohr.wasb_forward(sd, torch.from_numpy(x)).numpy()
+    m = WASBNet().to(dev).eval()
+    m.load_state_dict(sd)
+    y, _ = m(torch.from_numpy(x).to(dev))
+    np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=0, atol=_heat_tol(ref))
+    # peak index identical wherever the oracle's top-2 margin exceeds twice the tolerance
+    flat = ref.reshape(B, -1)
+    top2 = np.sort(flat, axis=1)[:, -2:]
+    sure = (top2[:, 1] - top2[:, 0]) > 2 * _heat_tol(ref)
+    got = y.view(B, -1).argmax(dim=1).cpu().numpy()
+    assert np.array_equal(got[sure], flat.argmax(axis=1)[sure])
+
+
+def test_wasb_bf16_bound(dev):
+    """bf16 storage / fp32 accumulate path: reported separately with its own (empirical) bound."""
+    from upliftingtabletennis_b200.detector import WASBNet
+    rng = np.random.default_rng(3)
+    sd = ohr.random_state_dict(9, 3, seed=78)
+    x = rng.standard_normal((2, 9, 64, 96)).astype(np.float32)
+    ref = ohr.wasb_forward(sd, torch.from_numpy(x)).numpy()
+    m = WASBNet().to(dev).eval()
+    m.load_state_dict(sd)
+    m.compute_dtype = torch.bfloat16
+    y, _ = m(torch.from_numpy(x).to(dev))
+    rel = np.linalg.norm(y.cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert rel < 3e-2, rel
+
+
+# ------------------------------------------------------------------------------------------------
+# uplifting transformer and tails
+# ------------------------------------------------------------------------------------------------
+UPLIFT_ATOL, UPLIFT_RTOL = 1e-4, 1e-4
+
+
+@pytest.mark.parametrize('name', ['connectstage', 'multistage'])
+def test_uplift_golden(dev, golden, name):
+    from upliftingtabletennis_b200.uplift import get_model
+    g = golden('uplift')
+    m = get_model(name, 'large', 'dynamic', 'new').to(dev).eval()
+    m.load_state_dict(oup.random_state_dict(int(g[name + '_seed'])))
+    args = [torch.from_numpy(g[name + '_' + k]).to(dev) for k in ('ball', 'table', 'mask', 'times')]
+    rot, pos = m(*args)
+    np.testing.assert_allclose(pos.cpu().numpy(), g[name + '_pos'], rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+    np.testing.assert_allclose(rot.cpu().numpy(), g[name + '_rot'], rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+
+
+def test_uplift_t60_and_batch(dev, golden):
+    from upliftingtabletennis_b200.uplift import get_model
+    g = golden('uplift')
+    m = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+    sd = oup.random_state_dict(int(g['connectstage_seed']))
+    m.load_state_dict(sd)
+    args = [torch.from_numpy(g['t60_' + k]).to(dev) for k in ('ball', 'table', 'mask', 'times')]
+    rot, pos = m(*args)
+    np.testing.assert_allclose(pos.cpu().numpy(), g['t60_pos'], rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+    np.testing.assert_allclose(rot.cpu().numpy(), g['t60_rot'], rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+    # a ragged batch against the oracle, and batch-composition independence
+    rng = np.random.default_rng(9)
+    ball, table, mask, times = synthetic_trajectories(rng, 37)
+    r_ref, p_ref = oup.uplift_forward(sd, *(torch.from_numpy(a) for a in (ball, table, mask, times)))
+    rot, pos = m(*(torch.from_numpy(a).to(dev) for a in (ball, table, mask, times)))
+    np.testing.assert_allclose(pos.cpu().numpy(), p_ref.numpy(), rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+    np.testing.assert_allclose(rot.cpu().numpy(), r_ref.numpy(), rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+    r1, p1 = m(*(torch.from_numpy(a[5:6]).to(dev) for a in (ball, table, mask, times)))
+    assert torch.equal(r1[0], rot[5]) and torch.equal(p1[0], pos[5])
+
+
+def test_uplift_mask_errors(dev):
+    from upliftingtabletennis_b200.uplift import get_model
+    m = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+    m.load_state_dict(oup.random_state_dict(1))
+    z = torch.zeros
+    with pytest.raises(ValueError):       # all-ones mask (uplifting/model.py:541-546)
+        m(z(1, 50, 2, device=dev), torch.ones(1, 13, 3, device=dev), torch.ones(1, 50, device=dev), z(1, 50, device=dev))
+
+
+def test_tails(dev, golden):
+    from upliftingtabletennis_b200 import ops
+    g = golden('tails')
+    rl = ops.rotation_local(torch.from_numpy(g['rot']).to(dev), torch.from_numpy(g['pos']).to(dev))
+    np.testing.assert_allclose(rl.cpu().numpy(), g['rot_local'], rtol=1e-5, atol=1e-6)
+    pr = ops.project(torch.from_numpy(g['p3']).double().to(dev), torch.from_numpy(g['Mext']).to(dev), torch.from_numpy(g['Mint']).to(dev))
+    np.testing.assert_allclose(pr.cpu().numpy(), g['proj'], rtol=1e-12, atol=1e-9)
+    pr32 = ops.project(torch.from_numpy(g['p3']).to(dev), torch.from_numpy(g['Mext']).to(dev), torch.from_numpy(g['Mint']).to(dev))
+    np.testing.assert_allclose(pr32.cpu().numpy(), g['proj'], rtol=1e-5)
+    # batched _uplifting_transform: one short clip (padding) and one long clip (crop to 50)
+    fpos, ftimes, table = g['fpos'], g['ftimes'], g['table']
+    ball = np.concatenate([fpos, g['long_pos']])
+    times = np.concatenate([ftimes, g['long_times']])
+    offs = np.array([0, len(fpos), len(fpos) + len(g['long_pos'])], np.int32)
+    b, t, ti, mk = ops.trajectory_pack(torch.from_numpy(ball).to(dev), torch.from_numpy(times).to(dev),
+                                       torch.from_numpy(offs).to(dev), torch.from_numpy(np.stack([table, table])).to(dev))
+    assert np.array_equal(b[0:1].cpu().numpy(), g['ut_ball']) and np.array_equal(t[0:1].cpu().numpy(), g['ut_table'])
+    assert np.array_equal(ti[0:1].cpu().numpy(), g['ut_times']) and np.array_equal(mk[0:1].cpu().numpy(), g['ut_mask'])
+    assert np.array_equal(b[1:2].cpu().numpy(), g['utl_ball']) and np.array_equal(ti[1:2].cpu().numpy(), g['utl_times'])
+    assert np.array_equal(mk[1:2].cpu().numpy(), g['utl_mask'])

@@ -1,0 +1,65 @@
+// HRNet executor internals shared between hrnet.cu (plan + SIMT kernels) and conv_umma.cu (tcgen05 path).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "ttk_internal.h"
+
+struct TtkConv {
+  std::string name, bn;
+  int cin, cout, k, stride;     // logical sizes (reference)
+  int cin_p, cout_p;            // padded to multiples of 16
+  bool set = false;
+  float* w_f32 = nullptr;       // device, [k*k][cin_p][cout_p] float32 (SIMT path)
+  float* w_bfr = nullptr;       // device, same layout, values rounded to bf16 (SIMT path on bf16 storage)
+  float* bias = nullptr;        // device, [cout_p] float32
+  __nv_bfloat16* w_umma = nullptr;  // device, tcgen05 B-operand image: [k*k][cout_p][cin_p] bf16 (K-major per tap)
+};
+
+struct TtkTensor {
+  int c;        // channels (padded)
+  int shift;    // resolution = (H >> shift, W >> shift)
+  int first, last;   // op indices of first write / last read (liveness)
+  size_t offset;     // byte offset in the workspace (per forward plan)
+};
+
+enum { OP_CONV = 0, OP_SUM = 1, OP_FINAL = 2 };
+
+struct TtkOp {
+  int type;
+  int conv = -1;
+  int in = -1, out = -1;
+  int nres = 0;
+  int res[3] = {-1, -1, -1};   // residual / summand tensors
+  bool relu = false;
+};
+
+struct ConvLaunch {
+  const void* in;
+  void* out;
+  const void* res[3];
+  int res_shift[3];
+  int nres;
+  int n, hin, win, hout, wout;
+  int cin, cout;       // padded
+  int relu;
+};
+
+struct ttk_hrnet {
+  int in_ch, out_ch, out_first, out_count;
+  std::vector<TtkConv> convs;
+  std::vector<TtkTensor> tensors;
+  std::vector<TtkOp> ops;
+  int input_tensor = -1;
+  int subbatch = 1;
+  int launches = 0;
+  int force_simt = 0;           // bf16 storage through the SIMT kernels (debug / cross-check of the tcgen05 path)
+  // final 1x1 conv weights: [out_count][16] + bias[out_count], float32 device
+  float* final_w = nullptr;
+  float* final_b = nullptr;
+};
+
+// conv_umma.cu: bf16 implicit-GEMM convolution on tcgen05/TMEM fed by TMA.
+// Returns TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel (caller falls back to SIMT on bf16).
+int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st);
+int ttk_conv_umma_pack(TtkConv& cv, const float* w_host);

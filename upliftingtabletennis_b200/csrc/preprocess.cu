@@ -1,0 +1,143 @@
+// Fused frame pre-processing: bit-exact cv2.resize (uint8 INTER_LINEAR, 11-bit fixed point)
+// + LUT normalise + [prev,cur,next] stack + layout change, one pass, uint8 in.
+// Reference: balldetection/transforms.py:17-52, :379-402; interface.py:110-112.
+//
+// HBM-bound: per stack 3 source frames are read once (later taps hit L1/L2) and the stack is
+// written once with 128-bit stores.  One thread produces one output pixel (all 3*F channels).
+#include "ttk_internal.h"
+
+namespace {
+
+struct AxisTap {
+  int s0, s1, a0, a1;
+};
+
+// OpenCV resize tap for destination index d (see oracle/preprocess.py: axis_taps).
+// __dmul_rn/__dadd_rn/__fsub_rn keep the compiler from contracting into FMAs, which would
+// change the rounding of the float32 coordinate.
+__device__ __forceinline__ AxisTap axis_tap(int d, int n_src, double scale) {
+  const double fd = __dadd_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), -0.5);
+  float f = (float)fd;
+  int s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (s < 0) {
+    s = 0;
+    f = 0.f;
+  }
+  if (s >= n_src - 1) {
+    s = n_src - 1;
+    f = 0.f;
+  }
+  AxisTap t;
+  t.s0 = s;
+  t.s1 = min(s + 1, n_src - 1);
+  t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+template <int F, int MODE>   // F frames per stack; MODE 0: NCHW f32, 1: NHWC16 f32, 2: NHWC16 bf16
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w,
+                                                         int stack_stride, int dst_h, int dst_w, double scale_x,
+                                                         double scale_y, const float* __restrict__ lut,
+                                                         void* __restrict__ out) {
+  __shared__ float s_lut[768];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int s = blockIdx.z;
+  if (x >= dst_w) return;
+  const bool same = (src_h == dst_h && src_w == dst_w);
+  const AxisTap tx = axis_tap(x, src_w, scale_x);
+  const AxisTap ty = axis_tap(y, src_h, scale_y);
+  float v[3 * F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    const uint8_t* img = frames + (size_t)(s * stack_stride + f) * src_h * src_w * 3;
+    const uint8_t* r0 = img + ((size_t)ty.s0 * src_w) * 3;
+    const uint8_t* r1 = img + ((size_t)ty.s1 * src_w) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int u8;
+      if (same) {
+        u8 = __ldg(img + ((size_t)y * src_w + x) * 3 + c);
+      } else {
+        const int h0 = __ldg(r0 + tx.s0 * 3 + c) * tx.a0 + __ldg(r0 + tx.s1 * 3 + c) * tx.a1;
+        const int h1 = __ldg(r1 + tx.s0 * 3 + c) * tx.a0 + __ldg(r1 + tx.s1 * 3 + c) * tx.a1;
+        const int acc = ((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16);
+        u8 = min(255, max(0, (acc + 2) >> 2));
+      }
+      v[f * 3 + c] = s_lut[c * 256 + u8];
+    }
+  }
+  if (MODE == 0) {
+    float* o = (float*)out + (size_t)s * (3 * F) * dst_h * dst_w + (size_t)y * dst_w + x;
+#pragma unroll
+    for (int c = 0; c < 3 * F; ++c) o[(size_t)c * dst_h * dst_w] = v[c];
+  } else if (MODE == 1) {
+    float4* o = (float4*)((float*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
+    float w[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) w[c] = c < 3 * F ? v[c] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  } else {
+    uint4* o = (uint4*)((__nv_bfloat16*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float lo = 2 * c < 3 * F ? v[2 * c] : 0.f;
+      const float hi = 2 * c + 1 < 3 * F ? v[2 * c + 1] : 0.f;
+      __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+      w[c] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+template <int F>
+int launch(int mode, dim3 grid, cudaStream_t st, const uint8_t* frames, int src_h, int src_w, int stack_stride, int dst_h,
+           int dst_w, const float* lut, void* out) {
+  const double sx = (double)src_w / (double)dst_w, sy = (double)src_h / (double)dst_h;
+  if (mode == 0)
+    preprocess_kernel<F, 0><<<grid, 256, 0, st>>>(frames, src_h, src_w, stack_stride, dst_h, dst_w, sx, sy, lut, out);
+  else if (mode == 1)
+    preprocess_kernel<F, 1><<<grid, 256, 0, st>>>(frames, src_h, src_w, stack_stride, dst_h, dst_w, sx, sy, lut, out);
+  else
+    preprocess_kernel<F, 2><<<grid, 256, 0, st>>>(frames, src_h, src_w, stack_stride, dst_h, dst_w, sx, sy, lut, out);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}
+
+}  // namespace
+
+extern "C" int ttk_preprocess_stacks(const uint8_t* frames_dev, int n_frames, int src_h, int src_w, int frames_per_stack,
+                                     int stack_stride, int n_stacks, int dst_h, int dst_w, const float* lut_dev,
+                                     void* out_dev, int layout, int dtype, void* stream) {
+  TTK_CHECK_ARG(frames_dev && lut_dev && out_dev, "ttk_preprocess_stacks: null pointer");
+  TTK_CHECK_ARG(frames_per_stack == 1 || frames_per_stack == 3, "ttk_preprocess_stacks: frames_per_stack must be 1 or 3");
+  TTK_CHECK_ARG(n_stacks >= 0 && stack_stride >= 1 && src_h > 0 && src_w > 0 && dst_h > 0 && dst_w > 0,
+                "ttk_preprocess_stacks: bad sizes");
+  TTK_CHECK_ARG(n_stacks == 0 || (n_stacks - 1) * stack_stride + frames_per_stack <= n_frames,
+                "ttk_preprocess_stacks: stacks read past the last frame (%d stacks, stride %d, %d frames)", n_stacks,
+                stack_stride, n_frames);
+  TTK_CHECK_ARG(n_stacks <= 65535 && dst_h <= 65535, "ttk_preprocess_stacks: grid too large");
+  int mode;
+  if (layout == TTK_LAYOUT_NCHW_F32) {
+    TTK_CHECK_ARG(dtype == TTK_F32, "ttk_preprocess_stacks: NCHW output is float32 only");
+    mode = 0;
+  } else if (layout == TTK_LAYOUT_NHWC16) {
+    TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16, "ttk_preprocess_stacks: bad dtype");
+    mode = dtype == TTK_F32 ? 1 : 2;
+  } else {
+    ttk_set_error("ttk_preprocess_stacks: bad layout %d", layout);
+    return TTK_ERR_ARG;
+  }
+  if (n_stacks == 0) return TTK_OK;
+  dim3 grid(ttk_cdiv(dst_w, 256), dst_h, n_stacks);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (frames_per_stack == 3) return launch<3>(mode, grid, st, frames_dev, src_h, src_w, stack_stride, dst_h, dst_w, lut_dev, out_dev);
+  return launch<1>(mode, grid, st, frames_dev, src_h, src_w, stack_stride, dst_h, dst_w, lut_dev, out_dev);
+}

@@ -1,0 +1,109 @@
+"""Python-side wrappers of the stateless libttk entry points (include/ttk.h).  Device memory,
+streams and tensors are torch's; arithmetic happens in the CUDA library only."""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+MEAN = (0.485, 0.456, 0.406)     # balldetection/transforms.py:507
+STD = (0.229, 0.224, 0.225)
+_lut_cache = {}
+
+
+def normalize_lut(device):
+    """3x256 float32 table of float32((v/255 - mean[c]) / std[c]), computed in float64 on the host
+    exactly as NormalizeImage does per pixel (balldetection/transforms.py:388-390)."""
+    key = str(device)
+    if key not in _lut_cache:
+        v = np.arange(256, dtype=np.float64) / 255.0
+        lut = np.stack([(v - MEAN[c]) / STD[c] for c in range(3)]).astype(np.float32)
+        _lut_cache[key] = torch.from_numpy(lut).to(device)
+    return _lut_cache[key]
+
+
+def preprocess_stacks(frames, frames_per_stack, stack_stride, n_stacks, dst_w, dst_h, layout='nhwc16', dtype=torch.float32,
+                      out=None):
+    """frames: (n, H, W, 3) uint8 CUDA tensor.  Returns (n_stacks, 3*fps, h, w) float32 for layout
+    'nchw' (the reference's tensor, interface.py:110-112) or (n_stacks, h, w, 16) for 'nhwc16'."""
+    _lib.require_device()
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
+    frames = frames.contiguous()
+    n, sh, sw, _ = frames.shape
+    if layout == 'nchw':
+        assert dtype == torch.float32
+        shape, lay = (n_stacks, 3 * frames_per_stack, dst_h, dst_w), _lib.LAYOUT_NCHW_F32
+    else:
+        shape, lay = (n_stacks, dst_h, dst_w, 16), _lib.LAYOUT_NHWC16
+    if out is None:
+        out = torch.empty(shape, dtype=dtype, device=frames.device)
+    assert tuple(out.shape) == shape and out.dtype == dtype and out.is_contiguous()
+    dt = _lib.F32 if dtype == torch.float32 else _lib.BF16
+    check(lib.ttk_preprocess_stacks(ptr(frames), n, sh, sw, frames_per_stack, stack_stride, n_stacks, dst_h, dst_w,
+                                    ptr(normalize_lut(frames.device)), ptr(out), lay, dt, stream_ptr()))
+    return out
+
+
+def decode_heatmaps(heatmaps, image_width, image_height, variant='table', return_debug=False):
+    """heatmaps: (..., H, W) float32 CUDA tensor -> (..., 3) float64 CUDA tensor [x_img, y_img, 1].
+    variant 'table': tabledetection/helper_tabledetection.py:50-156; 'ball': balldetection/helper_balldetection.py:29-110."""
+    _lib.require_device()
+    assert heatmaps.is_cuda and heatmaps.dtype == torch.float32 and heatmaps.dim() >= 2
+    hm = heatmaps.contiguous()
+    H, W = hm.shape[-2:]
+    lead = hm.shape[:-2]
+    n = int(np.prod(lead)) if len(lead) else 1
+    out = torch.empty((n, 3), dtype=torch.float64, device=hm.device)
+    idx = torch.empty((n,), dtype=torch.int32, device=hm.device)
+    win = torch.empty((n, 9), dtype=torch.float32, device=hm.device)
+    v = {'table': _lib.DECODE_TABLE, 'ball': _lib.DECODE_BALL}[variant]
+    for b0 in range(0, n, 65535):
+        nb = min(65535, n - b0)
+        ws_bytes = lib.ttk_decode_workspace_bytes(nb, H, W)
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=hm.device)
+        check(lib.ttk_heatmap_decode(ptr(hm.view(n, H, W)[b0:b0 + nb]), nb, H, W, v, int(image_width), int(image_height),
+                                     ptr(out[b0:b0 + nb]), ptr(idx[b0:b0 + nb]), ptr(win[b0:b0 + nb]), ptr(ws), ws_bytes,
+                                     stream_ptr()))
+    out = out.view(*lead, 3)
+    if return_debug:
+        return out, idx.view(*lead), win.view(*lead, 3, 3)
+    return out
+
+
+def trajectory_pack(ball_xy, times, offsets, table, seq_len=50, img_w=1920.0, img_h=1080.0):
+    """Batched _uplifting_transform (inference/utils.py:268-309).  ball_xy (sum T', 2) f64, times (sum T',) f64,
+    offsets (n+1,) int32 prefix sums, table (n, 13, 3) f64 -- all CUDA.  Returns float32 ball, table, times, mask."""
+    _lib.require_device()
+    n = table.shape[0]
+    dev = table.device
+    ball_o = torch.empty((n, seq_len, 2), dtype=torch.float32, device=dev)
+    table_o = torch.empty((n, 13, 3), dtype=torch.float32, device=dev)
+    times_o = torch.empty((n, seq_len), dtype=torch.float32, device=dev)
+    mask_o = torch.empty((n, seq_len), dtype=torch.float32, device=dev)
+    check(lib.ttk_trajectory_pack(ptr(ball_xy.contiguous()), ptr(times.contiguous()), ptr(offsets.contiguous()),
+                                  ptr(table.contiguous()), n, seq_len, float(img_w), float(img_h), ptr(ball_o), ptr(table_o),
+                                  ptr(times_o), ptr(mask_o), stream_ptr()))
+    return ball_o, table_o, times_o, mask_o
+
+
+def rotation_local(rot, pos):
+    """transform_rotationaxes (uplifting/helper.py:394-420): rot (B,3), pos (B,T,3) float32 CUDA -> (B,3)."""
+    _lib.require_device()
+    rot, pos = rot.contiguous(), pos.contiguous()
+    out = torch.empty_like(rot)
+    check(lib.ttk_rotation_local(ptr(rot), ptr(pos), rot.shape[0], pos.shape[1], ptr(out), stream_ptr()))
+    return out
+
+
+def project(points, mext, mint):
+    """cam2img(world2cam(points, Mext), Mint) (uplifting/helper.py:137-204).  points (N,3), Mext (4,4), Mint (3,3|3,4);
+    float64 or float32 CUDA tensors -> (N,2)."""
+    _lib.require_device()
+    f64 = points.dtype == torch.float64
+    dt = points.dtype
+    pts = points.contiguous()
+    me = mext.to(dt).contiguous()
+    mi = mint[:3, :3].to(dt).contiguous()
+    out = torch.empty((pts.shape[0], 2), dtype=dt, device=pts.device)
+    check(lib.ttk_project(ptr(pts), ptr(me), ptr(mi), pts.shape[0], 1 if f64 else 0, ptr(out), stream_ptr()))
+    return out

@@ -1,0 +1,318 @@
+"""Benchmark of the hot path (BASELINE.json: frames/sec end-to-end + uplift trajectories/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--dtype bf16|f32]
+
+A step = one pass of ball-detect + decode over one batch of 32 synthetic 1920x1080 three-frame stacks
+(BASELINE.json configs[1]): fused resize/normalise/stack -> WASB heatmap network -> argmax + sub-pixel decode.
+`value` counts frames (= stacks) per second with the uint8 frames already resident in HBM; `e2e` is the same
+metric through the hub API (`hubconf.ball_detection('wasb').predict`) with pinned HOST frames in and host
+positions out.  The uplifting transformer is timed in the same run and reported under "uplift".
+Multi-GPU: clips are independent, every rank processes its own batch (weak scaling) and NCCL gathers the
+per-stack results; time = max over ranks.  `--impl reference` times the CPU oracle port of the reference's
+path on the host cores (the reference is Python and cannot travel to the GPU box).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32                 # stacks per step (BASELINE.json configs[1])
+RES = (1280, 704)          # WASB input resolution (balldetection/config.py:84-85)
+SRC = (1080, 1920)
+WASB_GFLOP_PER_STACK = 344.07        # SURVEY.md section 8d (2*MAC, convs only)
+UPLIFT_GFLOP_PER_TRAJ = 0.753
+UPLIFT_BATCH = 4096
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def make_checkpoints(hub_dir):
+    """Synthetic weights tree in the reference's checkpoint format so that the hub API can be used as a user would."""
+    from upliftingtabletennis_b200 import synthetic
+    from upliftingtabletennis_b200.detector import HRNetEngine
+    from upliftingtabletennis_b200.uplift import get_model
+    w = os.path.join(hub_dir, 'checkpoints', 'tt_uplifting_extracted', 'weights')
+    wasb_sd = synthetic.hrnet_state_dict(HRNetEngine(9, 3, 1, 1).state_dict_layout(), seed=1)
+    up = get_model('connectstage', 'large', 'dynamic', 'new')
+    up_sd = synthetic.uplift_state_dict(up, seed=3)
+    for sub, sd, info in (('inference_balldetection/wasb', wasb_sd, {'model_name': 'wasb', 'image_resolution': RES, 'in_frames': 3, 'lr': 0.0}),
+                          ('inference_uplifting/ours', up_sd, {'name': 'connectstage', 'size': 'large', 'tabletoken_mode': 'dynamic',
+                                                               'time_rotation': 'new', 'transform_mode': 'global', 'randdet_prob': 0.0,
+                                                               'randmiss_prob': 0.0, 'tablemiss_prob': 0.0})):
+        d = os.path.join(w, sub)
+        os.makedirs(d, exist_ok=True)
+        torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(d, 'model.pt'))
+    return wasb_sd, up_sd
+
+
+def cpu_reference_step(wasb_sd, frames, n_stacks):
+    """The reference's path restated on the CPU (oracle port): transform -> WASB forward -> decode, B=1 per stack like
+    interface.py:102-119.  Returns seconds."""
+    from oracle import decode as odec, hrnet as ohr, preprocess as opre
+    t0 = time.perf_counter()
+    for s in range(n_stacks):
+        x = opre.preprocess_stack([frames[s], frames[s + 1], frames[s + 2]], RES[0], RES[1])
+        hm = ohr.wasb_forward(wasb_sd, torch.from_numpy(x)[None]).numpy()
+        odec.decode_heatmaps(hm[:, 0], SRC[1], SRC[0], odec.TABLE)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from upliftingtabletennis_b200 import synthetic
+    from upliftingtabletennis_b200.detector import HRNetEngine
+    torch.set_num_threads(os.cpu_count())
+    sd = synthetic.hrnet_state_dict(HRNetEngine(9, 3, 1, 1).state_dict_layout(), seed=1)
+    per_step = 2
+    frames = synthetic.frames_1080p(per_step + 2, seed=100)
+    for _ in range(args.warmup):
+        cpu_reference_step(sd, frames, 1)
+    t = sum(cpu_reference_step(sd, frames, per_step) for _ in range(args.steps))
+    v = per_step * args.steps / t
+    line = {'impl': 'reference', 'metric': 'frames_per_sec_detect_decode', 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: WASB ball-detect + decode on 1920x1080 3-frame stacks, 1280x704 input; bounded sample of %d stacks per step (B=1 per forward like interface.py)' % per_step},
+            'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': '%d steps x %d stacks through oracle/ (numpy resize + CPU torch fp32 WASB + SciPy L-BFGS-B decode)' % (args.steps, per_step)},
+            'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    from upliftingtabletennis_b200 import _lib, ops, synthetic
+    from upliftingtabletennis_b200._lib import lib
+    hub = tempfile.mkdtemp(prefix='ttk_bench_hub_')
+    torch.hub.set_dir(hub)
+    wasb_sd, up_sd = make_checkpoints(hub)
+    import hubconf
+    det = hubconf.ball_detection('wasb')
+    cdt = torch.bfloat16 if args.dtype == 'bf16' else torch.float32
+    det.model.compute_dtype = cdt
+    engine = det.model.engine
+
+    frames_np = synthetic.frames_1080p(BATCH + 2, seed=100 + rank)
+    frames_pinned = torch.from_numpy(frames_np).pin_memory()
+    frames_dev = frames_pinned.to(dev)
+    W, H = RES
+    x = torch.empty((BATCH, H, W, 16), dtype=cdt, device=dev)
+    heat = torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev)
+    gathered = torch.empty((world * BATCH, 3), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device(gather=True):
+        ops.preprocess_stacks(frames_dev, 3, 1, BATCH, W, H, layout='nhwc16', dtype=cdt, out=x)
+        det.model._sync()
+        engine.forward_nhwc16(x, out=heat)
+        pos = ops.decode_heatmaps(heat, SRC[1], SRC[0], 'table')
+        if world > 1 and gather:
+            dist.all_gather_into_tensor(gathered, pos.view(BATCH, 3))
+        return pos
+
+    triples = [(frames_pinned[i], frames_pinned[i + 1], frames_pinned[i + 2]) for i in range(BATCH)]
+
+    def step_e2e():
+        pos, _ = det.predict(triples, return_heatmaps=False)      # host frames in, host positions out
+        return pos
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_device, args.steps, args.warmup)
+    launches = 1 + engine.last_launches() + 2
+    clocks = sampler.stop() if rank == 0 else None
+    t0 = time.perf_counter()
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    value = world * BATCH * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
+
+    # ---- uplift transformer (trajectories/s), same run ------------------------------------------
+    from upliftingtabletennis_b200.uplift import get_model
+    up = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+    up.load_state_dict(up_sd)
+    ub, ut, um, uti = (torch.from_numpy(a) for a in synthetic.trajectories(UPLIFT_BATCH, seed=7 + rank))
+    ub_p, ut_p, um_p, uti_p = (a.pin_memory() for a in (ub, ut, um, uti))
+    ub_d, ut_d, um_d, uti_d = (a.to(dev) for a in (ub, ut, um, uti))
+    up._sync()
+
+    def uplift_device():
+        rot, pos = up.engine.forward(ub_d, ut_d, um_d, uti_d)
+        return ops.rotation_local(rot, pos)
+
+    def uplift_e2e():
+        args_d = [a.to(dev, non_blocking=True) for a in (ub_p, ut_p, um_p, uti_p)]
+        rot, pos = up.engine.forward(*args_d)
+        return ops.rotation_local(rot, pos).cpu(), pos.cpu()
+
+    ms_up = timed(uplift_device, args.steps, args.warmup)
+    ms_up_e2e = timed(uplift_e2e, args.steps, args.warmup)
+    up_value = world * UPLIFT_BATCH * args.steps / (ms_up * 1e-3)
+    up_e2e = world * UPLIFT_BATCH * args.steps / (ms_up_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----------
+    pk = peaks()
+    check = _lib.check
+    check(lib.ttk_hrnet_set_profile(engine.h, 1))
+    step_device(gather=False)
+    torch.cuda.synchronize()
+    per = {}
+    n = lib.ttk_hrnet_profile_count(engine.h)
+    ot, ci, ms, fl, by = C.c_int(), C.c_int(), C.c_float(), C.c_double(), C.c_double()
+    tot_ms = 0.0
+    for i in range(n):
+        check(lib.ttk_hrnet_profile_read(engine.h, i, C.byref(ot), C.byref(ci), C.byref(ms), C.byref(fl), C.byref(by)))
+        key = (ot.value, ci.value)
+        r = per.setdefault(key, [0.0, 0.0, 0.0, 0])
+        r[0] += ms.value
+        r[1] += fl.value
+        r[2] += by.value
+        r[3] += 1
+        tot_ms += ms.value
+    check(lib.ttk_hrnet_set_profile(engine.h, 0))
+    (top_type, top_conv), top = max(per.items(), key=lambda kv: kv[1][0])
+    name = engine.specs[top_conv][0] if top_conv >= 0 else ('fuse_sum' if top_type == 1 else 'final_conv')
+    achieved_tf = top[1] / (top[0] * 1e-3) / 1e12
+    conv_ms = sum(v[0] for k, v in per.items() if k[0] == 0)
+    conv_fl = sum(v[1] for k, v in per.items() if k[0] == 0)
+    roofline = {
+        'bound': 'tensor', 'kernel': 'conv %s (%d launches/step, %.1f%% of detector time)' % (name, top[3], 100 * top[0] / tot_ms),
+        'achieved': achieved_tf, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['bf16_tflops_sustained'],
+        'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)', 'traffic': None,
+        'hbm_achieved_gbs': top[2] / (top[0] * 1e-3) / 1e9, 'hbm_frac': top[2] / (top[0] * 1e-3) / 1e9 / pk['hbm_gbs'],
+        'all_convs': {'achieved_tflops': conv_fl / (conv_ms * 1e-3) / 1e12, 'frac': conv_fl / (conv_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                      'share_of_detector_time': conv_ms / tot_ms},
+        'whole_step_tflops': WASB_GFLOP_PER_STACK * BATCH * args.steps / (ms_dev * 1e-3) / 1e3,
+    }
+
+    # ---- CPU baseline: the oracle port of the reference path on the host cores, bounded sample ---
+    cpu = None
+    if not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        n_cpu = 3
+        cpu_reference_step(wasb_sd, frames_np, 1)
+        sec = cpu_reference_step(wasb_sd, frames_np, n_cpu)
+        cpu = {'value': n_cpu / sec, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '%d stacks (after 1 warm-up) through oracle/: numpy fixed-point resize, CPU torch fp32 WASB, SciPy L-BFGS-B decode, B=1 per forward' % n_cpu}
+
+    line = {
+        'metric': 'frames_per_sec_detect_decode', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': args.dtype, 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: WASB ball-detect (1280x704, 344 GFLOP/stack) + heatmap decode on synthetic 1920x1080 3-frame stacks, batch %d per GPU' % BATCH,
+                   'parallelism': 'clip-sharded x%d, NCCL all_gather of (x,y,v) records' % world, 'l2': 'inputs (211 MB of frames) and activations exceed the 126 MB L2',
+                   'weights': 'random-init (seeded), BN folded'},
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(frames_pinned.numel()), 'd2h_bytes_per_step': BATCH * 3 * 8,
+                'ms_per_step': ms_e2e / args.steps, 'api': "hubconf.ball_detection('wasb').predict(triples, return_heatmaps=False)"},
+        'gpu_launches': launches * args.steps,
+        'clocks': clocks,
+        'roofline': roofline,
+        'cpu_baseline': cpu,
+        'uplift': {'value': up_value, 'unit': 'trajectories/s', 'dtype': 'f32', 'batch_per_gpu': UPLIFT_BATCH, 'ms_per_step': ms_up / args.steps,
+                   'e2e': {'value': up_e2e, 'unit': 'trajectories/s', 'h2d_bytes_per_step': int(sum(a.numel() * 4 for a in (ub, ut, um, uti))),
+                           'd2h_bytes_per_step': UPLIFT_BATCH * (3 + 150) * 4},
+                   'tflops': UPLIFT_GFLOP_PER_TRAJ * up_value / 1e3, 'gpu_launches': up.engine.last_launches() + 1},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

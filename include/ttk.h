@@ -83,6 +83,17 @@ TTK_API int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int he
                       float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* kernels launched by the last ttk_hrnet_forward on this handle (for bench accounting) */
 TTK_API int ttk_hrnet_last_launches(const ttk_hrnet* h);
+/* Images processed per pass through the layer plan (default 1: a thin layer's input and output then
+ * both fit the 126 MB L2).  Bounds the activation workspace. */
+TTK_API int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images);
+/* Measurement aid (bench.py): when enabled, ttk_hrnet_forward brackets every kernel launch with CUDA
+ * events on `stream`.  After the caller synchronised the stream, ttk_hrnet_profile_read returns, per
+ * launch: op type (0 conv, 1 fuse-sum, 2 final conv), conv index (-1 if none), duration in ms,
+ * algorithmic flops (2*MAC on the reference's logical channel counts) and compulsory bytes
+ * (inputs + outputs + weights once). */
+TTK_API int ttk_hrnet_set_profile(ttk_hrnet* h, int enable);
+TTK_API int ttk_hrnet_profile_count(const ttk_hrnet* h);
+TTK_API int ttk_hrnet_profile_read(ttk_hrnet* h, int i, int* op_type, int* conv_index, float* ms, double* flops, double* bytes);
 
 /* ---------------------------------------------------------------------------------------
  * Heatmap decode: first-max argmax + 3x3 zero-padded window + bounded Gaussian fit +

@@ -1,0 +1,102 @@
+"""The hub-facing classes (drop-in boundary) against the outputs of the reference's
+own interface.py recorded in tests/golden/interface.npz.  Needs a B200: run with `-m gpu`."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def weights(tmp_path_factory):
+    """A synthetic weights tree in the reference's checkpoint format (oracle weights, seeds 31/32/33)."""
+    from oracle.gen_golden import write_checkpoints
+    hub = tmp_path_factory.mktemp('torchhome')
+    torch.hub.set_dir(str(hub))
+    w = os.path.join(str(hub), 'checkpoints', 'tt_uplifting_extracted', 'weights')
+    write_checkpoints(w)
+    return w
+
+
+def test_ball_detector_predict(weights, golden):
+    from upliftingtabletennis_b200.interface import BallDetector
+    g = golden('interface')
+    frames = list(g['frames'])
+    bd = BallDetector('wasb')
+    assert isinstance(bd.model, torch.nn.Module) and not bd.model.training and bd.resolution == (1920, 1080)
+    triples = [(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 5)]
+    pos, hm = bd.predict(triples)
+    assert pos.shape == (4, 3) and pos.dtype == np.float64 and hm.shape == (4, 1, 88, 160) and hm.dtype == np.float32
+    np.testing.assert_allclose(hm, g['ball_hm'], rtol=0, atol=1e-4 * np.abs(g['ball_hm']).max() + 1e-5)
+    assert np.all(pos[:, 2] == 1.0)
+    np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=0.05)
+    # independent (copied) triples take the stride-3 path and give the same answer
+    pos2, _ = bd.predict([tuple(f.copy() for f in t) for t in triples], return_heatmaps=False)
+    assert np.array_equal(pos, pos2)
+    # the transform seam works on the reference's dicts (HWC float64 out)
+    out = bd.transform({'image': frames[1], 'prev_image': frames[0], 'next_image': frames[2]})
+    assert out['image'].shape == (88, 160, 3) and out['image'].dtype == np.float64
+    p1 = np.array([[10.0, 10, 1], [50, 50, 1], [90, 90, 1]])
+    p2 = np.array([[12.0, 11, 1], [90, 50, 1], [90, 91, 0]])
+    f, idx, t = bd.filter_trajectory(p1, p2, 50)
+    assert np.array_equal(idx, [0]) and np.allclose(f, [[10, 10]]) and np.allclose(t, [0.0])
+
+
+def test_table_detector_predict(weights, golden):
+    from upliftingtabletennis_b200.interface import TableDetector
+    g = golden('interface')
+    frames = list(g['frames'])
+    td = TableDetector('hrnet')
+    pos, hm = td.predict(frames[:2])
+    assert pos.shape == (2, 13, 3) and hm.shape == (2, 1, 13, 88, 160)
+    np.testing.assert_allclose(hm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
+    err = np.abs(pos[..., :2] - g['table_pos'][..., :2]).max(axis=-1)
+    assert np.mean(err < 0.05) >= 0.9, err
+    with pytest.raises(NotImplementedError):
+        td.calibrate_camera(pos[0])
+
+
+def test_uplifting_model_predict(weights, golden):
+    from upliftingtabletennis_b200.interface import UpliftingModel
+    g = golden('interface')
+    um = UpliftingModel()
+    spin, pos3d = um.predict_without_normalization(*(torch.from_numpy(g['up_' + k]) for k in ('ball', 'table', 'mask', 'times')))
+    assert isinstance(spin, torch.Tensor) and spin.shape == (3,) and spin.is_cuda
+    assert isinstance(pos3d, np.ndarray) and pos3d.dtype == np.float32 and pos3d.shape == g['pos3d'].shape
+    np.testing.assert_allclose(pos3d, g['pos3d'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(spin.cpu().numpy(), g['spin'], rtol=1e-3, atol=1e-3)
+    with pytest.raises(ValueError):
+        um.predict_without_normalization(torch.zeros(1, 50, 2), torch.ones(1, 13, 3), torch.ones(1, 50), torch.zeros(1, 50))
+
+
+def test_full_pipeline_runs(weights, golden):
+    """TableTennisPipeline.predict end to end on a short synthetic clip, compared with the oracle chained by hand."""
+    from oracle import decode as odec, hrnet as ohr, preprocess as opre, tails as otl, uplift as oup
+    from upliftingtabletennis_b200.interface import TableTennisPipeline, filter_trajectory_table
+    g = golden('interface')
+    frames = list(g['frames'])
+    pipe = TableTennisPipeline()
+    spin, pos3d = pipe.predict(frames, 50.0)
+    # oracle chain
+    sd_b, sd_t, sd_u = ohr.random_state_dict(9, 3, seed=31), ohr.random_state_dict(3, 13, seed=32), oup.random_state_dict(33)
+    stacks = np.stack([opre.preprocess_stack(frames[i - 1:i + 2], 160, 88) for i in range(1, len(frames) - 1)])
+    bpos, _, _ = odec.decode_heatmaps(ohr.wasb_forward(sd_b, torch.from_numpy(stacks)).numpy()[:, 0], 1920, 1080, odec.TABLE)
+    fpos, _, ftimes = otl.filter_trajectory_ball(bpos, bpos, 50.0)
+    tst = np.stack([opre.preprocess_stack([f], 160, 88) for f in frames])
+    thm = ohr.hrnet_forward(sd_t, torch.from_numpy(tst)).numpy()
+    tpos, _, _ = odec.decode_heatmaps(thm.reshape(-1, 88, 160), 1920, 1080, odec.TABLE)
+    tpos = tpos.reshape(len(frames), 13, 3)
+    table = filter_trajectory_table(tpos, tpos)
+    b, t, ti, m = otl.uplifting_transform(fpos, table, ftimes)
+    rot, pos = oup.uplift_forward(sd_u, *(torch.from_numpy(a) for a in (b, t, m, ti)))
+    n = int(m.sum())
+    assert pos3d.shape == (n, 3)
+    np.testing.assert_allclose(pos3d, pos.numpy()[0, :n], rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(spin.cpu().numpy(), otl.transform_rotationaxes(rot.numpy(), pos.numpy())[0], rtol=2e-2, atol=2e-2)
+    # reprojection helper
+    Mext = np.eye(4)
+    Mext[2, 3] = 5.0
+    Mint = np.array([[2000.0, 0, 960, 0], [0, 2000.0, 540, 0], [0, 0, 1, 0]])
+    np.testing.assert_allclose(pipe.reproject(pos3d, Mint, Mext), otl.reproject(pos3d, Mint, Mext), rtol=1e-12)

@@ -36,6 +36,10 @@ def _load():
         'ttk_hrnet_workspace_bytes': (sz, [vp, i32, i32, i32, i32]),
         'ttk_hrnet_forward': (i32, [vp, vp, i32, i32, i32, i32, vp, vp, sz, vp]),
         'ttk_hrnet_last_launches': (i32, [vp]),
+        'ttk_hrnet_set_subbatch': (i32, [vp, i32]),
+        'ttk_hrnet_set_profile': (i32, [vp, i32]),
+        'ttk_hrnet_profile_count': (i32, [vp]),
+        'ttk_hrnet_profile_read': (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         'ttk_decode_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_heatmap_decode': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
         'ttk_trajectory_pack': (i32, [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),

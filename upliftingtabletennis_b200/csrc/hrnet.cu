@@ -467,9 +467,47 @@ __global__ void __launch_bounds__(256) final_kernel(const T* __restrict__ in, fl
   }
 }
 
+// Record an event before launch #recs.size() and describe the launch (algorithmic flops, compulsory bytes).
+int profile_mark(ttk_hrnet* h, int oi, int bs, int H, int W, size_t elem, cudaStream_t st) {
+  const size_t i = h->recs.size();
+  while (h->events.size() <= i + 1) {
+    cudaEvent_t e;
+    TTK_CUDA(cudaEventCreate(&e));
+    h->events.push_back(e);
+  }
+  TTK_CUDA(cudaEventRecord(h->events[i], st));
+  const TtkOp& op = h->ops[oi];
+  ttk_hrnet::Rec r;
+  r.op = oi;
+  r.n = bs;
+  auto numel = [&](int t) { const TtkTensor& tt = h->tensors[t]; return (double)bs * (H >> tt.shift) * (W >> tt.shift) * tt.c; };
+  if (op.type == OP_CONV) {
+    const TtkConv& c = h->convs[op.conv];
+    const TtkTensor& to = h->tensors[op.out];
+    const double opix = (double)bs * (H >> to.shift) * (W >> to.shift);
+    r.flops = 2.0 * opix * c.cin * c.cout * c.k * c.k;
+    r.bytes = (numel(op.in) + numel(op.out)) * elem + (double)c.cin_p * c.cout_p * c.k * c.k * elem;
+    for (int k = 0; k < op.nres; ++k) r.bytes += numel(op.res[k]) * elem;
+  } else if (op.type == OP_SUM) {
+    r.flops = numel(op.out) * op.nres;
+    r.bytes = (numel(op.in) + numel(op.out)) * elem;
+    for (int k = 0; k < op.nres; ++k) r.bytes += numel(op.res[k]) * elem;
+  } else {
+    r.flops = 2.0 * bs * H * W * 16 * h->out_count;
+    r.bytes = numel(op.in) * elem + (double)bs * H * W * h->out_count * 4;
+  }
+  h->recs.push_back(r);
+  return TTK_OK;
+}
+
 template <typename T>
 int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, char* ws, bool umma, cudaStream_t st) {
-  for (const TtkOp& op : h->ops) {
+  for (size_t oi = 0; oi < h->ops.size(); ++oi) {
+    const TtkOp& op = h->ops[oi];
+    if (h->profile) {
+      int rc = profile_mark(h, (int)oi, bs, H, W, sizeof(T), st);
+      if (rc) return rc;
+    }
     auto ptr = [&](int t) -> void* {
       if (t == h->input_tensor) return const_cast<void*>(x);
       return ws + h->tensors[t].offset;
@@ -526,6 +564,8 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
   return TTK_OK;
 }
 
+}  // namespace
+namespace {
 int upload(float** dst, const std::vector<float>& src) {
   if (!*dst) TTK_CUDA(cudaMalloc((void**)dst, src.size() * sizeof(float)));
   TTK_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -563,6 +603,7 @@ extern "C" int ttk_hrnet_create(int in_ch, int out_ch, int out_first, int out_co
 
 extern "C" void ttk_hrnet_destroy(ttk_hrnet* h) {
   if (!h) return;
+  for (cudaEvent_t e : h->events) cudaEventDestroy(e);
   for (TtkConv& c : h->convs) {
     cudaFree(c.w_f32);
     cudaFree(c.w_bfr);
@@ -648,6 +689,7 @@ extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int
       return TTK_ERR_STATE;
     }
   h->launches = 0;
+  h->recs.clear();
   if (batch == 0) return TTK_OK;
   TTK_CHECK_ARG(x_dev && heatmaps_dev && workspace_dev, "ttk_hrnet_forward: null pointer");
   const size_t elem = dtype == TTK_BF16 ? 2 : 4;
@@ -666,6 +708,35 @@ extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int
       rc = run_plan<__nv_bfloat16>(h, x, nb, height, width, heat, (char*)workspace_dev, !h->force_simt, st);
     if (rc != TTK_OK) return rc;
   }
+  if (h->profile && !h->recs.empty()) TTK_CUDA(cudaEventRecord(h->events[h->recs.size()], st));
+  return TTK_OK;
+}
+
+extern "C" int ttk_hrnet_set_profile(ttk_hrnet* h, int enable) {
+  TTK_CHECK_ARG(h, "ttk_hrnet_set_profile: null handle");
+  h->profile = enable ? 1 : 0;
+  h->recs.clear();
+  return TTK_OK;
+}
+
+extern "C" int ttk_hrnet_profile_count(const ttk_hrnet* h) { return h ? (int)h->recs.size() : 0; }
+
+extern "C" int ttk_hrnet_profile_read(ttk_hrnet* h, int i, int* op_type, int* conv_index, float* ms, double* flops, double* bytes) {
+  TTK_CHECK_ARG(h && i >= 0 && i < (int)h->recs.size(), "ttk_hrnet_profile_read: bad index %d", i);
+  const ttk_hrnet::Rec& r = h->recs[i];
+  float t = 0.f;
+  TTK_CUDA(cudaEventElapsedTime(&t, h->events[i], h->events[i + 1]));   // caller synchronised the stream
+  if (op_type) *op_type = h->ops[r.op].type;
+  if (conv_index) *conv_index = h->ops[r.op].conv;
+  if (ms) *ms = t;
+  if (flops) *flops = r.flops;
+  if (bytes) *bytes = r.bytes;
+  return TTK_OK;
+}
+
+extern "C" int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images) {
+  TTK_CHECK_ARG(h && images >= 1, "ttk_hrnet_set_subbatch: need images >= 1");
+  h->subbatch = images;
   return TTK_OK;
 }
 

@@ -57,6 +57,11 @@ struct ttk_hrnet {
   // final 1x1 conv weights: [out_count][16] + bias[out_count], float32 device
   float* final_w = nullptr;
   float* final_b = nullptr;
+  // optional per-launch timing (ttk_hrnet_set_profile): events bracket every launch on the caller's stream
+  int profile = 0;
+  std::vector<cudaEvent_t> events;     // pool, events[i] precedes launch i
+  struct Rec { int op; int n; double flops, bytes; };
+  std::vector<Rec> recs;
 };
 
 // conv_umma.cu: bf16 implicit-GEMM convolution on tcgen05/TMEM fed by TMA.

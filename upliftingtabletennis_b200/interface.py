@@ -1,0 +1,378 @@
+"""Drop-in for the reference's ``interface.py`` (BallDetector, TableDetector, UpliftingModel,
+TableTennisPipeline; reference ``interface.py:83-312``) with the hot path on libttk.
+
+Same names, arguments, return types and error behaviour as the reference.  Differences are internal:
+frames are uploaded once and processed as a batch on the GPU (the reference loops B=1 with a host
+round-trip per frame), and the segformer++ detectors, whose architecture is not part of the reference
+repository (fetched from another hub repo at construction time, ``balldetection/models/segformer_pp.py:12-19``),
+are substituted by the in-repo WASB / HRNet architectures unless their weights are unavailable.
+"""
+import os
+import zipfile
+
+import numpy as np
+import torch
+
+from . import ops
+from .detector import MyHRNet, WASBNet
+from .uplift import get_model as get_uplifting_model
+
+HEIGHT, WIDTH = 1080, 1920          # inference/utils.py:22
+BALL_VISIBLE = 1
+KEYPOINT_VISIBLE, KEYPOINT_INVISIBLE = 1, 0
+SEQ_LEN = 50                        # inference/utils.py:293
+
+WEIGHTS_ZIP_URL = "https://mediastore.rz.uni-augsburg.de/get/TL7oQRStHG/"     # interface.py:29
+ZIP_FILENAME = "tt_uplifting_weights.zip"
+EXTRACTED_FOLDER_NAME = "weights"
+
+
+def _get_weights_path(relative_path):
+    """interface.py:34-73: locate (download + extract if needed) a file of the released weights tree."""
+    hub_dir = torch.hub.get_dir()
+    download_dir = os.path.join(hub_dir, "checkpoints")
+    os.makedirs(download_dir, exist_ok=True)
+    zip_path = os.path.join(download_dir, ZIP_FILENAME)
+    extract_path = os.path.join(download_dir, "tt_uplifting_extracted")
+    target_file = os.path.join(extract_path, EXTRACTED_FOLDER_NAME, relative_path)
+    if os.path.exists(target_file):
+        return target_file
+    print(f"Weights not found at {target_file}.")
+    if not os.path.exists(zip_path):
+        print(f"Downloading weights from {WEIGHTS_ZIP_URL}...")
+        try:
+            torch.hub.download_url_to_file(WEIGHTS_ZIP_URL, zip_path, progress=True)
+        except Exception as e:
+            raise RuntimeError(f"Failed to download weights: {e}")
+    if not os.path.exists(extract_path) or not os.path.exists(target_file):
+        print("Extracting weights... this may take a moment.")
+        try:
+            with zipfile.ZipFile(zip_path, 'r') as zip_ref:
+                zip_ref.extractall(extract_path)
+            print("Extraction complete.")
+        except Exception as e:
+            raise RuntimeError(f"Failed to extract weights: {e}")
+    return target_file
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError('upliftingtabletennis_b200 needs a B200 (sm_100) GPU; there is no CPU fallback')
+    return torch.device('cuda')
+
+
+# ---- loaders (inference/inference_balldetection.py:40-61, inference_tabledetection.py:40-57, inference_uplifting.py:33-58) ----
+class _DetectorTransform:
+    """Stand-in for the reference's Compose([Resize, NormalizeImage]) (balldetection/transforms.py:504-508).
+    Callable on the same dicts; the work happens in the fused CUDA pre-processing kernel."""
+
+    def __init__(self, resolution):
+        self.resolution = tuple(resolution)
+
+    def __call__(self, data):
+        dev = _device()
+        out = dict(data)
+        for k in ('image', 'prev_image', 'next_image'):
+            if k in data and data[k] is not None:
+                f = torch.from_numpy(np.ascontiguousarray(data[k])).to(dev)[None]
+                x = ops.preprocess_stacks(f, 1, 1, 1, self.resolution[0], self.resolution[1], layout='nchw')
+                out[k] = x[0].permute(1, 2, 0).double().cpu().numpy()       # HWC float64 like the reference
+        return out
+
+
+def _unsupported(model_name):
+    return NotImplementedError(
+        f"model '{model_name}': its architecture is not part of the reference repository (segformer++ is fetched from "
+        "KieDani/SegformerPlusPlus at construction time) or has no B200 kernels yet (vitpose); available: 'wasb' / 'hrnet'")
+
+
+def load_ball_model(model_path):
+    load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
+    info = load_dict['additional_info']
+    model_name, resolution, in_frames = info['model_name'], info['image_resolution'], info['in_frames']
+    if model_name != 'wasb':
+        raise _unsupported(model_name)
+    model = WASBNet(in_frames=in_frames, resolution=resolution, pretraining=False)
+    model.load_state_dict(load_dict['model_state_dict'])
+    model.eval()
+    print(f'Loaded BallDetection model: {model_name} with resolution {resolution}')
+    print(f" - in_frames: {in_frames}, lr: {info.get('lr')}")
+    return model, _DetectorTransform(resolution)
+
+
+def load_table_model(model_path):
+    load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
+    info = load_dict['additional_info']
+    model_name, resolution = info['model_name'], info['image_resolution']
+    if model_name != 'hrnet':
+        raise _unsupported(model_name)
+    model = MyHRNet(resolution=resolution, pretraining=False)
+    model.load_state_dict(load_dict['model_state_dict'])
+    model.eval()
+    print(f'Loaded tabledetection model: {model_name} with resolution {resolution}')
+    return model, _DetectorTransform(resolution)
+
+
+class NormalizeImgCoords:
+    """uplifting/transformations.py:252-266 (divides by 2560 x 1440, uplifting/helper.py:26)."""
+
+    def __call__(self, data):
+        r_img, table_img = data['r_img'], data['table_img']
+        r_img = r_img / np.array([2560, 1440])
+        table_img[..., :2] = table_img[..., :2] / np.array([2560, 1440])
+        data['r_img'], data['table_img'] = r_img, table_img
+        return data
+
+
+def load_uplifting_model(model_path):
+    d = torch.load(model_path, weights_only=False, map_location=torch.device('cpu'))
+    info = d['additional_info']
+    model = get_uplifting_model(info['name'], size=info['size'], mode=info['tabletoken_mode'], time_rotation=info['time_rotation'])
+    model.load_state_dict(d['model_state_dict'])
+    model.eval()
+    print(f"Loaded Uplifting model: {info['name']} with size {info['size']}, tabletoken_mode: {info['tabletoken_mode']}, "
+          f"time_rotation: {info['time_rotation']}, transform_mode: {info['transform_mode']}")
+    return model, NormalizeImgCoords(), info['transform_mode']
+
+
+# ---- glue (inference/utils.py) ------------------------------------------------------------------
+def filter_trajectory_ball(pred_positions1, pred_positions2, fps):
+    """inference/utils.py:70-102: keep frames where both detectors see the ball and agree within 20 px."""
+    fps = float(fps)
+    diff = np.linalg.norm(pred_positions1[:, :2] - pred_positions2[:, :2], axis=1)
+    keep = ~((diff > 20) | (pred_positions1[:, 2] != BALL_VISIBLE) | (pred_positions2[:, 2] != BALL_VISIBLE))
+    idx = np.nonzero(keep)[0]
+    valid = np.array([pred_positions1[t] for t in idx])[:, :2]      # IndexError on an empty trajectory, like the reference (:98)
+    return valid, idx, np.array([float(t / fps) for t in idx])
+
+
+def _filter_keypoints_with_dbscan(detections, eps=10, min_samples=5):
+    """inference/utils.py:172-232: centroid of the largest DBSCAN cluster (scikit-learn, as in the reference)."""
+    from collections import Counter
+    from sklearn.cluster import DBSCAN
+    detections = np.asarray(detections)
+    if detections.shape[0] < min_samples:
+        return np.mean(detections, axis=0) if detections.shape[0] > 0 else None
+    labels = DBSCAN(eps=eps, min_samples=min_samples).fit(detections).labels_
+    valid = [l for l in labels if l != -1]
+    if not valid:
+        return np.mean(detections, axis=0)
+    best = Counter(valid).most_common(1)[0][0]
+    return np.mean(detections[labels == best], axis=0)
+
+
+def filter_trajectory_table(pred_positions1, pred_positions2):
+    """inference/utils.py:137-169: two-model agreement (< 10 px) then DBSCAN(eps=10, min_samples=3) per keypoint."""
+    T = pred_positions1.shape[0]
+    out = []
+    for n in range(pred_positions1.shape[1]):
+        xs, ys = [], []
+        for t in range(T):
+            if pred_positions1[t, n, 2] == KEYPOINT_VISIBLE and pred_positions2[t, n, 2] == KEYPOINT_VISIBLE:
+                d = np.linalg.norm([pred_positions1[t, n, 0] - pred_positions2[t, n, 0], pred_positions1[t, n, 1] - pred_positions2[t, n, 1]])
+                if d < 10:
+                    xs.append(pred_positions1[t, n, 0])
+                    ys.append(pred_positions1[t, n, 1])
+        if len(xs) < 3:
+            out.append([-1, -1, KEYPOINT_INVISIBLE])
+        else:
+            p = _filter_keypoints_with_dbscan(np.stack([xs, ys], axis=1), eps=10, min_samples=3)
+            out.append([p[0], p[1], KEYPOINT_VISIBLE] if p is not None else [-1, -1, KEYPOINT_INVISIBLE])
+    return np.array(out)
+
+
+def _uplifting_transform(ball_coords, table_coords, times):
+    """inference/utils.py:268-309 on the GPU (ttk_trajectory_pack): returns CUDA float32 tensors
+    ball (1,50,2), table (1,13,3), times (1,50), mask (1,50)."""
+    dev = _device()
+    ball = torch.from_numpy(np.ascontiguousarray(ball_coords, dtype=np.float64)).to(dev)
+    tms = torch.from_numpy(np.ascontiguousarray(times, dtype=np.float64)).to(dev)
+    tab = torch.from_numpy(np.ascontiguousarray(table_coords, dtype=np.float64)).to(dev)[None]
+    offs = torch.tensor([0, ball.shape[0]], dtype=torch.int32, device=dev)
+    b, t, ti, m = ops.trajectory_pack(ball, tms, offs, tab, SEQ_LEN, WIDTH, HEIGHT)
+    return b, t, ti, m
+
+
+# ---- public classes ---------------------------------------------------------------------------------
+class _Detector:
+    frames_per_stack = 1
+    chunk = 32                     # stacks per network launch (bounds the activation workspace)
+
+    def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps):
+        """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None."""
+        w, h = self.model.resolution
+        dt = self.model.compute_dtype
+        pos, hms = [], []
+        for s0 in range(0, n_stacks, self.chunk):
+            ns = min(self.chunk, n_stacks - s0)
+            f0 = s0 * stack_stride
+            x = ops.preprocess_stacks(frames_u8[f0:f0 + (ns - 1) * stack_stride + self.frames_per_stack], self.frames_per_stack,
+                                      stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
+            hm = self.model.heatmaps_from_nhwc16(x)
+            # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian
+            pos.append(ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table'))
+            if return_heatmaps:
+                hms.append(hm)
+        return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
+
+    def _upload(self, images, dev):
+        """Upload each distinct frame once.  numpy frames are staged through a cached pinned buffer; torch CPU
+        tensors (e.g. already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA tensor and, per
+        input image, its row in it."""
+        slots, order, uniq = {}, [], []
+        for im in images:
+            k = id(im)
+            if k not in slots:
+                slots[k] = len(uniq)
+                uniq.append(im)
+            order.append(slots[k])
+        shape = (len(uniq),) + tuple(uniq[0].shape)
+        out = torch.empty(shape, dtype=torch.uint8, device=dev)
+        if all(isinstance(u, torch.Tensor) for u in uniq):
+            for i, u in enumerate(uniq):
+                out[i].copy_(u, non_blocking=True)
+            return out, order
+        stage = getattr(self, '_stage', None)
+        if stage is None or stage.shape[1:] != shape[1:] or stage.shape[0] < shape[0]:
+            stage = self._stage = torch.empty(shape, dtype=torch.uint8).pin_memory()
+        view = stage[:shape[0]].numpy()
+        for i, u in enumerate(uniq):
+            view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
+        out.copy_(stage[:shape[0]], non_blocking=True)
+        return out, order
+
+
+class BallDetector(_Detector):
+    """interface.py:83-134."""
+    frames_per_stack = 3
+
+    def __init__(self, model_name='segformerpp_b2'):
+        self.device = _device()
+        self.resolution = (WIDTH, HEIGHT)
+        self.model, self.transform = load_ball_model(model_path=_get_weights_path(f"inference_balldetection/{model_name}/model.pt"))
+        self.model.to(self.device)
+        self.model.eval()
+
+    def predict(self, images, return_heatmaps=True):
+        """images: list (length B) of (prev, curr, next) HWC uint8 BGR frames.
+        Returns pred_pos (B, 3) float64 [x, y, 1.0] and the heatmaps (B, 1, h, w) float32 (None if return_heatmaps=False)."""
+        flat = [im for triple in images for im in (triple[0], triple[1], triple[2])]
+        frames, order = self._upload(flat, self.device)
+        consecutive = all(order[3 * i + j] == i + j for i in range(len(images)) for j in range(3))
+        if consecutive:                 # a sliding window over one clip (TableTennisPipeline.predict): every frame uploaded once
+            stride = 1
+        else:
+            frames = frames[torch.tensor(order, device=self.device)] if order != list(range(len(flat))) else frames
+            stride = 3
+        with torch.no_grad():
+            pos, hm = self._run(frames, stride, len(images), return_heatmaps)
+        pos = pos[:, 0].cpu().numpy()
+        return pos, (hm.cpu().numpy() if return_heatmaps else None)
+
+    def filter_trajectory(self, ball_positions, ball_positions_aux, fps):
+        return filter_trajectory_ball(ball_positions, ball_positions_aux, fps)
+
+
+class TableDetector(_Detector):
+    """interface.py:137-186."""
+    frames_per_stack = 1
+
+    def __init__(self, model_name='segformerpp_b2'):
+        self.device = _device()
+        self.resolution = (WIDTH, HEIGHT)
+        self.KEYPOINT_VISIBLE = KEYPOINT_VISIBLE
+        self.model, self.transform = load_table_model(model_path=_get_weights_path(f"inference_tabledetection/{model_name}/model.pt"))
+        self.model.to(self.device)
+        self.model.eval()
+
+    def predict(self, images, return_heatmaps=True):
+        """images: list of HWC uint8 BGR frames -> pred_pos (B, 13, 3) float64, heatmaps (B, 1, 13, h, w)."""
+        frames, order = self._upload(list(images), self.device)
+        if order != list(range(len(images))):
+            frames = frames[torch.tensor(order, device=self.device)]
+        with torch.no_grad():
+            pos, hm = self._run(frames, 1, len(images), return_heatmaps)
+        return pos.cpu().numpy(), (hm[:, None].cpu().numpy() if return_heatmaps else None)
+
+    def calibrate_camera(self, keypoints):
+        return calibrate_camera(keypoints)
+
+    def filter_trajectory(self, table_keypoints, table_keypoints_aux):
+        return filter_trajectory_table(table_keypoints, table_keypoints_aux)
+
+
+def calibrate_camera(table_coords):
+    """inference/utils.py:312-329 (DLT + RANSAC-BFGS, dataprocessing/regress_cameramatrices.py): SURVEY.md section 8f row 3,
+    not on the predict path -- not built yet."""
+    raise NotImplementedError('camera calibration (SURVEY.md section 8f, row 3) is not part of this build yet')
+
+
+class UpliftingModel:
+    """interface.py:189-247."""
+
+    def __init__(self):
+        self.device = _device()
+        self.model, self.transform, self.transform_mode = load_uplifting_model(model_path=_get_weights_path("inference_uplifting/ours/model.pt"))
+        self.model.to(self.device)
+        self.model.eval()
+
+    def predict(self, ball_coords, table_coords, times):
+        data = self.transform({'r_img': ball_coords, 'table_img': table_coords})
+        ball_coords, table_coords = data['r_img'], data['table_img']
+        mask = np.zeros((ball_coords.shape[0] + 1,), dtype=np.float32)
+        mask[:-1] = 1.0
+        return self.predict_without_normalization(ball_coords, table_coords, torch.tensor(mask).to(self.device), times)
+
+    def predict_without_normalization(self, ball_coords, table_coords, mask, times):
+        ball_coords, table_coords, mask, times = (a.to(self.device) for a in (ball_coords, table_coords, mask, times))
+        with torch.no_grad():
+            pred_rotation, pred_position = self.model(ball_coords, table_coords, mask, times)
+            if self.transform_mode == 'global':
+                pred_rotation_local = ops.rotation_local(pred_rotation, pred_position)
+            else:
+                pred_rotation_local = pred_rotation
+        T_prime = int(mask.sum().item())
+        pred_position = pred_position[:, :T_prime, :].cpu().numpy()
+        return pred_rotation_local.squeeze(0), pred_position.squeeze(0)
+
+
+class TableTennisPipeline:
+    """interface.py:251-312.  The reference hard-codes segformerpp_b2 for the main detectors; their architecture
+    is not in the reference repository, so the in-repo WASB / HRNet checkpoints serve as main *and* auxiliary
+    models unless overridden (substitution 4)."""
+
+    def __init__(self, ball_model='wasb', ball_model_aux='wasb', table_model='hrnet', table_model_aux='hrnet'):
+        self.device = _device()
+        self.ball_detector = BallDetector(model_name=ball_model)
+        self.ball_detector_aux = self.ball_detector if ball_model_aux == ball_model else BallDetector(model_name=ball_model_aux)
+        self.table_detector = TableDetector(model_name=table_model)
+        self.table_detector_aux = self.table_detector if table_model_aux == table_model else TableDetector(model_name=table_model_aux)
+        self.uplifting_model = UpliftingModel()
+        self.KEYPOINT_VISIBLE = self.table_detector.KEYPOINT_VISIBLE
+
+    def predict(self, images, fps):
+        image_triples = [(images[i - 1], images[i], images[i + 1]) for i in range(1, len(images) - 1)]
+        ball_positions, _ = self.ball_detector.predict(image_triples, return_heatmaps=False)
+        if self.ball_detector_aux is self.ball_detector:
+            ball_positions_aux = ball_positions
+        else:
+            ball_positions_aux, _ = self.ball_detector_aux.predict(image_triples, return_heatmaps=False)
+        filtered_ball_positions, valid_indices_ball, times_ball = self.ball_detector.filter_trajectory(ball_positions, ball_positions_aux, fps)
+        table_keypoints, _ = self.table_detector.predict(images, return_heatmaps=False)
+        if self.table_detector_aux is self.table_detector:
+            table_keypoints_aux = table_keypoints
+        else:
+            table_keypoints_aux, _ = self.table_detector_aux.predict(images, return_heatmaps=False)
+        filtered_table_keypoints = self.table_detector_aux.filter_trajectory(table_keypoints, table_keypoints_aux)
+        ball_coords, table_coords, times, mask = _uplifting_transform(filtered_ball_positions, filtered_table_keypoints, times_ball)
+        return self.uplifting_model.predict_without_normalization(ball_coords, table_coords, mask, times)
+
+    def calibrate_camera(self, keypoints):
+        return calibrate_camera(keypoints)
+
+    def reproject(self, positions_3d, Mint, Mext):
+        """interface.py:301-312: numpy in, numpy out (float64 like the reference's numpy path)."""
+        p = torch.from_numpy(np.asarray(positions_3d, dtype=np.float64)).to(self.device)
+        out = ops.project(p, torch.from_numpy(np.asarray(Mext, dtype=np.float64)).to(self.device),
+                          torch.from_numpy(np.asarray(Mint, dtype=np.float64)).to(self.device))
+        return out.cpu().numpy()

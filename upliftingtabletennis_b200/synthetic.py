@@ -1,0 +1,81 @@
+"""Synthetic weights and inputs for benchmarking (there is no network for checkpoints or datasets).
+Same distributions as the test oracle's generators, implemented independently of oracle/."""
+import math
+
+import numpy as np
+import torch
+
+
+def hrnet_state_dict(layout, seed):
+    """layout: [(key, shape)] from HRNetEngine.state_dict_layout()."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for key, shape in layout:
+        if key.endswith('num_batches_tracked'):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+            continue
+        if len(shape) == 4:
+            a = rng.standard_normal(shape) * np.sqrt(2.0 / (shape[0] * shape[2] * shape[3]))
+            if 'final_layers' in key:
+                a *= 0.01
+        elif key.endswith('running_var'):
+            a = rng.uniform(0.5, 1.5, shape)
+        elif key.endswith('running_mean') or key.endswith('.bias'):
+            a = rng.standard_normal(shape) * 0.1
+        else:
+            a = rng.uniform(0.5, 1.5, shape)
+        sd[key] = torch.from_numpy(a.astype(np.float32))
+    return sd
+
+
+def uplift_state_dict(module, seed):
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for key, t in module.state_dict().items():
+        shape = tuple(t.shape)
+        if key.endswith('inv_freq'):
+            a = (1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))).numpy()
+        elif key == 'cls_token':
+            a = rng.uniform(-0.2, 0.2, shape)
+        elif 'norm' in key and key.endswith('weight'):
+            a = rng.uniform(0.8, 1.2, shape)
+        elif 'norm' in key:
+            a = rng.standard_normal(shape) * 0.05
+        elif key.endswith('.bias'):
+            a = rng.standard_normal(shape) * 0.02
+        else:
+            lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+            a = rng.uniform(-lim, lim, shape)
+        sd[key] = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    return sd
+
+
+def frames_1080p(n, seed, h=1080, w=1920):
+    """n consecutive uint8 BGR noise frames with a moving bright blob."""
+    rng = np.random.default_rng(seed)
+    out = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    for i in range(n):
+        cx = int(w * (0.2 + 0.6 * i / max(n - 1, 1)))
+        cy = int(h * (0.4 + 0.2 * math.sin(i * 0.3)))
+        y0, y1, x0, x1 = max(cy - 12, 0), min(cy + 13, h), max(cx - 12, 0), min(cx + 13, w)
+        yy, xx = np.mgrid[y0:y1, x0:x1]
+        g = np.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * 3.0 ** 2))[..., None]
+        out[i, y0:y1, x0:x1] = np.clip(out[i, y0:y1, x0:x1] * (1 - g) + 255 * g, 0, 255).astype(np.uint8)
+    return out
+
+
+def trajectories(n, seed, T=50):
+    """n synthetic 2D trajectories in the uplifting model's input format (normalised coordinates), T' ~ U{10..49}."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(10, 50, n)
+    fps = rng.choice(np.array([25.0, 30.0, 50.0, 60.0, 120.0]), n)
+    idx = np.arange(T)[None, :]
+    mask = (idx < lens[:, None]).astype(np.float32)
+    times = (idx / fps[:, None]).astype(np.float32) * mask
+    tn = times / np.maximum(times.max(axis=1, keepdims=True), 1e-3)
+    ball = np.stack([0.2 + 0.5 * tn, 0.6 - 1.2 * times + 2.5 * times * times], axis=-1).astype(np.float32)
+    ball += rng.normal(0, 0.002, ball.shape).astype(np.float32)
+    ball *= mask[..., None]
+    table = np.concatenate([rng.uniform(0.2, 0.8, (n, 13, 1)), rng.uniform(0.4, 0.9, (n, 13, 1)),
+                            (rng.uniform(0, 1, (n, 13, 1)) > 0.15).astype(np.float64)], axis=-1).astype(np.float32)
+    return ball, table, mask, times

@@ -139,6 +139,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--dump-profile', default='', help='write the per-kernel table of one profiled step to this JSON file')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -266,6 +267,14 @@ def main():
         r[3] += 1
         tot_ms += ms.value
     check(lib.ttk_hrnet_set_profile(engine.h, 0))
+    if args.dump_profile:
+        rows = []
+        for (t_, c_), v in sorted(per.items(), key=lambda kv: -kv[1][0]):
+            nm = engine.specs[c_][0] if c_ >= 0 else ('fuse_sum' if t_ == 1 else 'final_conv')
+            spec = engine.specs[c_][2:] if c_ >= 0 else None
+            rows.append({'kernel': nm, 'spec_cin_cout_k_stride': spec, 'launches': v[3], 'ms': v[0], 'share': v[0] / tot_ms,
+                         'tflops': v[1] / (v[0] * 1e-3) / 1e12, 'gbs': v[2] / (v[0] * 1e-3) / 1e9})
+        json.dump({'total_ms': tot_ms, 'rows': rows}, open(args.dump_profile, 'w'), indent=1)
     (top_type, top_conv), top = max(per.items(), key=lambda kv: kv[1][0])
     name = engine.specs[top_conv][0] if top_conv >= 0 else ('fuse_sum' if top_type == 1 else 'final_conv')
     achieved_tf = top[1] / (top[0] * 1e-3) / 1e12

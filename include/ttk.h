@@ -91,6 +91,11 @@ TTK_API int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images);
  * launch: op type (0 conv, 1 fuse-sum, 2 final conv), conv index (-1 if none), duration in ms,
  * algorithmic flops (2*MAC on the reference's logical channel counts) and compulsory bytes
  * (inputs + outputs + weights once). */
+TTK_API int ttk_hrnet_set_force_simt(ttk_hrnet* h, int enable);   /* bf16 path through the SIMT kernels (cross-check of the tcgen05 path) */
+/* Test hook: run one convolution of the plan on caller buffers (NHWC, channels padded to 16): out = act(conv(in) + bias [+ res]).
+ * path 0: fp32 SIMT (float32 tensors), 1: bf16 SIMT, 2: bf16 tcgen05 (TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel). */
+TTK_API int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, const void* res_dev,
+                         int relu, int path, void* out_dev, void* stream);
 TTK_API int ttk_hrnet_set_profile(ttk_hrnet* h, int enable);
 TTK_API int ttk_hrnet_profile_count(const ttk_hrnet* h);
 TTK_API int ttk_hrnet_profile_read(ttk_hrnet* h, int i, int* op_type, int* conv_index, float* ms, double* flops, double* bytes);

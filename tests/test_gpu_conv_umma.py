@@ -1,0 +1,93 @@
+"""tcgen05 implicit-GEMM convolution against (a) the SIMT kernel on the same bf16 data and (b) a CPU torch fp32
+convolution of the bf16-rounded operands, for every convolution of the WASB / HRNet plans.  Needs a B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hrnet as ohr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def net():
+    assert torch.cuda.is_available()
+    from upliftingtabletennis_b200.detector import WASBNet
+    m = WASBNet().cuda().eval()
+    sd = ohr.random_state_dict(9, 3, seed=123)
+    m.load_state_dict(sd)
+    m._sync()
+    return m, sd
+
+
+def _run(engine, idx, x, res, relu, path, out_shape, dtype):
+    from upliftingtabletennis_b200._lib import lib, ptr, stream_ptr
+    out = torch.full(out_shape, float('nan'), dtype=dtype, device=x.device)
+    rc = lib.ttk_hrnet_debug_conv(engine.h, idx, ptr(x), x.shape[0], x.shape[1], x.shape[2], ptr(res), 1 if relu else 0, path,
+                                  ptr(out), stream_ptr())
+    torch.cuda.synchronize()
+    return rc, out
+
+
+@pytest.mark.parametrize('shape', [(2, 24, 200), (1, 9, 130), (1, 40, 72)])
+def test_every_conv_umma_vs_simt_and_cpu(net, shape):
+    m, sd = net
+    eng = m.engine
+    n, H, W = shape
+    rng = np.random.default_rng(H * W)
+    covered = 0
+    for idx, (name, bn, cin, cout, k, stride) in enumerate(eng.specs[:-1]):
+        cin_p, cout_p = (cin + 15) // 16 * 16, (cout + 15) // 16 * 16
+        x = torch.zeros((n, H, W, cin_p), dtype=torch.float32)
+        x[..., :cin] = torch.from_numpy(rng.standard_normal((n, H, W, cin)).astype(np.float32))
+        xb = x.to(torch.bfloat16).cuda()
+        Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+        res = torch.zeros((n, Ho, Wo, cout_p), dtype=torch.float32)
+        res[..., :cout] = torch.from_numpy(rng.standard_normal((n, Ho, Wo, cout)).astype(np.float32))
+        rb = res.to(torch.bfloat16).cuda()
+        rc2, y2 = _run(eng, idx, xb, rb, True, 2, (n, Ho, Wo, cout_p), torch.bfloat16)
+        if rc2 == -4:       # no tensor-core kernel for this shape (stride 2, 128->128): the executor falls back to SIMT
+            continue
+        assert rc2 == 0, name
+        covered += 1
+        rc1, y1 = _run(eng, idx, xb, rb, True, 1, (n, Ho, Wo, cout_p), torch.bfloat16)
+        assert rc1 == 0
+        y1f, y2f = y1.float().cpu(), y2.float().cpu()
+        assert torch.isfinite(y2f).all(), name
+        scale = float(y1f.abs().max()) + 1e-6
+        assert float((y1f - y2f).abs().max()) <= 1.6e-2 * scale, (name, float((y1f - y2f).abs().max()), scale)
+        # CPU fp32 conv of the bf16-rounded operands (BN folded), rounded to bf16 at the end like the kernel
+        spec = ohr.conv_specs(9, 3)[idx]
+        w, b = ohr.fold_bn(sd, spec)
+        wq = torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+        xin = xb.float().cpu()[..., :cin].permute(0, 3, 1, 2)
+        ref = F.conv2d(xin, wq, torch.from_numpy(b.astype(np.float32)), stride=stride, padding=k // 2)
+        ref = torch.relu(ref + rb.float().cpu()[..., :cout].permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        err = float((ref - y2f[..., :cout]).abs().max())
+        assert err <= 1.6e-2 * (float(ref.abs().max()) + 1e-6), (name, err)
+        assert float(y2f[..., cout:].abs().max() if cout_p > cout else 0.0) == 0.0
+    assert covered >= 40, covered     # the bulk of the 71 convs run on tensor cores
+
+
+def test_network_umma_vs_simt(net):
+    from upliftingtabletennis_b200._lib import lib
+    m, sd = net
+    rng = np.random.default_rng(1)
+    x = torch.from_numpy(rng.standard_normal((2, 9, 64, 160)).astype(np.float32)).cuda()
+    m.compute_dtype = torch.bfloat16
+    try:
+        lib.ttk_hrnet_set_force_simt(m.engine.h, 0)
+        y_tc, _ = m(x)
+        lib.ttk_hrnet_set_force_simt(m.engine.h, 1)
+        y_simt, _ = m(x)
+    finally:
+        lib.ttk_hrnet_set_force_simt(m.engine.h, 0)
+        m.compute_dtype = torch.float32
+    ref = ohr.wasb_forward(sd, x.cpu()).numpy()
+    r_tc = np.linalg.norm(y_tc.cpu().numpy() - ref) / np.linalg.norm(ref)
+    r_simt = np.linalg.norm(y_simt.cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert r_tc < 3e-2 and r_simt < 3e-2, (r_tc, r_simt)
+    assert np.linalg.norm((y_tc - y_simt).cpu().numpy()) / np.linalg.norm(ref) < 3e-2

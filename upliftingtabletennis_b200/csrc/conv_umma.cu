@@ -1,16 +1,398 @@
-// bf16 implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (placeholder until the kernel lands:
-// every shape reports "unsupported" and the executor runs the SIMT kernel on bf16 storage).
+// bf16 implicit-GEMM convolution (stride 1, 3x3 or 1x1) on the 5th-generation tensor cores:
+// tcgen05.mma with TMEM accumulators, operands staged by TMA, fused bias / residual / ReLU epilogue.
+// Reference ops: the Conv2d + BatchNorm2d(eval) + ReLU (+ residual / fuse sum) groups of
+// balldetection/models/wasb.py:35-105, :179-245, :383-416.
+//
+// Mapping (NHWC bf16 activations):
+//   M = 128 consecutive output pixels of one image row, N = Cout, K = taps x Cin.
+//   A CTA tile is R output rows x 128 pixels.  ONE TMA box brings the (R+2) x 130 pixel halo of a
+//   K-chunk (<= 64 channels = one swizzled row of 32/64/128 bytes per pixel) into shared memory;
+//   the 9 taps are NOT re-loaded: tap (ky,kx) of output row r is the same staged tile with the
+//   matrix descriptor's start address moved by ((r+ky)*130 + kx) pixel rows.  tools/umma_probe.cu
+//   established on a B200 that the 32/64/128-byte swizzles are applied to absolute shared-memory
+//   address bits, so row-shifted descriptors (base_offset 0) read exactly what TMA wrote.
+//   Image borders come for free from TMA's zero fill of out-of-bounds coordinates.
+// Roles (persistent CTA, static tile round-robin): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected thread), warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
+// Pipelines: smem full/empty ring over K-chunks, double-buffered TMEM accumulators (tmem full/empty).
+#include <cuda.h>
+
+#include <vector>
+
 #include "hrnet.h"
 
+namespace {
+
+constexpr int BW = 128;          // output pixels per tile row = MMA M
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO | SBO | version 1 | layout
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                                   // LBO (ignored for swizzled K-major layouts)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout & 7) << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
+template <int KS, int CIN, int COUT, int R, int STAGES>
+struct Cfg {
+  static constexpr int KC = CIN < 64 ? CIN : 64;        // channels per K-chunk = one swizzled smem row
+  static constexpr int NKC = CIN / KC;
+  static constexpr int ROWB = KC * 2;
+  static constexpr int HALO = KS == 3 ? 2 : 0;
+  static constexpr int PAD = KS / 2;
+  static constexpr int TW = BW + HALO;
+  static constexpr int TR = R + HALO;
+  static constexpr int CHUNK_BYTES = TR * TW * ROWB;
+  static constexpr int STAGE_BYTES = (CHUNK_BYTES + 1023) & ~1023;
+  static constexpr int TAPS = KS * KS;
+  static constexpr int W_BYTES = TAPS * NKC * COUT * ROWB;
+  static constexpr int W_BYTES_AL = (W_BYTES + 1023) & ~1023;
+  static constexpr int ACC_COLS = R * COUT;
+  static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + COUT * 4 + 256;
+  static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : ROWB == 64 ? 4u : 2u;     // SWIZZLE_32B / 64B / 128B
+  static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(COUT % 16 == 0 && COUT <= 256 && CIN % 16 == 0, "bad channel counts");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct KArgs {
+  const __nv_bfloat16* w;      // packed [tap][kchunk][cout][KC]
+  const float* bias;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* res[3];
+  int rsh[3];
+  int nres;
+  int n, h, w_img, cout_stride;
+  int relu;
+  int tiles_x, tiles_y, total;
+};
+
+template <int KS, int CIN, int COUT, int R, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs a) {
+  using C = Cfg<KS, CIN, COUT, R, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + C::W_BYTES_AL;
+  float* sBias = reinterpret_cast<float*>(sA + STAGES * C::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + COUT);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
+                 bar_tempty = bar_tfull + 16;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), bias, barriers, TMEM ----
+  {
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
+    const uint32_t wbase = smem_u32(sW);
+    constexpr int CPR = C::ROWB / 16;
+    for (int i = tid; i < C::W_BYTES / 16; i += THREADS) {
+      uint32_t addr = wbase + (i / CPR) * C::ROWB + (i % CPR) * 16;
+      addr ^= ((addr >> 7) & C::SWZ) << 4;
+      *reinterpret_cast<uint4*>(sW + (addr - wbase)) = __ldg(wsrc + i);
+    }
+    for (int i = tid; i < COUT; i += THREADS) sBias[i] = a.bias[i];
+  }
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_tfull + 8 * i, 1);
+      mbar_init(bar_tempty + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // weights: generic-proxy writes -> async proxy (tensor core)
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x) {
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
+        for (int kc = 0; kc < C::NKC; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_full + 8 * s, C::CHUNK_BYTES);
+          tma_load_4d(smem_u32(sA + s * C::STAGE_BYTES), &tmap, bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, COUT);
+      const uint32_t wbase = smem_u32(sW);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < C::NKC; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES);
+#pragma unroll 1
+          for (int r = 0; r < R; ++r) {
+            const uint32_t d_tmem = tmem + acc * C::ACC_COLS + r * COUT;
+#pragma unroll
+            for (int tap = 0; tap < C::TAPS; ++tap) {
+              const int ky = tap / KS, kx = tap % KS;
+              const uint32_t arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
+              const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
+#pragma unroll
+              for (int k16 = 0; k16 < C::KC / 16; ++k16) {
+                const uint64_t da = make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
+                const uint64_t db = make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
+                umma(d_tmem, da, db, idesc, (kc | tap | k16) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(bar_empty + 8 * s);          // smem stage reusable once these MMAs have read it
+        }
+        umma_commit(bar_tfull + 8 * acc);          // accumulators complete
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter (warp % 4) =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                   // pixel within the tile row = TMEM lane
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+      const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const int ox = tx * BW + m;
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        const int oy = ty * R + r;
+        const bool live = ox < a.w_img && oy < a.h;
+        const size_t pix = ((size_t)img * a.h + oy) * a.w_img + ox;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + r * COUT + c0;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (live) {
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
+            for (int rr = 0; rr < a.nres; ++rr) {
+              const int sh = a.rsh[rr];
+              const __nv_bfloat16* rp =
+                  a.res[rr] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_stride + c0;
+              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
+              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                f[2 * j] += __low2float(b2);
+                f[2 * j + 1] += __high2float(b2);
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              o[j] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.cout_stride + c0);
+            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)p;
+  }
+  return fn;
+}
+
+template <int KS, int CIN, int COUT, int R, int STAGES>
+int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
+  using C = Cfg<KS, CIN, COUT, R, STAGES>;
+  EncodeFn encode = get_encode();
+  if (!encode) {
+    ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return TTK_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, CIN, COUT, R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)a.win, (cuuint64_t)a.hin, (cuuint64_t)a.n};
+  cuuint64_t strides[3] = {(cuuint64_t)CIN * 2, (cuuint64_t)a.win * CIN * 2, (cuuint64_t)a.hin * a.win * CIN * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C::KC, (cuuint32_t)C::TW, (cuuint32_t)C::TR, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = C::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : C::ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ttk_set_error("cuTensorMapEncodeTiled failed (%d) for conv %s", (int)r, cv.name.c_str());
+    return TTK_ERR_CUDA;
+  }
+  KArgs k;
+  k.w = cv.w_umma;
+  k.bias = cv.bias;
+  k.out = (__nv_bfloat16*)a.out;
+  for (int i = 0; i < 3; ++i) {
+    k.res[i] = (const __nv_bfloat16*)a.res[i];
+    k.rsh[i] = a.res_shift[i];
+  }
+  k.nres = a.nres;
+  k.n = a.n;
+  k.h = a.hout;
+  k.w_img = a.wout;
+  k.cout_stride = a.cout;
+  k.relu = a.relu;
+  k.tiles_x = ttk_cdiv(a.wout, BW);
+  k.tiles_y = ttk_cdiv(a.hout, R);
+  k.total = k.tiles_x * k.tiles_y * a.n;
+  const int grid = std::min(k.total, ttk_num_sms());
+  conv_umma_kernel<KS, CIN, COUT, R, STAGES><<<grid, THREADS, C::SMEM_BYTES, st>>>(map, k);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}
+
+}  // namespace
+
+// Weights for the tensor-core path: bf16, [tap][k-chunk][cout_p][KC] (K-major rows of one chunk), zero padded.
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
-  (void)cv;
-  (void)w_host;
+  const int kk = cv.k * cv.k;
+  const int KC = cv.cin_p < 64 ? cv.cin_p : 64;
+  const int nkc = cv.cin_p / KC;
+  std::vector<__nv_bfloat16> w((size_t)kk * cv.cin_p * cv.cout_p, __float2bfloat16_rn(0.f));
+  for (int co = 0; co < cv.cout; ++co)
+    for (int ci = 0; ci < cv.cin; ++ci)
+      for (int t = 0; t < kk; ++t) {
+        const int kc = ci / KC, c = ci % KC;
+        w[(((size_t)t * nkc + kc) * cv.cout_p + co) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
+      }
+  if (!cv.w_umma) TTK_CUDA(cudaMalloc((void**)&cv.w_umma, w.size() * sizeof(__nv_bfloat16)));
+  TTK_CUDA(cudaMemcpy(cv.w_umma, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   return TTK_OK;
 }
 
 int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  (void)cv;
-  (void)a;
-  (void)st;
+  if (cv.stride != 1) return TTK_ERR_UNSUPPORTED;
+  const int ci = cv.cin_p, co = cv.cout_p;
+#define TTK_UMMA(KS_, CI_, CO_, R_, ST_) \
+  if (cv.k == KS_ && ci == CI_ && co == CO_) return launch<KS_, CI_, CO_, R_, ST_>(cv, a, st);
+  // 3x3
+  TTK_UMMA(3, 16, 64, 4, 3)     // stem conv1 (9 -> 64, input padded to 16 channels)
+  TTK_UMMA(3, 64, 64, 2, 2)     // stem conv2, quarter-resolution branch
+  TTK_UMMA(3, 32, 32, 4, 3)     // bottleneck conv2, half-resolution branch
+  TTK_UMMA(3, 16, 16, 8, 3)     // full-resolution branch
+  TTK_UMMA(3, 128, 16, 2, 2)    // transition1.0
+  // 1x1
+  TTK_UMMA(1, 64, 32, 4, 2)     // bottleneck conv1
+  TTK_UMMA(1, 32, 128, 2, 3)    // bottleneck conv3
+  TTK_UMMA(1, 64, 128, 2, 3)    // bottleneck projection shortcut
+  TTK_UMMA(1, 32, 16, 4, 3)     // fuse layers (low -> high resolution)
+  TTK_UMMA(1, 64, 16, 4, 3)
+  TTK_UMMA(1, 128, 16, 4, 2)
+  TTK_UMMA(1, 64, 32, 4, 2)
+  TTK_UMMA(1, 128, 32, 4, 2)
+  TTK_UMMA(1, 128, 64, 2, 2)
+#undef TTK_UMMA
   return TTK_ERR_UNSUPPORTED;
 }

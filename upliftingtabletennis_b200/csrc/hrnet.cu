@@ -740,4 +740,39 @@ extern "C" int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images) {
   return TTK_OK;
 }
 
+extern "C" int ttk_hrnet_set_force_simt(ttk_hrnet* h, int enable) {
+  TTK_CHECK_ARG(h, "ttk_hrnet_set_force_simt: null handle");
+  h->force_simt = enable ? 1 : 0;
+  return TTK_OK;
+}
+
+// Test hook: run ONE convolution of the plan (bias + optional same-shape residual + optional ReLU) on caller buffers.
+// path: 0 = fp32 SIMT (float tensors), 1 = bf16 SIMT, 2 = bf16 tcgen05 (returns TTK_ERR_UNSUPPORTED if the shape has no kernel).
+extern "C" int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, const void* res_dev,
+                                    int relu, int path, void* out_dev, void* stream) {
+  TTK_CHECK_ARG(h && conv_index >= 0 && conv_index < (int)h->convs.size() - 1, "ttk_hrnet_debug_conv: bad conv index %d", conv_index);
+  const TtkConv& cv = h->convs[conv_index];
+  TTK_CHECK_ARG(cv.set, "ttk_hrnet_debug_conv: weights not set");
+  ConvLaunch a;
+  a.in = in_dev;
+  a.out = out_dev;
+  a.nres = res_dev ? 1 : 0;
+  for (int r = 0; r < 3; ++r) {
+    a.res[r] = r == 0 ? res_dev : nullptr;
+    a.res_shift[r] = 0;
+  }
+  a.n = n;
+  a.hin = hin;
+  a.win = win;
+  a.hout = cv.stride == 2 ? (hin + 1) / 2 : hin;
+  a.wout = cv.stride == 2 ? (win + 1) / 2 : win;
+  a.cin = cv.cin_p;
+  a.cout = cv.cout_p;
+  a.relu = relu;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (path == 0) return launch_conv_simt<float>(cv, a, false, st);
+  if (path == 1) return launch_conv_simt<__nv_bfloat16>(cv, a, true, st);
+  return ttk_conv_umma_launch(cv, a, st);
+}
+
 extern "C" int ttk_hrnet_last_launches(const ttk_hrnet* h) { return h ? h->launches : 0; }

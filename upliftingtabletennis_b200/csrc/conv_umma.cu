@@ -1,22 +1,25 @@
-// bf16 implicit-GEMM convolution (stride 1, 3x3 or 1x1) on the 5th-generation tensor cores:
+// bf16 implicit-GEMM convolution (3x3 stride 1/2, 1x1) on the 5th-generation tensor cores:
 // tcgen05.mma with TMEM accumulators, operands staged by TMA, fused bias / residual / ReLU epilogue.
 // Reference ops: the Conv2d + BatchNorm2d(eval) + ReLU (+ residual / fuse sum) groups of
 // balldetection/models/wasb.py:35-105, :179-245, :383-416.
 //
 // Mapping (NHWC bf16 activations):
-//   M = 128 consecutive output pixels of one image row, N = Cout, K = taps x Cin.
+//   M = 128 consecutive output pixels of one image row, N = Cout (or a 64-wide slice of it), K = taps x Cin.
 //   A CTA tile is R output rows x 128 pixels.  ONE TMA box brings the (R+2) x 130 pixel halo of a
 //   K-chunk (<= 64 channels = one swizzled row of 32/64/128 bytes per pixel) into shared memory;
 //   the 9 taps are NOT re-loaded: tap (ky,kx) of output row r is the same staged tile with the
 //   matrix descriptor's start address moved by ((r+ky)*130 + kx) pixel rows.  tools/umma_probe.cu
 //   established on a B200 that the 32/64/128-byte swizzles are applied to absolute shared-memory
 //   address bits, so row-shifted descriptors (base_offset 0) read exactly what TMA wrote.
+//   Stride 2: the input is addressed as four parity sub-grids (even/odd rows x even/odd columns, one
+//   tensor map each, strides doubled); every tap then reads one sub-grid with unit pixel stride.
 //   Image borders come for free from TMA's zero fill of out-of-bounds coordinates.
 // Roles (persistent CTA, static tile round-robin): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected thread), warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
-// Pipelines: smem full/empty ring over K-chunks, double-buffered TMEM accumulators (tmem full/empty).
+// Pipelines: smem full/empty ring over load units, double-buffered TMEM accumulators (tmem full/empty).
 #include <cuda.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "hrnet.h"
@@ -80,48 +83,66 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
-template <int KS, int CIN, int COUT, int R, int STAGES>
+// KS: 1 or 3; S: stride 1 or 2 (3x3 only); CIN: padded input channels; COUT: output channels handled by one CTA
+// (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth.
+template <int KS, int S, int CIN, int COUT, int R, int STAGES>
 struct Cfg {
   static constexpr int KC = CIN < 64 ? CIN : 64;        // channels per K-chunk = one swizzled smem row
   static constexpr int NKC = CIN / KC;
   static constexpr int ROWB = KC * 2;
-  static constexpr int HALO = KS == 3 ? 2 : 0;
   static constexpr int PAD = KS / 2;
-  static constexpr int TW = BW + HALO;
-  static constexpr int TR = R + HALO;
-  static constexpr int CHUNK_BYTES = TR * TW * ROWB;
-  static constexpr int STAGE_BYTES = (CHUNK_BYTES + 1023) & ~1023;
+  static constexpr int NPY = S == 2 ? 2 : 1;            // row-parity units per K-chunk
+  static constexpr int NBOX = S == 2 ? 2 : 1;           // TMA boxes per unit (column parities)
+  static constexpr int TW = S == 2 ? BW + 1 : BW + 2 * PAD;
+  static constexpr int TR = S == 2 ? R + 1 : R + 2 * PAD;
+  static constexpr int BOX_BYTES = TR * TW * ROWB;
+  static constexpr int BOX_AL = al1024(BOX_BYTES);
+  static constexpr int STAGE_BYTES = NBOX * BOX_AL;
+  static constexpr int UNITS = NKC * NPY;               // load units per tile
   static constexpr int TAPS = KS * KS;
   static constexpr int W_BYTES = TAPS * NKC * COUT * ROWB;
-  static constexpr int W_BYTES_AL = (W_BYTES + 1023) & ~1023;
+  static constexpr int W_BYTES_AL = al1024(W_BYTES);
   static constexpr int ACC_COLS = R * COUT;
   static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
   static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + COUT * 4 + 256;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : ROWB == 64 ? 4u : 2u;     // SWIZZLE_32B / 64B / 128B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
+  static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static_assert(COUT % 16 == 0 && COUT <= 256 && CIN % 16 == 0, "bad channel counts");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+struct KMaps {
+  CUtensorMap m[4];            // stride 1: m[0]; stride 2: m[py * 2 + px] (parity sub-grids)
+};
+
 struct KArgs {
-  const __nv_bfloat16* w;      // packed [tap][kchunk][cout][KC]
+  const __nv_bfloat16* w;      // packed [cout slice][tap][kchunk][COUT][KC]
   const float* bias;
   __nv_bfloat16* out;
   const __nv_bfloat16* res[3];
   int rsh[3];
   int nres;
-  int n, h, w_img, cout_stride;
+  int n, h, w_img, cout_total;
   int relu;
   int tiles_x, tiles_y, total;
 };
 
-template <int KS, int CIN, int COUT, int R, int STAGES>
-__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap tmap, const KArgs a) {
-  using C = Cfg<KS, CIN, COUT, R, STAGES>;
+template <int KS, int S, int CIN, int COUT, int R, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
@@ -132,10 +153,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
                  bar_tempty = bar_tfull + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_off = blockIdx.y * COUT;                  // output-channel slice of this CTA
 
   // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), bias, barriers, TMEM ----
   {
-    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w);
+    const uint4* wsrc = reinterpret_cast<const uint4*>(a.w) + (size_t)blockIdx.y * (C::W_BYTES / 16);
     const uint32_t wbase = smem_u32(sW);
     constexpr int CPR = C::ROWB / 16;
     for (int i = tid; i < C::W_BYTES / 16; i += THREADS) {
@@ -143,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       addr ^= ((addr >> 7) & C::SWZ) << 4;
       *reinterpret_cast<uint4*>(sW + (addr - wbase)) = __ldg(wsrc + i);
     }
-    for (int i = tid; i < COUT; i += THREADS) sBias[i] = a.bias[i];
+    for (int i = tid; i < COUT; i += THREADS) sBias[i] = a.bias[n_off + i];
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -172,11 +194,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x) {
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
-        for (int kc = 0; kc < C::NKC; ++kc, ++it) {
+        for (int u = 0; u < C::UNITS; ++u, ++it) {
+          const int kc = u / C::NPY, py = u % C::NPY;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_full + 8 * s, C::CHUNK_BYTES);
-          tma_load_4d(smem_u32(sA + s * C::STAGE_BYTES), &tmap, bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
+          mbar_expect_tx(bar_full + 8 * s, C::NBOX * C::BOX_BYTES);
+          const uint32_t dst = smem_u32(sA + s * C::STAGE_BYTES);
+          if (S == 1) {
+            tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
+          } else {
+#pragma unroll
+            for (int px = 0; px < 2; ++px)
+              tma_load_4d(dst + px * C::BOX_AL, &maps.m[py * 2 + px], bar_full + 8 * s, kc * C::KC, tx * BW - px, ty * R - py, img);
+          }
         }
       }
     }
@@ -190,7 +220,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < C::NKC; ++kc, ++it) {
+        for (int u = 0; u < C::UNITS; ++u, ++it) {
+          const int kc = u / C::NPY, py = u % C::NPY;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
@@ -198,16 +229,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
 #pragma unroll 1
           for (int r = 0; r < R; ++r) {
             const uint32_t d_tmem = tmem + acc * C::ACC_COLS + r * COUT;
+            bool first = (u == 0);
 #pragma unroll
             for (int tap = 0; tap < C::TAPS; ++tap) {
               const int ky = tap / KS, kx = tap % KS;
-              const uint32_t arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
+              uint32_t arow;
+              if (S == 1) {
+                arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
+              } else {
+                if ((ky != 1 ? 1 : 0) != py) continue;     // this unit holds the other row parity
+                const int px = kx != 1 ? 1 : 0;
+                arow = abase + px * C::BOX_AL + ((r + (ky == 2 ? 1 : 0)) * C::TW + (kx == 2 ? 1 : 0)) * C::ROWB;
+              }
               const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
 #pragma unroll
               for (int k16 = 0; k16 < C::KC / 16; ++k16) {
                 const uint64_t da = make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
                 const uint64_t db = make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
-                umma(d_tmem, da, db, idesc, (kc | tap | k16) != 0 ? 1u : 0u);
+                umma(d_tmem, da, db, idesc, first ? 0u : 1u);
+                first = false;
               }
             }
           }
@@ -220,60 +260,82 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     // ===== epilogue warps 2..5: TMEM lane quarter (warp % 4) =====
     const int q = warp & 3;
     const int m = q * 32 + lane;                   // pixel within the tile row = TMEM lane
+    constexpr int GCOLS = C::ACC_COLS < 64 ? C::ACC_COLS : 64;      // accumulator columns fetched per TMEM wait
+    constexpr int NSUB = GCOLS / 16;
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
       const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      const int ox = tx * BW + m;
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
-      const int ox = tx * BW + m;
 #pragma unroll 1
-      for (int r = 0; r < R; ++r) {
-        const int oy = ty * R + r;
-        const bool live = ox < a.w_img && oy < a.h;
-        const size_t pix = ((size_t)img * a.h + oy) * a.w_img + ox;
-#pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 16) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + r * COUT + c0;
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (live) {
-            float f[16];
+      for (int g0 = 0; g0 < C::ACC_COLS; g0 += GCOLS) {
+        uint32_t v[NSUB][16];
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + g0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
-            for (int rr = 0; rr < a.nres; ++rr) {
+        for (int sb = 0; sb < NSUB; ++sb) tmem_ld16(taddr + sb * 16, v[sb]);
+        // residual operands for the same columns, issued before the TMEM wait so that both latencies overlap
+        uint4 rv[NSUB][2];
+        const int nres = a.nres;
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) {
+          const int col = g0 + sb * 16, r = col / COUT, c0 = col % COUT;
+          const int oy = ty * R + r;
+          const bool live = ox < a.w_img && oy < a.h;
+          rv[sb][0] = rv[sb][1] = make_uint4(0, 0, 0, 0);
+          if (live && nres > 0) {
+            const int sh = a.rsh[0];
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                a.res[0] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
+            rv[sb][0] = __ldg(rp);
+            rv[sb][1] = __ldg(rp + 1);
+          }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) {
+          const int col = g0 + sb * 16, r = col / COUT, c0 = col % COUT;
+          const int oy = ty * R + r;
+          if (!(ox < a.w_img && oy < a.h)) continue;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[sb][j]) + sBias[c0 + j];
+          if (nres > 0) {
+            const uint32_t rw[8] = {rv[sb][0].x, rv[sb][0].y, rv[sb][0].z, rv[sb][0].w, rv[sb][1].x, rv[sb][1].y, rv[sb][1].z, rv[sb][1].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+              f[2 * j] += __low2float(b2);
+              f[2 * j + 1] += __high2float(b2);
+            }
+            for (int rr = 1; rr < nres; ++rr) {
               const int sh = a.rsh[rr];
-              const __nv_bfloat16* rp =
-                  a.res[rr] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_stride + c0;
-              const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rp) + 1);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  a.res[rr] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t xw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
                 f[2 * j] += __low2float(b2);
                 f[2 * j + 1] += __high2float(b2);
               }
             }
-            if (a.relu) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              o[j] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.cout_stride + c0);
-            op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            op[1] = make_uint4(o[4], o[5], o[6], o[7]);
           }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            o[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0);
+          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
       tc_fence_before();
@@ -305,9 +367,12 @@ EncodeFn get_encode() {
   return fn;
 }
 
-template <int KS, int CIN, int COUT, int R, int STAGES>
+// output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
+int cout_tile(const TtkConv& cv) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? 64 : cv.cout_p; }
+
+template <int KS, int S, int CIN, int COUT, int R, int STAGES>
 int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  using C = Cfg<KS, CIN, COUT, R, STAGES>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES>;
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -315,21 +380,27 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, CIN, COUT, R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
-  CUtensorMap map;
-  cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)a.win, (cuuint64_t)a.hin, (cuuint64_t)a.n};
-  cuuint64_t strides[3] = {(cuuint64_t)CIN * 2, (cuuint64_t)a.win * CIN * 2, (cuuint64_t)a.hin * a.win * CIN * 2};
+  if (S == 2 && ((a.hin & 1) || (a.win & 1))) return TTK_ERR_UNSUPPORTED;
+  KMaps maps;
+  const CUtensorMapSwizzle sw = C::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : C::ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint32_t box[4] = {(cuuint32_t)C::KC, (cuuint32_t)C::TW, (cuuint32_t)C::TR, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  const CUtensorMapSwizzle sw = C::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : C::ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
-  const CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.in), dims, strides, box, es,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    ttk_set_error("cuTensorMapEncodeTiled failed (%d) for conv %s", (int)r, cv.name.c_str());
-    return TTK_ERR_CUDA;
+  for (int i = 0; i < (S == 2 ? 4 : 1); ++i) {
+    const int py = i >> 1, px = i & 1;
+    cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)(a.win / S), (cuuint64_t)(a.hin / S), (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {(cuuint64_t)CIN * 2 * S, (cuuint64_t)a.win * CIN * 2 * S, (cuuint64_t)a.hin * a.win * CIN * 2};
+    void* base = (char*)const_cast<void*>(a.in) + ((size_t)py * a.win + px) * CIN * 2;
+    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ttk_set_error("cuTensorMapEncodeTiled failed (%d) for conv %s", (int)r, cv.name.c_str());
+      return TTK_ERR_CUDA;
+    }
   }
+  for (int i = (S == 2 ? 4 : 1); i < 4; ++i) maps.m[i] = maps.m[0];
   KArgs k;
   k.w = cv.w_umma;
   k.bias = cv.bias;
@@ -342,30 +413,36 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   k.n = a.n;
   k.h = a.hout;
   k.w_img = a.wout;
-  k.cout_stride = a.cout;
+  k.cout_total = a.cout;
   k.relu = a.relu;
   k.tiles_x = ttk_cdiv(a.wout, BW);
   k.tiles_y = ttk_cdiv(a.hout, R);
   k.total = k.tiles_x * k.tiles_y * a.n;
-  const int grid = std::min(k.total, ttk_num_sms());
-  conv_umma_kernel<KS, CIN, COUT, R, STAGES><<<grid, THREADS, C::SMEM_BYTES, st>>>(map, k);
+  const int nsplit = a.cout / COUT;
+  // persistent CTAs: as many as fit per SM (shared memory and TMEM columns), never more than there are tiles
+  int occ = std::min(232448 / (C::SMEM_BYTES + 1024), 512 / C::TMEM_COLS);
+  occ = std::max(1, std::min(occ, 2));
+  const int gx = std::max(1, std::min(k.total, ttk_num_sms() * occ / nsplit));
+  dim3 grid(gx, nsplit);
+  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
 }  // namespace
 
-// Weights for the tensor-core path: bf16, [tap][k-chunk][cout_p][KC] (K-major rows of one chunk), zero padded.
+// Weights for the tensor-core path: bf16, [cout slice][tap][k-chunk][cout_tile][KC] (K-major rows of one chunk), zero padded.
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
   const int kk = cv.k * cv.k;
   const int KC = cv.cin_p < 64 ? cv.cin_p : 64;
   const int nkc = cv.cin_p / KC;
+  const int ct = cout_tile(cv);
   std::vector<__nv_bfloat16> w((size_t)kk * cv.cin_p * cv.cout_p, __float2bfloat16_rn(0.f));
   for (int co = 0; co < cv.cout; ++co)
     for (int ci = 0; ci < cv.cin; ++ci)
       for (int t = 0; t < kk; ++t) {
-        const int kc = ci / KC, c = ci % KC;
-        w[(((size_t)t * nkc + kc) * cv.cout_p + co) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
+        const int kc = ci / KC, c = ci % KC, sl = co / ct, cl = co % ct;
+        w[((((size_t)sl * kk + t) * nkc + kc) * ct + cl) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
       }
   if (!cv.w_umma) TTK_CUDA(cudaMalloc((void**)&cv.w_umma, w.size() * sizeof(__nv_bfloat16)));
   TTK_CUDA(cudaMemcpy(cv.w_umma, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
@@ -373,26 +450,35 @@ int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
 }
 
 int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  if (cv.stride != 1) return TTK_ERR_UNSUPPORTED;
-  const int ci = cv.cin_p, co = cv.cout_p;
-#define TTK_UMMA(KS_, CI_, CO_, R_, ST_) \
-  if (cv.k == KS_ && ci == CI_ && co == CO_) return launch<KS_, CI_, CO_, R_, ST_>(cv, a, st);
-  // 3x3
-  TTK_UMMA(3, 16, 64, 4, 3)     // stem conv1 (9 -> 64, input padded to 16 channels)
-  TTK_UMMA(3, 64, 64, 2, 2)     // stem conv2, quarter-resolution branch
-  TTK_UMMA(3, 32, 32, 4, 3)     // bottleneck conv2, half-resolution branch
-  TTK_UMMA(3, 16, 16, 8, 3)     // full-resolution branch
-  TTK_UMMA(3, 128, 16, 2, 2)    // transition1.0
+  const int ci = cv.cin_p, co = cout_tile(cv);
+#define TTK_UMMA(KS_, S_, CI_, CO_, R_, ST_) \
+  if (cv.k == KS_ && cv.stride == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_>(cv, a, st);
+  // 3x3 stride 1
+  TTK_UMMA(3, 1, 16, 64, 4, 3)     // stem conv1 (9 -> 64, input padded to 16 channels)
+  TTK_UMMA(3, 1, 64, 64, 2, 2)     // stem conv2, quarter-resolution branch
+  TTK_UMMA(3, 1, 32, 32, 4, 3)     // bottleneck conv2, half-resolution branch
+  TTK_UMMA(3, 1, 16, 16, 8, 3)     // full-resolution branch
+  TTK_UMMA(3, 1, 128, 16, 2, 2)    // transition1.0
+  if (cv.cout_p == 128) TTK_UMMA(3, 1, 128, 64, 2, 1)   // eighth-resolution branch, two 64-channel output slices
+  // 3x3 stride 2 (transitions and fuse down-paths)
+  TTK_UMMA(3, 2, 128, 32, 1, 2)
+  TTK_UMMA(3, 2, 16, 16, 4, 3)
+  TTK_UMMA(3, 2, 16, 32, 4, 3)
+  TTK_UMMA(3, 2, 16, 64, 4, 3)
+  TTK_UMMA(3, 2, 16, 128, 2, 3)
+  TTK_UMMA(3, 2, 32, 32, 4, 2)
+  TTK_UMMA(3, 2, 32, 64, 4, 2)
+  TTK_UMMA(3, 2, 32, 128, 2, 2)
+  if (cv.cout_p == 128) TTK_UMMA(3, 2, 64, 64, 1, 2)    // 64 -> 128, two output slices
   // 1x1
-  TTK_UMMA(1, 64, 32, 4, 2)     // bottleneck conv1
-  TTK_UMMA(1, 32, 128, 2, 3)    // bottleneck conv3
-  TTK_UMMA(1, 64, 128, 2, 3)    // bottleneck projection shortcut
-  TTK_UMMA(1, 32, 16, 4, 3)     // fuse layers (low -> high resolution)
-  TTK_UMMA(1, 64, 16, 4, 3)
-  TTK_UMMA(1, 128, 16, 4, 2)
-  TTK_UMMA(1, 64, 32, 4, 2)
-  TTK_UMMA(1, 128, 32, 4, 2)
-  TTK_UMMA(1, 128, 64, 2, 2)
+  TTK_UMMA(1, 1, 64, 32, 4, 2)     // bottleneck conv1, fuse 64 -> 32
+  TTK_UMMA(1, 1, 32, 128, 2, 3)    // bottleneck conv3
+  TTK_UMMA(1, 1, 64, 128, 2, 3)    // bottleneck projection shortcut
+  TTK_UMMA(1, 1, 32, 16, 4, 3)     // fuse layers (low -> high resolution)
+  TTK_UMMA(1, 1, 64, 16, 4, 3)
+  TTK_UMMA(1, 1, 128, 16, 4, 2)
+  TTK_UMMA(1, 1, 128, 32, 4, 2)
+  TTK_UMMA(1, 1, 128, 64, 2, 2)
 #undef TTK_UMMA
   return TTK_ERR_UNSUPPORTED;
 }

@@ -324,4 +324,13 @@ def main():
 
 
 if __name__ == '__main__':
+    # stdout carries exactly one JSON line: everything else the libraries print (model loaders etc.) goes to stderr
+    _real_stdout = sys.stdout
+    sys.stdout = sys.stderr
+    _orig_print = print
+
+    def print(*a, **k):          # noqa: A001 - the JSON line
+        k.setdefault('file', _real_stdout)
+        _orig_print(*a, **k)
+        _real_stdout.flush()
     main()

@@ -14,6 +14,12 @@
 //   Stride 2: the input is addressed as four parity sub-grids (even/odd rows x even/odd columns, one
 //   tensor map each, strides doubled); every tap then reads one sub-grid with unit pixel stride.
 //   Image borders come for free from TMA's zero fill of out-of-bounds coordinates.
+//   Vertical tap fusion (3x3 stride 1, Cout <= 64): an MMA costs at least the shared-memory read of its
+//   128 x 16 A slab, so N = Cout = 16..64 leaves the tensor pipe mostly fetching.  The accumulators of a
+//   tile's R output rows sit side by side in TMEM in REVERSE row order; input row yi and horizontal tap kx
+//   are then multiplied ONCE with B = [W(ky=0,kx) | W(ky=1,kx) | W(ky=2,kx)] (N = 3 Cout), which lands in
+//   the column blocks of output rows yi+1, yi, yi-1.  3(R+2) wide MMAs replace 9R narrow ones.
+//   Accumulators are zeroed by the epilogue after it drains them, so every MMA accumulates.
 // Roles (persistent CTA, static tile round-robin): warp 0 = TMA producer, warp 1 = MMA issuer
 // (one elected thread), warps 2-5 = epilogue (TMEM -> registers -> bias/residual/ReLU -> bf16 -> global).
 // Pipelines: smem full/empty ring over load units, double-buffered TMEM accumulators (tmem full/empty).
@@ -44,7 +50,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n\t"
       "@p bra LAB_DONE;\n\t"
       "bra LAB_WAIT;\n\t"
       "LAB_DONE:\n\t}" ::"r"(bar),
@@ -91,17 +97,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
 // KS: 1 or 3; S: stride 1 or 2 (3x3 only); CIN: padded input channels; COUT: output channels handled by one CTA
-// (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth.
-template <int KS, int S, int CIN, int COUT, int R, int STAGES>
+// (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth;
+// RB: reserve shared memory for TMA-staged residual tiles (double buffered with the accumulators).
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
 struct Cfg {
   static constexpr int KC = CIN < 64 ? CIN : 64;        // channels per K-chunk = one swizzled smem row
   static constexpr int NKC = CIN / KC;
   static constexpr int ROWB = KC * 2;
   static constexpr int PAD = KS / 2;
+  static constexpr bool FUSE = KS == 3 && S == 1 && 3 * COUT <= 256;   // vertical tap fusion
   static constexpr int NPY = S == 2 ? 2 : 1;            // row-parity units per K-chunk
   static constexpr int NBOX = S == 2 ? 2 : 1;           // TMA boxes per unit (column parities)
   static constexpr int TW = S == 2 ? BW + 1 : BW + 2 * PAD;
@@ -115,7 +128,14 @@ struct Cfg {
   static constexpr int W_BYTES_AL = al1024(W_BYTES);
   static constexpr int ACC_COLS = R * COUT;
   static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
-  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + COUT * 4 + 256;
+  // residual staging: boxes of CB channels (<= 64 = 128 swizzled bytes per pixel) x 128 px x R rows
+  static constexpr int CB = COUT < 64 ? COUT : 64;
+  static constexpr int NRB = COUT / CB;
+  static constexpr int RROWB = CB * 2;
+  static constexpr int RBOX_BYTES = R * BW * RROWB;     // multiple of 1024
+  static constexpr int RES_BYTES = RB ? 2 * NRB * RBOX_BYTES : 0;
+  static constexpr uint32_t RSWZ = RROWB == 32 ? 1u : RROWB == 64 ? 3u : 7u;
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + RES_BYTES + COUT * 4 + 256;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : ROWB == 64 ? 4u : 2u;     // SWIZZLE_32B / 64B / 128B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
@@ -126,34 +146,38 @@ struct Cfg {
 
 struct KMaps {
   CUtensorMap m[4];            // stride 1: m[0]; stride 2: m[py * 2 + px] (parity sub-grids)
+  CUtensorMap res;             // residual tensor (same shape as the output), when staged by TMA
 };
 
 struct KArgs {
-  const __nv_bfloat16* w;      // packed [cout slice][tap][kchunk][COUT][KC]
+  const __nv_bfloat16* w;      // packed weights, see ttk_conv_umma_pack
   const float* bias;
   __nv_bfloat16* out;
   const __nv_bfloat16* res[3];
   int rsh[3];
   int nres;
+  int res_tma;                 // res[0] (shift 0) arrives through shared memory
   int n, h, w_img, cout_total;
   int relu;
   int tiles_x, tiles_y, total;
 };
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sA = smem + C::W_BYTES_AL;
-  float* sBias = reinterpret_cast<float*>(sA + STAGES * C::STAGE_BYTES);
+  uint8_t* sR = sA + STAGES * C::STAGE_BYTES;           // [acc][box][row][px][CB] swizzled (1024-aligned)
+  float* sBias = reinterpret_cast<float*>(sR + C::RES_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + COUT);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
-                 bar_tempty = bar_tfull + 16;
+                 bar_tempty = bar_tfull + 16, bar_rfull = bar_tempty + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_off = blockIdx.y * COUT;                  // output-channel slice of this CTA
+  const bool res_tma = RB && a.res_tma;
 
   // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), bias, barriers, TMEM ----
   {
@@ -175,6 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
       mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_rfull + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -191,8 +216,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
         for (int u = 0; u < C::UNITS; ++u, ++it) {
           const int kc = u / C::NPY, py = u % C::NPY;
@@ -208,46 +233,72 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               tma_load_4d(dst + px * C::BOX_AL, &maps.m[py * 2 + px], bar_full + 8 * s, kc * C::KC, tx * BW - px, ty * R - py, img);
           }
         }
+        if (res_tma) {
+          // the residual buffer pairs with the accumulator buffer: free once the epilogue of tile-2 has finished
+          const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+          mbar_wait(bar_tempty + 8 * acc, aph);
+          mbar_expect_tx(bar_rfull + 8 * acc, C::NRB * C::RBOX_BYTES);
+#pragma unroll
+          for (int b = 0; b < C::NRB; ++b)
+            tma_load_4d(smem_u32(sR + (acc * C::NRB + b) * C::RBOX_BYTES), &maps.res, bar_rfull + 8 * acc, n_off + b * C::CB, tx * BW,
+                        ty * R, img);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, COUT);
       const uint32_t wbase = smem_u32(sW);
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+        mbar_wait(bar_tempty + 8 * acc, aph);      // accumulators drained and zeroed by the epilogue
         tc_fence_after();
+        const uint32_t d_acc = tmem + acc * C::ACC_COLS;
         for (int u = 0; u < C::UNITS; ++u, ++it) {
           const int kc = u / C::NPY, py = u % C::NPY;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           tc_fence_after();
           const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES);
+          if (C::FUSE) {
+            // input (halo) row hr = yi + 1 feeds output rows yo = yi + 1 - ky; row yo lives in column block R-1-yo
 #pragma unroll 1
-          for (int r = 0; r < R; ++r) {
-            const uint32_t d_tmem = tmem + acc * C::ACC_COLS + r * COUT;
-            bool first = (u == 0);
+            for (int hr = 0; hr < R + 2; ++hr) {
+              const int yi = hr - 1;
+              const int k0 = yi + 2 - R > 0 ? yi + 2 - R : 0;
+              const int k1 = yi + 1 < 2 ? yi + 1 : 2;
+              const uint32_t idesc = make_idesc(128, (k1 - k0 + 1) * COUT);
+              const uint32_t d_tmem = d_acc + (R - 2 - yi + k0) * COUT;
 #pragma unroll
-            for (int tap = 0; tap < C::TAPS; ++tap) {
-              const int ky = tap / KS, kx = tap % KS;
-              uint32_t arow;
-              if (S == 1) {
-                arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
-              } else {
-                if ((ky != 1 ? 1 : 0) != py) continue;     // this unit holds the other row parity
-                const int px = kx != 1 ? 1 : 0;
-                arow = abase + px * C::BOX_AL + ((r + (ky == 2 ? 1 : 0)) * C::TW + (kx == 2 ? 1 : 0)) * C::ROWB;
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint32_t arow = abase + (hr * C::TW + kx) * C::ROWB;
+                const uint32_t brow = wbase + (((kc * 3 + kx) * 3 + k0) * COUT) * C::ROWB;
+#pragma unroll
+                for (int k16 = 0; k16 < C::KC / 16; ++k16)
+                  umma(d_tmem, make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT), idesc, 1u);
               }
-              const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
+            }
+          } else {
+            constexpr uint32_t idesc = make_idesc(128, COUT);
+#pragma unroll 1
+            for (int r = 0; r < R; ++r) {
+              const uint32_t d_tmem = d_acc + (R - 1 - r) * COUT;
 #pragma unroll
-              for (int k16 = 0; k16 < C::KC / 16; ++k16) {
-                const uint64_t da = make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
-                const uint64_t db = make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT);
-                umma(d_tmem, da, db, idesc, first ? 0u : 1u);
-                first = false;
+              for (int tap = 0; tap < C::TAPS; ++tap) {
+                const int ky = tap / KS, kx = tap % KS;
+                uint32_t arow;
+                if (S == 1) {
+                  arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
+                } else {
+                  if ((ky != 1 ? 1 : 0) != py) continue;     // this unit holds the other row parity
+                  const int px = kx != 1 ? 1 : 0;
+                  arow = abase + px * C::BOX_AL + ((r + (ky == 2 ? 1 : 0)) * C::TW + (kx == 2 ? 1 : 0)) * C::ROWB;
+                }
+                const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
+#pragma unroll
+                for (int k16 = 0; k16 < C::KC / 16; ++k16)
+                  umma(d_tmem, make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT), idesc, 1u);
               }
             }
           }
@@ -262,40 +313,62 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const int m = q * 32 + lane;                   // pixel within the tile row = TMEM lane
     constexpr int GCOLS = C::ACC_COLS < 64 ? C::ACC_COLS : 64;      // accumulator columns fetched per TMEM wait
     constexpr int NSUB = GCOLS / 16;
+    const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    // zero both accumulator buffers, then open them for the MMA warp
+    for (int c = 0; c < 2 * C::ACC_COLS; c += 16) tmem_zero16(lane_base + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(bar_tempty);
+      mbar_arrive(bar_tempty + 8);
+    }
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
       const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       const int ox = tx * BW + m;
+      if (res_tma) mbar_wait(bar_rfull + 8 * acc, aph);
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
 #pragma unroll 1
       for (int g0 = 0; g0 < C::ACC_COLS; g0 += GCOLS) {
         uint32_t v[NSUB][16];
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + g0;
+        const uint32_t taddr = lane_base + acc * C::ACC_COLS + g0;
 #pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) tmem_ld16(taddr + sb * 16, v[sb]);
-        // residual operands for the same columns, issued before the TMEM wait so that both latencies overlap
+        // first residual operand for the same columns, fetched before the TMEM wait so that the latencies overlap
         uint4 rv[NSUB][2];
         const int nres = a.nres;
 #pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) {
-          const int col = g0 + sb * 16, r = col / COUT, c0 = col % COUT;
+          const int col = g0 + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
           const int oy = ty * R + r;
           const bool live = ox < a.w_img && oy < a.h;
           rv[sb][0] = rv[sb][1] = make_uint4(0, 0, 0, 0);
-          if (live && nres > 0) {
-            const int sh = a.rsh[0];
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                a.res[0] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
-            rv[sb][0] = __ldg(rp);
-            rv[sb][1] = __ldg(rp + 1);
+          if (nres > 0) {
+            if (res_tma) {
+              const uint32_t base = smem_u32(sR + (acc * C::NRB + c0 / C::CB) * C::RBOX_BYTES);
+              uint32_t ad = base + (r * BW + m) * C::RROWB + (c0 % C::CB) * 2;
+              ad ^= ((ad >> 7) & C::RSWZ) << 4;
+              const uint32_t ad2 = (base + (r * BW + m) * C::RROWB + (c0 % C::CB) * 2 + 16) ^ ((((base + (r * BW + m) * C::RROWB) >> 7) & C::RSWZ) << 4);
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[sb][0].x), "=r"(rv[sb][0].y), "=r"(rv[sb][0].z), "=r"(rv[sb][0].w) : "r"(ad));
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[sb][1].x), "=r"(rv[sb][1].y), "=r"(rv[sb][1].z), "=r"(rv[sb][1].w) : "r"(ad2));
+            } else if (live) {
+              const int sh = a.rsh[0];
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  a.res[0] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
+              rv[sb][0] = __ldg(rp);
+              rv[sb][1] = __ldg(rp + 1);
+            }
           }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) tmem_zero16(taddr + sb * 16);     // leave the columns zeroed for the next tile
+#pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) {
-          const int col = g0 + sb * 16, r = col / COUT, c0 = col % COUT;
+          const int col = g0 + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
           const int oy = ty * R + r;
           if (!(ox < a.w_img && oy < a.h)) continue;
           float f[16];
@@ -304,10 +377,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           if (nres > 0) {
             const uint32_t rw[8] = {rv[sb][0].x, rv[sb][0].y, rv[sb][0].z, rv[sb][0].w, rv[sb][1].x, rv[sb][1].y, rv[sb][1].z, rv[sb][1].w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
-              f[2 * j] += __low2float(b2);
-              f[2 * j + 1] += __high2float(b2);
+            for (int j = 0; j < 8; ++j) {            // bf16 -> f32 by bit placement (keeps the conversion pipe free)
+              f[2 * j] += __uint_as_float(rw[j] << 16);
+              f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
             }
             for (int rr = 1; rr < nres; ++rr) {
               const int sh = a.rsh[rr];
@@ -317,9 +389,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               const uint32_t xw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
-                f[2 * j] += __low2float(b2);
-                f[2 * j + 1] += __high2float(b2);
+                f[2 * j] += __uint_as_float(xw[j] << 16);
+                f[2 * j + 1] += __uint_as_float(xw[j] & 0xffff0000u);
               }
             }
           }
@@ -338,6 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           op[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -369,10 +441,15 @@ EncodeFn get_encode() {
 
 // output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
 int cout_tile(const TtkConv& cv) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? 64 : cv.cout_p; }
+bool fused_ky(const TtkConv& cv) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv) <= 256; }
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES>
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+}
+
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
 int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB>;
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -380,12 +457,11 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
   if (S == 2 && ((a.hin & 1) || (a.win & 1))) return TTK_ERR_UNSUPPORTED;
   KMaps maps;
-  const CUtensorMapSwizzle sw = C::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : C::ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint32_t box[4] = {(cuuint32_t)C::KC, (cuuint32_t)C::TW, (cuuint32_t)C::TR, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   for (int i = 0; i < (S == 2 ? 4 : 1); ++i) {
@@ -393,14 +469,28 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
     cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)(a.win / S), (cuuint64_t)(a.hin / S), (cuuint64_t)a.n};
     cuuint64_t strides[3] = {(cuuint64_t)CIN * 2 * S, (cuuint64_t)a.win * CIN * 2 * S, (cuuint64_t)a.hin * a.win * CIN * 2};
     void* base = (char*)const_cast<void*>(a.in) + ((size_t)py * a.win + px) * CIN * 2;
-    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_for(C::ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       ttk_set_error("cuTensorMapEncodeTiled failed (%d) for conv %s", (int)r, cv.name.c_str());
       return TTK_ERR_CUDA;
     }
   }
   for (int i = (S == 2 ? 4 : 1); i < 4; ++i) maps.m[i] = maps.m[0];
+  const bool res_tma = RB && a.nres > 0 && a.res_shift[0] == 0;
+  maps.res = maps.m[0];
+  if (res_tma) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.cout, (cuuint64_t)a.wout, (cuuint64_t)a.hout, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {(cuuint64_t)a.cout * 2, (cuuint64_t)a.wout * a.cout * 2, (cuuint64_t)a.hout * a.wout * a.cout * 2};
+    cuuint32_t rbox[4] = {(cuuint32_t)C::CB, (cuuint32_t)BW, (cuuint32_t)R, 1};
+    const CUresult r = encode(&maps.res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.res[0]), dims, strides, rbox, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::RROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ttk_set_error("cuTensorMapEncodeTiled (residual) failed (%d) for conv %s", (int)r, cv.name.c_str());
+      return TTK_ERR_CUDA;
+    }
+  }
   KArgs k;
   k.w = cv.w_umma;
   k.bias = cv.bias;
@@ -410,6 +500,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
     k.rsh[i] = a.res_shift[i];
   }
   k.nres = a.nres;
+  k.res_tma = res_tma ? 1 : 0;
   k.n = a.n;
   k.h = a.hout;
   k.w_img = a.wout;
@@ -424,25 +515,35 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   occ = std::max(1, std::min(occ, 2));
   const int gx = std::max(1, std::min(k.total, ttk_num_sms() * occ / nsplit));
   dim3 grid(gx, nsplit);
-  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
 }  // namespace
 
-// Weights for the tensor-core path: bf16, [cout slice][tap][k-chunk][cout_tile][KC] (K-major rows of one chunk), zero padded.
+// Weights for the tensor-core path: bf16 rows of KC input channels (K-major), zero padded, per output-channel slice:
+//   fused 3x3 stride 1 : [slice][k-chunk][kx][ky][cout_tile][KC]   (B = the three vertical taps side by side)
+//   otherwise          : [slice][tap][k-chunk][cout_tile][KC]
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
   const int kk = cv.k * cv.k;
   const int KC = cv.cin_p < 64 ? cv.cin_p : 64;
   const int nkc = cv.cin_p / KC;
   const int ct = cout_tile(cv);
+  const bool fused = fused_ky(cv);
   std::vector<__nv_bfloat16> w((size_t)kk * cv.cin_p * cv.cout_p, __float2bfloat16_rn(0.f));
   for (int co = 0; co < cv.cout; ++co)
     for (int ci = 0; ci < cv.cin; ++ci)
       for (int t = 0; t < kk; ++t) {
         const int kc = ci / KC, c = ci % KC, sl = co / ct, cl = co % ct;
-        w[((((size_t)sl * kk + t) * nkc + kc) * ct + cl) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
+        size_t row;
+        if (fused) {
+          const int ky = t / 3, kx = t % 3;
+          row = (((size_t)sl * nkc + kc) * 3 + kx) * 3 + ky;
+        } else {
+          row = ((size_t)sl * kk + t) * nkc + kc;
+        }
+        w[(row * ct + cl) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
       }
   if (!cv.w_umma) TTK_CUDA(cudaMalloc((void**)&cv.w_umma, w.size() * sizeof(__nv_bfloat16)));
   TTK_CUDA(cudaMemcpy(cv.w_umma, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
@@ -451,34 +552,34 @@ int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
 
 int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   const int ci = cv.cin_p, co = cout_tile(cv);
-#define TTK_UMMA(KS_, S_, CI_, CO_, R_, ST_) \
-  if (cv.k == KS_ && cv.stride == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_>(cv, a, st);
+#define TTK_UMMA(KS_, S_, CI_, CO_, R_, ST_, RB_) \
+  if (cv.k == KS_ && cv.stride == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_>(cv, a, st);
   // 3x3 stride 1
-  TTK_UMMA(3, 1, 16, 64, 4, 3)     // stem conv1 (9 -> 64, input padded to 16 channels)
-  TTK_UMMA(3, 1, 64, 64, 2, 2)     // stem conv2, quarter-resolution branch
-  TTK_UMMA(3, 1, 32, 32, 4, 3)     // bottleneck conv2, half-resolution branch
-  TTK_UMMA(3, 1, 16, 16, 8, 3)     // full-resolution branch
-  TTK_UMMA(3, 1, 128, 16, 2, 2)    // transition1.0
-  if (cv.cout_p == 128) TTK_UMMA(3, 1, 128, 64, 2, 1)   // eighth-resolution branch, two 64-channel output slices
+  TTK_UMMA(3, 1, 16, 64, 4, 3, 0)     // stem conv1 (9 -> 64, input padded to 16 channels)
+  TTK_UMMA(3, 1, 64, 64, 2, 2, 0)     // stem conv2, quarter-resolution branch
+  TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
+  TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
+  TTK_UMMA(3, 1, 128, 16, 2, 2, 0)    // transition1.0
+  TTK_UMMA(3, 1, 128, 64, 2, 1, 0)    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
   // 3x3 stride 2 (transitions and fuse down-paths)
-  TTK_UMMA(3, 2, 128, 32, 1, 2)
-  TTK_UMMA(3, 2, 16, 16, 4, 3)
-  TTK_UMMA(3, 2, 16, 32, 4, 3)
-  TTK_UMMA(3, 2, 16, 64, 4, 3)
-  TTK_UMMA(3, 2, 16, 128, 2, 3)
-  TTK_UMMA(3, 2, 32, 32, 4, 2)
-  TTK_UMMA(3, 2, 32, 64, 4, 2)
-  TTK_UMMA(3, 2, 32, 128, 2, 2)
-  if (cv.cout_p == 128) TTK_UMMA(3, 2, 64, 64, 1, 2)    // 64 -> 128, two output slices
+  TTK_UMMA(3, 2, 128, 32, 1, 2, 0)
+  TTK_UMMA(3, 2, 16, 16, 4, 3, 0)
+  TTK_UMMA(3, 2, 16, 32, 4, 3, 0)
+  TTK_UMMA(3, 2, 16, 64, 4, 3, 0)
+  TTK_UMMA(3, 2, 16, 128, 2, 3, 0)
+  TTK_UMMA(3, 2, 32, 32, 4, 2, 0)
+  TTK_UMMA(3, 2, 32, 64, 4, 2, 0)
+  TTK_UMMA(3, 2, 32, 128, 2, 2, 0)
+  TTK_UMMA(3, 2, 64, 64, 1, 2, 0)     // 64 -> 128 as two output slices
   // 1x1
-  TTK_UMMA(1, 1, 64, 32, 4, 2)     // bottleneck conv1, fuse 64 -> 32
-  TTK_UMMA(1, 1, 32, 128, 2, 3)    // bottleneck conv3
-  TTK_UMMA(1, 1, 64, 128, 2, 3)    // bottleneck projection shortcut
-  TTK_UMMA(1, 1, 32, 16, 4, 3)     // fuse layers (low -> high resolution)
-  TTK_UMMA(1, 1, 64, 16, 4, 3)
-  TTK_UMMA(1, 1, 128, 16, 4, 2)
-  TTK_UMMA(1, 1, 128, 32, 4, 2)
-  TTK_UMMA(1, 1, 128, 64, 2, 2)
+  TTK_UMMA(1, 1, 64, 32, 4, 2, 0)     // bottleneck conv1, fuse 64 -> 32
+  TTK_UMMA(1, 1, 32, 128, 2, 3, 1)    // bottleneck conv3 (+ projection shortcut as residual)
+  TTK_UMMA(1, 1, 64, 128, 2, 3, 0)    // bottleneck projection shortcut
+  TTK_UMMA(1, 1, 32, 16, 4, 3, 0)     // fuse layers (low -> high resolution)
+  TTK_UMMA(1, 1, 64, 16, 4, 3, 0)
+  TTK_UMMA(1, 1, 128, 16, 4, 2, 0)
+  TTK_UMMA(1, 1, 128, 32, 4, 2, 0)
+  TTK_UMMA(1, 1, 128, 64, 2, 2, 0)
 #undef TTK_UMMA
   return TTK_ERR_UNSUPPORTED;
 }

@@ -31,7 +31,7 @@ def test_ball_detector_predict(weights, golden):
     assert pos.shape == (4, 3) and pos.dtype == np.float64 and hm.shape == (4, 1, 88, 160) and hm.dtype == np.float32
     np.testing.assert_allclose(hm, g['ball_hm'], rtol=0, atol=1e-4 * np.abs(g['ball_hm']).max() + 1e-5)
     assert np.all(pos[:, 2] == 1.0)
-    np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=0.05)
+    np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=1e-3)
     # independent (copied) triples take the stride-3 path and give the same answer
     pos2, _ = bd.predict([tuple(f.copy() for f in t) for t in triples], return_heatmaps=False)
     assert np.array_equal(pos, pos2)
@@ -53,7 +53,7 @@ def test_table_detector_predict(weights, golden):
     assert pos.shape == (2, 13, 3) and hm.shape == (2, 1, 13, 88, 160)
     np.testing.assert_allclose(hm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
     err = np.abs(pos[..., :2] - g['table_pos'][..., :2]).max(axis=-1)
-    assert np.mean(err < 0.05) >= 0.8, err   # tightened once the decode solver follows L-BFGS-B step for step
+    assert np.mean(err < 1e-3) >= 0.95, err
     with pytest.raises(NotImplementedError):
         td.calibrate_camera(pos[0])
 

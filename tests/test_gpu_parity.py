@@ -60,7 +60,8 @@ def test_preprocess_1080p_bit_exact(dev, res):
 # ------------------------------------------------------------------------------------------------
 # decode
 # ------------------------------------------------------------------------------------------------
-DECODE_TOL_PX = 5e-3    # image pixels; SciPy's own stopping error (pgtol 1e-5) is ~1e-3 px, see DESIGN.md
+DECODE_TOL_PX = 1e-3    # image pixels.  The kernel runs SciPy's L-BFGS-B iteration itself (csrc/lbfgsb4.h); only
+                        # ill-conditioned fits (a sigma on its bound leaves the centre nearly undetermined) drift further
 
 
 def _decode_both(dev, hm, variant):
@@ -81,9 +82,8 @@ def test_decode_golden(dev, golden, variant):
     ok = np.ones(len(hm), bool) if variant == 'table' else g['ball_ok']
     assert np.all(out[:, 2] == 1.0)
     err = np.abs(out[ok, :2] - gold[ok, :2]).max(axis=1)
-    # well-conditioned windows (a real peak) agree to SciPy's stopping error; report the rest
-    assert np.median(err) < 2e-4, np.median(err)
-    assert np.mean(err < DECODE_TOL_PX) >= 0.9, np.sort(err)[-8:]
+    assert np.median(err) < 1e-5, np.median(err)
+    assert np.mean(err < DECODE_TOL_PX) >= (0.97 if variant == 'table' else 0.85), np.sort(err)[-8:]
 
 
 def test_decode_full_size_and_properties(dev):
@@ -122,7 +122,7 @@ def test_decode_shapes_and_ragged(dev):
     assert out.shape == (2, 13, 3) and out.dtype == torch.float64
     ref, _, _ = odec.decode_heatmaps(hm, 1920, 1080, odec.TABLE)
     err = np.abs(out.view(26, 3).cpu().numpy() - ref)[:, :2].max(axis=1)
-    assert np.mean(err < DECODE_TOL_PX) >= 0.9
+    assert np.mean(err < DECODE_TOL_PX) >= 0.95
     empty = ops.decode_heatmaps(torch.zeros((0, 8, 8), device=dev), 1920, 1080, 'ball')
     assert empty.shape == (0, 3)
 

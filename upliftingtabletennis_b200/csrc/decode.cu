@@ -1,10 +1,11 @@
 // Heatmap decode: argmax (first maximum, NaN counts as maximum, like torch.argmax) ->
-// 3x3 zero-padded window -> bounded Gaussian fit (float64) -> heatmap->image rescale.
+// 3x3 zero-padded window -> bounded Gaussian fit (float64 L-BFGS-B that follows SciPy's iteration, lbfgsb4.h)
+// -> heatmap->image rescale.
 // Reference: tabledetection/helper_tabledetection.py:50-156, balldetection/helper_balldetection.py:29-110.
 //
 // HBM-bound: every heatmap value is read exactly once with 128-bit loads
 // (H*W*4 bytes per map); the fit is O(10^3) flops per map.
-#include "gaussfit.h"
+#include "lbfgsb4.h"
 #include "ttk_internal.h"
 
 namespace {
@@ -131,11 +132,11 @@ __global__ void __launch_bounds__(32) decode_finalize_kernel(const float* __rest
       wf[j * 3 + i] = v;
       w[j * 3 + i] = (double)v;
     }
-  const TtkFit fit = ttk_gauss_fit(w, variant);
+  const TtkLbfgsbResult fit = ttk_lbfgsb_gauss(w, variant);
   double xi, yi;
-  if (fit.ok) {
-    const double xs = (double)(x - 1) + fit.p[0];
-    const double ys = (double)(y - 1) + fit.p[1];
+  if (fit.success) {
+    const double xs = (double)(x - 1) + fit.x[0];
+    const double ys = (double)(y - 1) + fit.x[1];
     xi = (xs + 0.5) * scale_x - 0.5;
     yi = (ys + 0.5) * scale_y - 0.5;
   } else {

@@ -278,14 +278,30 @@ def main():
     (top_type, top_conv), top = max(per.items(), key=lambda kv: kv[1][0])
     name = engine.specs[top_conv][0] if top_conv >= 0 else ('fuse_sum' if top_type == 1 else 'final_conv')
     achieved_tf = top[1] / (top[0] * 1e-3) / 1e12
+    achieved_gbs = top[2] / (top[0] * 1e-3) / 1e9
     conv_ms = sum(v[0] for k, v in per.items() if k[0] == 0)
     conv_fl = sum(v[1] for k, v in per.items() if k[0] == 0)
+    conv_by = sum(v[2] for k, v in per.items() if k[0] == 0)
+    # which roofline bounds the dominant kernel: arithmetic intensity against the ridge of the measured peaks
+    ridge = pk['bf16_tflops_sustained'] * 1e12 / (pk['hbm_gbs'] * 1e9)
+    intensity = top[1] / top[2]
+    hbm_bound = intensity < ridge
     roofline = {
-        'bound': 'tensor', 'kernel': 'conv %s (%d launches/step, %.1f%% of detector time)' % (name, top[3], 100 * top[0] / tot_ms),
-        'achieved': achieved_tf, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': achieved_tf / pk['bf16_tflops_sustained'],
-        'peak_source': pk['source'] + ', sustained bf16 (kernel timed inside a long step)', 'traffic': None,
-        'hbm_achieved_gbs': top[2] / (top[0] * 1e-3) / 1e9, 'hbm_frac': top[2] / (top[0] * 1e-3) / 1e9 / pk['hbm_gbs'],
-        'all_convs': {'achieved_tflops': conv_fl / (conv_ms * 1e-3) / 1e12, 'frac': conv_fl / (conv_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+        'bound': 'hbm' if hbm_bound else 'tensor',
+        'kernel': 'conv %s (%d launches/step, %.1f%% of detector time)' % (name, top[3], 100 * top[0] / tot_ms),
+        'achieved': achieved_gbs if hbm_bound else achieved_tf,
+        'peak': pk['hbm_gbs'] if hbm_bound else pk['bf16_tflops_sustained'],
+        'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
+        'frac': (achieved_gbs / pk['hbm_gbs']) if hbm_bound else (achieved_tf / pk['bf16_tflops_sustained']),
+        'traffic': None,
+        'peak_source': pk['source'] + (', copy bandwidth' if hbm_bound else ', sustained bf16 (kernel timed inside a long step)'),
+        'intensity_flop_per_byte': intensity, 'ridge_flop_per_byte': ridge,
+        'algorithmic_bytes_per_launch': top[2] / top[3], 'algorithmic_flops_per_launch': top[1] / top[3],
+        'avg_launch_ms': top[0] / top[3],
+        'tensor_achieved_tflops': achieved_tf, 'tensor_frac': achieved_tf / pk['bf16_tflops_sustained'],
+        'hbm_achieved_gbs': achieved_gbs, 'hbm_frac': achieved_gbs / pk['hbm_gbs'],
+        'all_convs': {'achieved_tflops': conv_fl / (conv_ms * 1e-3) / 1e12, 'tensor_frac': conv_fl / (conv_ms * 1e-3) / 1e12 / pk['bf16_tflops_sustained'],
+                      'achieved_gbs': conv_by / (conv_ms * 1e-3) / 1e9, 'hbm_frac': conv_by / (conv_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
                       'share_of_detector_time': conv_ms / tot_ms},
         'whole_step_tflops': WASB_GFLOP_PER_STACK * BATCH * args.steps / (ms_dev * 1e-3) / 1e3,
     }

@@ -260,3 +260,31 @@ def test_tails(dev, golden):
     assert np.array_equal(ti[0:1].cpu().numpy(), g['ut_times']) and np.array_equal(mk[0:1].cpu().numpy(), g['ut_mask'])
     assert np.array_equal(b[1:2].cpu().numpy(), g['utl_ball']) and np.array_equal(ti[1:2].cpu().numpy(), g['utl_times'])
     assert np.array_equal(mk[1:2].cpu().numpy(), g['utl_mask'])
+
+
+@pytest.mark.parametrize('name', ['connectstage', 'multistage'])
+def test_uplift_bf16_tensor_core_bound(dev, golden, name):
+    """bf16 tcgen05 path: reported separately with its own bound (relative L2 per trajectory on valid rows)."""
+    from upliftingtabletennis_b200.uplift import get_model
+    g = golden('uplift')
+    sd = oup.random_state_dict(int(g[name + '_seed']))
+    m = get_model(name, 'large', 'dynamic', 'new').to(dev).eval()
+    m.load_state_dict(sd)
+    rng = np.random.default_rng(21)
+    ball, table, mask, times = synthetic_trajectories(rng, 23)
+    r_ref, p_ref = oup.uplift_forward(sd, *(torch.from_numpy(a) for a in (ball, table, mask, times)), use_skipconnection=(name == 'connectstage'))
+    args = [torch.from_numpy(a).to(dev) for a in (ball, table, mask, times)]
+    r32, p32 = m(*args)
+    m.compute_dtype = torch.bfloat16
+    r16, p16 = m(*args)
+    m.compute_dtype = torch.float32
+    assert torch.isfinite(p16).all() and torch.isfinite(r16).all()
+    valid = mask.astype(bool)
+    for b in range(ball.shape[0]):
+        ref = p_ref.numpy()[b][valid[b]]
+        rel = np.linalg.norm(p16.cpu().numpy()[b][valid[b]] - ref) / (np.linalg.norm(ref) + 1e-6)
+        assert rel < 5e-2, (b, rel)
+    rel_rot = np.linalg.norm(r16.cpu().numpy() - r_ref.numpy()) / np.linalg.norm(r_ref.numpy())
+    assert rel_rot < 5e-2, rel_rot
+    # and the fp32 path is untouched by switching back and forth
+    np.testing.assert_allclose(p32.cpu().numpy(), p_ref.numpy(), rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)

@@ -12,7 +12,7 @@
 #include <string>
 #include <vector>
 
-#include "ttk_internal.h"
+#include "uplift.h"
 
 namespace {
 
@@ -28,13 +28,6 @@ constexpr int LDW = 132;
 constexpr int THREADS = 256;
 constexpr size_t SMEM_FLOATS = (size_t)MT * (LDX + LDX + LDQ + LDW) + MT * 2 * NF + MT * 2;
 constexpr size_t SMEM_BYTES = SMEM_FLOATS * sizeof(float);
-
-struct LayerW {
-  const float *ln1w, *ln1b, *qkvw, *qkvb, *projw, *invf, *fc1w, *fc1b, *fc2w, *fc2b, *ln2w, *ln2b;
-};
-struct HeadW {
-  const float *w1, *b1, *w2, *b2, *w3, *b3;
-};
 
 enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
 
@@ -327,6 +320,14 @@ __global__ void __launch_bounds__(THREADS, 1) uplift_stack_kernel(StackParams p)
   }
 }
 
+// MyHead on rows of a [n_rows][128] fp32 matrix in global memory; one warp per row (used by the bf16 path).
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ rows, long long n_rows, HeadW hw, float* __restrict__ out) {
+  __shared__ __align__(16) float scratch[8 * 96];
+  const int warp = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r < n_rows) head_row(rows + r * D, hw, out + r * 3, scratch + warp * 96);
+}
+
 // Two-layer embedding (Linear(in_dim,128) -> ReLU -> Linear(128,128)) for 64 tokens per CTA
 // (BallEmbedding / TableEmbedding, model.py:105-158).
 __global__ void __launch_bounds__(THREADS, 1) embed_kernel(const float* __restrict__ in, int in_dim, int in_stride,
@@ -357,28 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) embed_kernel(const float* __restri
   }
 }
 
-struct Param {
-  std::string name;
-  int numel;
-  float* dev = nullptr;
-  bool set = false;
-};
-
 }  // namespace
-
-struct ttk_uplift {
-  int dim, heads, depth, skip;
-  std::vector<Param> params;
-  LayerW* layers_dev = nullptr;    // [4 pos + (depth-4) temporal + 4 second]
-  bool layers_ready = false;
-  int launches = 0;
-  int find(const std::string& n) const {
-    for (size_t i = 0; i < params.size(); ++i)
-      if (params[i].name == n) return (int)i;
-    return -1;
-  }
-  const float* dev(const std::string& n) const { return params[find(n)].dev; }
-};
 
 namespace {
 
@@ -484,7 +464,8 @@ extern "C" int ttk_uplift_create(int dim, int heads, int depth, int use_skipconn
 
 extern "C" void ttk_uplift_destroy(ttk_uplift* h) {
   if (!h) return;
-  for (Param& p : h->params) cudaFree(p.dev);
+  for (UpliftParam& p : h->params) cudaFree(p.dev);
+  cudaFree(h->wmat_dev);
   cudaFree(h->layers_dev);
   delete h;
 }
@@ -500,12 +481,13 @@ extern "C" int ttk_uplift_param_info(const ttk_uplift* h, int i, char* name, int
 
 extern "C" int ttk_uplift_set_param(ttk_uplift* h, int i, const float* data_host, int numel) {
   TTK_CHECK_ARG(h && i >= 0 && i < (int)h->params.size(), "ttk_uplift_set_param: bad index %d", i);
-  Param& p = h->params[i];
+  UpliftParam& p = h->params[i];
   TTK_CHECK_ARG(data_host && numel == p.numel, "ttk_uplift_set_param: %s expects %d elements, got %d", p.name.c_str(), p.numel, numel);
   if (!p.dev) TTK_CUDA(cudaMalloc((void**)&p.dev, (size_t)numel * sizeof(float)));
   TTK_CUDA(cudaMemcpy(p.dev, data_host, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
   p.set = true;
   h->layers_ready = false;
+  h->wmat_ready = false;
   return TTK_OK;
 }
 
@@ -521,12 +503,9 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
                                   const float* times_dev, int batch, int seq_len, int dtype, float* rot_out_dev,
                                   float* pos_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_uplift_forward: null handle");
-  if (dtype != TTK_F32) {
-    ttk_set_error("ttk_uplift_forward: only the fp32 path is implemented in this build");
-    return TTK_ERR_UNSUPPORTED;
-  }
+  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16, "ttk_uplift_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0 && seq_len >= 2 && seq_len + 1 <= MT, "ttk_uplift_forward: seq_len must be in [2, %d] (got %d)", MT - 1, seq_len);
-  for (const Param& p : h->params)
+  for (const UpliftParam& p : h->params)
     if (!p.set) {
       ttk_set_error("ttk_uplift_forward: parameter %s was never set", p.name.c_str());
       return TTK_ERR_STATE;
@@ -566,6 +545,46 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
       h->dev("firststage.table_embed.fc2.weight"), h->dev("firststage.table_embed.fc2.bias"), table_emb);
   TTK_LAUNCH_CHECK();
   h->launches += 2;
+
+  if (dtype == TTK_BF16) {
+    // tensor-core path: tcgen05 GEMMs, residual stream in TMEM (uplift_tc.cu); heads stay fp32
+    if (!h->wmat_ready) {
+      int rc = ttk_uplift_tc_prepare(h);
+      if (rc) return rc;
+    }
+    UpliftIO io;
+    io.ball = ball_dev;
+    io.table = table_dev;
+    io.mask = mask_dev;
+    io.times = times_dev;
+    io.batch = batch;
+    io.T = T;
+    io.rot_out = rot_out_dev;
+    io.pos_out = pos_out_dev;
+    io.X = X;
+    io.table_emb = table_emb;
+    io.second_emb = second_emb;
+    int rc = ttk_uplift_tc_stage(h, MODE_POS, io, st);
+    if (rc) return rc;
+    rc = ttk_uplift_tc_stage(h, MODE_TEMPORAL, io, st);
+    if (rc) return rc;
+    head_kernel<<<ttk_cdiv(ntok, 8), 256, 0, st>>>(X, ntok, head_ptrs(h, "firststage.position_head"), pos_out_dev);
+    TTK_LAUNCH_CHECK();
+    h->launches += 3;
+    if (!h->skip) {
+      embed_kernel<<<ttk_cdiv(ntok, MT), THREADS, SMEM_BYTES, st>>>(pos_out_dev, 3, 3, ntok, h->dev("embed.fc1.weight"),
+                                                                   h->dev("embed.fc1.bias"), h->dev("embed.fc2.weight"),
+                                                                   h->dev("embed.fc2.bias"), second_emb);
+      TTK_LAUNCH_CHECK();
+      h->launches += 1;
+    }
+    rc = ttk_uplift_tc_stage(h, MODE_SECOND, io, st);
+    if (rc) return rc;
+    head_kernel<<<ttk_cdiv(batch, 8), 256, 0, st>>>(table_emb, batch, head_ptrs(h, "rotation_head"), rot_out_dev);
+    TTK_LAUNCH_CHECK();
+    h->launches += 2;
+    return TTK_OK;
+  }
 
   StackParams p;
   p.batch = batch;

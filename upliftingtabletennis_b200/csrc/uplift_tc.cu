@@ -1,0 +1,618 @@
+// Uplifting transformer, bf16 tensor-core path: one fused kernel per stage (table-token layers, temporal
+// layers, second stage) with every Linear layer on tcgen05.mma.
+// Reference: uplifting/model.py:278-300 (SimpleStaticLayer), :186-229 (rotary attention), :335-390, :529-571.
+//
+// A CTA owns 128 token rows (9 table-token sequences of 14, or 2 temporal sequences of <= 64) for ALL layers of a
+// stage:
+//   * the fp32 residual stream lives in TMEM (128 lanes x 128 columns) for the whole stage; thread r owns row r,
+//     so LayerNorm is a per-thread reduction over tcgen05.ld'ed registers and the residual adds are TMEM
+//     read-modify-writes by the same thread;
+//   * GEMM A operands (LayerNorm output, attention output, ReLU(fc1)) are written as bf16 into 128-byte-swizzled
+//     K-major shared tiles, B operands are the weight matrices' own (out, in) rows streamed by TMA from one
+//     [layers*768][128] bf16 matrix through a 3-slot ring, accumulators go to TMEM columns 0..383;
+//   * bias + RoPE + bf16 packing of q/k/v and the 14x14 / 50x50 masked safe-softmax attention run on CUDA cores
+//     out of shared memory.
+#include <cuda.h>
+
+#include "uplift.h"
+
+namespace {
+
+constexpr int D = 128, HEADS = 4, HD = 32, NF = 16, NTAB = 13;
+constexpr int TC_THREADS = 256;
+constexpr int ROWS = 128;
+constexpr int CHUNK_BYTES = 32768;                 // 128 weight rows x 128 K bf16 = two 16 KB K-halves
+constexpr int SA_BYTES = 32768, SQ_BYTES = 128 * 384 * 2, SW_BYTES = 3 * CHUNK_BYTES;
+constexpr int TC_SMEM = 1024 + SA_BYTES + SQ_BYTES + SW_BYTES;
+constexpr int LAYER_ROWS = 768;                    // qkv 384 | proj 128 | fc1 128 | fc2 128
+
+enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n\t"
+      "@p bra LAB_DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "LAB_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;      // 8 rows x 128 B between core-matrix groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t IDESC_128x128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(IDESC_128x128), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+        "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]), "=r"(u[17]), "=r"(u[18]),
+        "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
+        "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]), "r"(u[10]),
+      "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15]), "r"(u[16]), "r"(u[17]), "r"(u[18]), "r"(u[19]), "r"(u[20]),
+      "r"(u[21]), "r"(u[22]), "r"(u[23]), "r"(u[24]), "r"(u[25]), "r"(u[26]), "r"(u[27]), "r"(u[28]), "r"(u[29]), "r"(u[30]),
+      "r"(u[31])
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// byte offset of element (row, col) of a [128 x 128] bf16 A/B operand stored as two 128-byte-swizzled K-halves
+__device__ __forceinline__ uint32_t a_off(int row, int col) {
+  const int kh = col >> 6, b = (col & 63) * 2;
+  return kh * 16384 + row * 128 + ((((b >> 4) ^ (row & 7)) << 4) | (b & 15));
+}
+
+struct TcParams {
+  const LayerW* layers;
+  int n_layers, layer_first;      // index of the stage's first layer in the weight matrix
+  int batch, T;
+  float* X;
+  const float* table_emb;
+  const float* table;
+  const float* mask;
+  const float* times;
+  const float* cls;
+  const float* second_in;
+  float* out_rows;                // POS/TEMPORAL: X; SECOND: [batch][128] cls rows
+};
+
+// LayerNorm of the row held in v[128] -> bf16 A operand row
+__device__ __forceinline__ void ln_row_to_sA(const float* v, int row, uint8_t* sA, const float* __restrict__ g, const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) s += v[i];
+  const float mean = s * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    const float d = v[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = rsqrtf(q * (1.f / D) + 1e-5f);
+#pragma unroll
+  for (int c = 0; c < D; c += 8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = c + 2 * j;
+      const float y0 = (v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i);
+      const float y1 = (v[i + 1] - mean) * rstd * __ldg(g + i + 1) + __ldg(b + i + 1);
+      w[j] = pack_bf16(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_constant__ CUtensorMap wmap, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sQ = sA + SA_BYTES;                  // [128][384] bf16; its first 32 KB doubles as the fc2 A operand
+  uint8_t* sW = sQ + SQ_BYTES;
+  __shared__ float sMask[ROWS];
+  __shared__ float sTime[ROWS];
+  __shared__ uint64_t bars[4];                  // full[3], mma
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_full = smem_u32(bars), bar_mma = bar_full + 24;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;       // TMEM lane of this thread (warps w and w+4 share a lane quarter)
+  const bool row_thread = tid < ROWS;
+  const int T = p.T;
+  const int S = MODE == MODE_POS ? NTAB + 1 : (MODE == MODE_TEMPORAL ? T : T + 1);
+  const int SSTRIDE = MODE == MODE_POS ? NTAB + 1 : 64;
+  const int G = MODE == MODE_POS ? 9 : 2;
+  const long long n_seq = MODE == MODE_POS ? (long long)p.batch * T : p.batch;
+  const long long seq0 = (long long)blockIdx.x * G;
+  const float NEG_INF = -INFINITY;
+
+  if (tid == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(bar_full + 8 * i, 1);
+    mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // per-row sequence bookkeeping
+  const int g_row = row / SSTRIDE, s_row = row - g_row * SSTRIDE;
+  const long long seq_row = seq0 + g_row;
+  const bool valid = g_row < G && s_row < S && seq_row < n_seq;
+  float t_row = __int_as_float(0x7fc00000);     // NaN: no rotation (cls token / padding row)
+  if (tid < ROWS) {
+    float m = NEG_INF;
+    if (valid) {
+      m = 0.f;
+      if (MODE == MODE_POS) {
+        if (s_row > 0) {
+          const long long b = seq_row / T;
+          m = p.table[(b * NTAB + (s_row - 1)) * 3 + 2] == 1.f ? 0.f : NEG_INF;
+          t_row = (float)(s_row - 1) / 100.f;
+        }
+      } else if (MODE == MODE_TEMPORAL) {
+        m = p.mask[seq_row * T + s_row] == 0.f ? NEG_INF : 0.f;
+        t_row = p.times[seq_row * T + s_row];
+      } else if (s_row > 0) {
+        m = p.mask[seq_row * T + (s_row - 1)] == 0.f ? NEG_INF : 0.f;
+        t_row = p.times[seq_row * T + (s_row - 1)];
+      }
+    }
+    sMask[row] = m;
+    sTime[row] = t_row;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  constexpr uint32_t COL_X = 384;
+
+  // rotary table of this thread's row (both warp groups keep a copy): angle = rint(t / 0.002) * inv_freq
+  float rc[NF], rs[NF];
+  {
+    const float t = sTime[row];
+    const float* invf = p.layers[0].invf;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      rc[f] = 1.f;
+      rs[f] = 0.f;
+      if (t == t) {
+        const float pos = rintf(__fdiv_rn(t, 0.002f));
+        sincosf(__fmul_rn(pos, __ldg(invf + f)), &rs[f], &rc[f]);
+      }
+    }
+  }
+
+  const int total_chunks = p.n_layers * 6;
+  auto issue_load = [&](int gchunk) {           // thread 0 only
+    if (gchunk >= total_chunks) return;
+    const int slot = gchunk % 3;
+    const int wrow = (p.layer_first + gchunk / 6) * LAYER_ROWS + (gchunk % 6) * 128;
+    mbar_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
+    const uint32_t dst = smem_u32(sW + slot * CHUNK_BYTES);
+    tma_load_2d(dst, &wmap, bar_full + 8 * slot, 0, wrow);
+    tma_load_2d(dst + 16384, &wmap, bar_full + 8 * slot, 64, wrow);
+  };
+  auto gemm = [&](int gchunk, uint32_t a_base, uint32_t col) {   // thread 0 only: D[128 x 128] at TMEM column `col`
+    const int slot = gchunk % 3;
+    mbar_wait(bar_full + 8 * slot, (gchunk / 3) & 1);
+    tc_fence_after();
+    const uint32_t b_base = smem_u32(sW + slot * CHUNK_BYTES);
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+      for (int k16 = 0; k16 < 4; ++k16)
+        umma(tmem + col, make_desc_sw128(a_base + kh * 16384 + k16 * 32), make_desc_sw128(b_base + kh * 16384 + k16 * 32),
+             (kh | k16) != 0 ? 1u : 0u);
+  };
+  uint32_t mma_phase = 0;
+  auto mma_sync = [&]() {                       // all threads: wait for the committed MMAs
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+  };
+
+  if (tid == 0) {
+    issue_load(0);
+    issue_load(1);
+    issue_load(2);
+  }
+
+  // ---- prologue: residual rows -> TMEM, first LayerNorm -> sA --------------------------------
+  float v[D];
+  if (row_thread) {
+    const float* src = nullptr;
+    if (valid) {
+      if (MODE == MODE_POS) {
+        const long long b = seq_row / T;
+        src = s_row == 0 ? p.X + seq_row * D : p.table_emb + (b * NTAB + (s_row - 1)) * D;
+      } else if (MODE == MODE_TEMPORAL) {
+        src = p.X + (seq_row * T + s_row) * D;
+      } else {
+        src = s_row == 0 ? p.cls : p.second_in + (seq_row * T + (s_row - 1)) * D;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) q = __ldg(reinterpret_cast<const float4*>(src + c));
+      v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+    }
+#pragma unroll
+    for (int c = 0; c < D; c += 32) tmem_st32(lane_base + COL_X + c, v + c);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    ln_row_to_sA(v, row, sA, p.layers[0].ln1w, p.layers[0].ln1b);
+  }
+
+  const float scale = 0.17677669529663687f;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const LayerW lw = p.layers[l];
+    const int g0 = l * 6;
+    // ---- QKV GEMM ---------------------------------------------------------------------------
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      gemm(g0 + 0, smem_u32(sA), 0);
+      gemm(g0 + 1, smem_u32(sA), 128);
+      gemm(g0 + 2, smem_u32(sA), 256);
+      umma_commit(bar_mma);
+    }
+    mma_sync();
+    if (tid == 0) {
+      issue_load(g0 + 3);
+      issue_load(g0 + 4);
+      issue_load(g0 + 5);
+    }
+    // ---- q/k/v epilogue: bias, RoPE (q, k), bf16 -> sQ; warps 0-3 take columns 0..191, warps 4-7 192..383 --------
+    {
+      const int cbase = (warp >> 2) * 192;
+#pragma unroll 1
+      for (int c0 = cbase; c0 < cbase + 192; c0 += 32) {
+        float a[32];
+        tmem_ld32(lane_base + c0, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] += __ldg(lw.qkvb + c0 + j);
+        if (c0 < 256) {           // one head of q or k: rotate pairs (2f, 2f+1)
+#pragma unroll
+          for (int f = 0; f < NF; ++f) {
+            const float x0 = a[2 * f], x1 = a[2 * f + 1];
+            a[2 * f] = x0 * rc[f] - x1 * rs[f];
+            a[2 * f + 1] = x0 * rs[f] + x1 * rc[f];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(sQ + (size_t)row * 768 + c0 * 2);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          dst[q4] = make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                               pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- attention on CUDA cores: one warp per (row, head); writes the bf16 A operand of the projection --------
+    for (int item = warp; item < ROWS * HEADS; item += TC_THREADS / 32) {
+      const int r = item >> 2, hh = item & 3;
+      const int gr = r / SSTRIDE;
+      const int k0 = gr * SSTRIDE;
+      const float mq = sMask[r];
+      const uint4* qp = reinterpret_cast<const uint4*>(sQ + (size_t)r * 768 + hh * 64);
+      uint4 qv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = qp[i];
+      float sc[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        float val = NEG_INF;
+        if (j < S && gr < G) {
+          const uint4* kp = reinterpret_cast<const uint4*>(sQ + (size_t)(k0 + j) * 768 + 256 + hh * 64);
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 kv = kp[i];
+            const uint32_t qa[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              acc = fmaf(bf_lo(qa[w]), bf_lo(ka[w]), acc);
+              acc = fmaf(bf_hi(qa[w]), bf_hi(ka[w]), acc);
+            }
+          }
+          val = acc * scale + (sMask[k0 + j] + mq);
+        }
+        sc[u] = val;
+      }
+      float mx = fmaxf(sc[0], sc[1]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float e0 = 0.f, e1 = 0.f, inv = 0.f;
+      if (mx != NEG_INF) {
+        e0 = sc[0] == NEG_INF ? 0.f : __expf(sc[0] - mx);
+        e1 = sc[1] == NEG_INF ? 0.f : __expf(sc[1] - mx);
+        float sum = e0 + e1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        inv = 1.f / sum;
+      }
+      e0 *= inv;
+      e1 *= inv;
+      float acc = 0.f;
+      if (gr < G) {
+        const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(sQ) + (size_t)k0 * 384 + 256 + hh * HD + lane;
+        for (int j = 0; j < S; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, j < 32 ? e0 : e1, j & 31);
+          acc = fmaf(pj, __bfloat162float(vp[(size_t)j * 384]), acc);
+        }
+      }
+      *reinterpret_cast<__nv_bfloat16*>(sA + a_off(r, hh * HD + lane)) = __float2bfloat16_rn(acc);
+    }
+    // ---- projection GEMM (no bias, model.py:268) -------------------------------------------
+    proxy_fence();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      gemm(g0 + 3, smem_u32(sA), 0);
+      umma_commit(bar_mma);
+    }
+    mma_sync();
+    if (tid == 0) issue_load(g0 + 6);
+    // ---- x += proj ; LayerNorm 2 -> sA ---------------------------------------------------
+    if (row_thread) {
+#pragma unroll
+      for (int c = 0; c < D; c += 32) {
+        float a[32];
+        tmem_ld32(lane_base + c, a);
+        tmem_ld32(lane_base + COL_X + c, v + c);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c + j] += a[j];
+        tmem_st32(lane_base + COL_X + c, v + c);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ln_row_to_sA(v, row, sA, lw.ln2w, lw.ln2b);
+    }
+    // ---- fc1 GEMM ---------------------------------------------------------------------------
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      gemm(g0 + 4, smem_u32(sA), 128);
+      umma_commit(bar_mma);
+    }
+    mma_sync();
+    if (tid == 0) issue_load(g0 + 7);
+    // ---- ReLU(fc1 + b) -> bf16 A operand in the q/k/v buffer; warps 0-3 columns 0..63, warps 4-7 64..127 ----------
+    {
+      const int cbase = (warp >> 2) * 64;
+#pragma unroll 1
+      for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
+        float a[32];
+        tmem_ld32(lane_base + 128 + c0, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j] + __ldg(lw.fc1b + c0 + j), 0.f);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(sQ + a_off(row, c0 + 8 * q4)) =
+              make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                         pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+      }
+    }
+    // ---- fc2 GEMM ---------------------------------------------------------------------------
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      gemm(g0 + 5, smem_u32(sQ), 256);
+      umma_commit(bar_mma);
+    }
+    mma_sync();
+    if (tid == 0) issue_load(g0 + 8);
+    // ---- x += fc2 + b ; next layer's LayerNorm 1 -> sA ---------------------------------------
+    if (row_thread) {
+#pragma unroll
+      for (int c = 0; c < D; c += 32) {
+        float a[32];
+        tmem_ld32(lane_base + 256 + c, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + __ldg(lw.fc2b + c + j);
+        tmem_st32(lane_base + COL_X + c, v + c);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      if (l + 1 < p.n_layers) ln_row_to_sA(v, row, sA, p.layers[l + 1].ln1w, p.layers[l + 1].ln1b);
+    }
+  }
+
+  // ---- epilogue: residual rows back to global memory ---------------------------------------------
+  if (row_thread && valid) {
+    float* dst = nullptr;
+    if (MODE == MODE_POS) {
+      if (s_row == 0) dst = p.out_rows + seq_row * D;
+    } else if (MODE == MODE_TEMPORAL) {
+      dst = p.out_rows + (seq_row * T + s_row) * D;
+    } else if (s_row == 0) {
+      dst = p.out_rows + seq_row * D;
+    }
+    if (dst) {
+#pragma unroll
+      for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* ptr = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeFn)ptr;
+  }
+  return fn;
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+}  // namespace
+
+// Build the [layers*768][128] bf16 weight matrix (qkv | proj | fc1 | fc2 per layer, torch (out, in) rows = K-major).
+int ttk_uplift_tc_prepare(ttk_uplift* h) {
+  const int n_layers = h->depth + 4;
+  const size_t elems = (size_t)n_layers * LAYER_ROWS * D;
+  if (!h->wmat_dev) TTK_CUDA(cudaMalloc((void**)&h->wmat_dev, elems * sizeof(__nv_bfloat16)));
+  std::vector<std::string> prefixes;
+  char buf[96];
+  for (int i = 0; i < 4; ++i) { snprintf(buf, sizeof(buf), "firststage.pos_layers.%d.", i); prefixes.push_back(buf); }
+  for (int i = 0; i < h->depth - 4; ++i) { snprintf(buf, sizeof(buf), "firststage.layers.%d.", i); prefixes.push_back(buf); }
+  for (int i = 0; i < 4; ++i) { snprintf(buf, sizeof(buf), "secondstage.%d.", i); prefixes.push_back(buf); }
+  const float* inv0 = nullptr;
+  for (int l = 0; l < n_layers; ++l) {
+    const std::string& p = prefixes[l];
+    const char* names[4] = {"attn.qkv.weight", "attn.proj.weight", "mlp1.fc1.weight", "mlp1.fc2.weight"};
+    const int rows[4] = {384, 128, 128, 128};
+    size_t off = (size_t)l * LAYER_ROWS * D;
+    for (int m = 0; m < 4; ++m) {
+      const int n = rows[m] * D;
+      pack_weights_kernel<<<ttk_cdiv(n, 256), 256>>>(h->dev(p + names[m]), h->wmat_dev + off, n);
+      TTK_LAUNCH_CHECK();
+      off += n;
+    }
+    if (!inv0) inv0 = h->dev(p + "attn.rotary_emb.inv_freq");
+  }
+  TTK_CUDA(cudaDeviceSynchronize());
+  // the kernels build each row's rotary table once per stage from the first layer's inv_freq (a non-trainable buffer)
+  std::vector<float> a(NF), b(NF);
+  TTK_CUDA(cudaMemcpy(a.data(), inv0, NF * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int l = 1; l < n_layers; ++l) {
+    TTK_CUDA(cudaMemcpy(b.data(), h->dev(prefixes[l] + "attn.rotary_emb.inv_freq"), NF * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < NF; ++f)
+      if (a[f] != b[f]) {
+        ttk_set_error("bf16 uplift path: layers carry different rotary inv_freq tables, which this path does not support");
+        return TTK_ERR_UNSUPPORTED;
+      }
+  }
+  h->wmat_ready = true;
+  return TTK_OK;
+}
+
+int ttk_uplift_tc_stage(ttk_uplift* h, int mode, const UpliftIO& io, cudaStream_t st) {
+  EncodeFn encode = get_encode();
+  if (!encode) {
+    ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return TTK_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_SECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    attr = true;
+  }
+  const int n_layers_total = h->depth + 4;
+  CUtensorMap wmap;
+  cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)n_layers_total * LAYER_ROWS};
+  cuuint64_t strides[1] = {(cuuint64_t)D * 2};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->wmat_dev, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ttk_set_error("cuTensorMapEncodeTiled failed (%d) for the uplift weight matrix", (int)r);
+    return TTK_ERR_CUDA;
+  }
+  TcParams p;
+  p.batch = io.batch;
+  p.T = io.T;
+  p.X = io.X;
+  p.table_emb = io.table_emb;
+  p.table = io.table;
+  p.mask = io.mask;
+  p.times = io.times;
+  p.cls = h->dev("cls_token");
+  p.second_in = h->skip ? io.X : io.second_emb;
+  const long long ntok = (long long)io.batch * io.T;
+  if (mode == MODE_POS) {
+    p.layers = h->layers_dev;
+    p.n_layers = 4;
+    p.layer_first = 0;
+    p.out_rows = io.X;
+    uplift_tc_kernel<MODE_POS><<<ttk_cdiv(ntok, 9), TC_THREADS, TC_SMEM, st>>>(wmap, p);
+  } else if (mode == MODE_TEMPORAL) {
+    p.layers = h->layers_dev + 4;
+    p.n_layers = h->depth - 4;
+    p.layer_first = 4;
+    p.out_rows = io.X;
+    uplift_tc_kernel<MODE_TEMPORAL><<<ttk_cdiv(io.batch, 2), TC_THREADS, TC_SMEM, st>>>(wmap, p);
+  } else {
+    p.layers = h->layers_dev + h->depth;
+    p.n_layers = 4;
+    p.layer_first = h->depth;
+    p.out_rows = io.table_emb;        // dead by now: receives the [batch][128] cls rows
+    uplift_tc_kernel<MODE_SECOND><<<ttk_cdiv(io.batch, 2), TC_THREADS, TC_SMEM, st>>>(wmap, p);
+  }
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}

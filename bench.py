@@ -228,19 +228,29 @@ def main():
     ub_d, ut_d, um_d, uti_d = (a.to(dev) for a in (ub, ut, um, uti))
     up._sync()
 
-    def uplift_device():
-        rot, pos = up.engine.forward(ub_d, ut_d, um_d, uti_d)
-        return ops.rotation_local(rot, pos)
+    def make_uplift(dt):
+        def dev_fn():
+            rot, pos = up.engine.forward(ub_d, ut_d, um_d, uti_d, dt)
+            return ops.rotation_local(rot, pos)
 
-    def uplift_e2e():
-        args_d = [a.to(dev, non_blocking=True) for a in (ub_p, ut_p, um_p, uti_p)]
-        rot, pos = up.engine.forward(*args_d)
-        return ops.rotation_local(rot, pos).cpu(), pos.cpu()
+        def e2e_fn():
+            args_d = [a.to(dev, non_blocking=True) for a in (ub_p, ut_p, um_p, uti_p)]
+            rot, pos = up.engine.forward(*args_d, dt)
+            return ops.rotation_local(rot, pos).cpu(), pos.cpu()
+        return dev_fn, e2e_fn
 
-    ms_up = timed(uplift_device, args.steps, args.warmup)
-    ms_up_e2e = timed(uplift_e2e, args.steps, args.warmup)
-    up_value = world * UPLIFT_BATCH * args.steps / (ms_up * 1e-3)
-    up_e2e = world * UPLIFT_BATCH * args.steps / (ms_up_e2e * 1e-3)
+    up_res = {}
+    for key, dt in (('bf16', torch.bfloat16), ('f32', torch.float32)):
+        dev_fn, e2e_fn = make_uplift(dt)
+        ms_a = timed(dev_fn, args.steps, args.warmup)
+        launches_up = up.engine.last_launches() + 1
+        ms_b = timed(e2e_fn, args.steps, args.warmup)
+        up_res[key] = (world * UPLIFT_BATCH * args.steps / (ms_a * 1e-3), world * UPLIFT_BATCH * args.steps / (ms_b * 1e-3), ms_a / args.steps, launches_up)
+    with torch.no_grad():
+        r32, p32 = up.engine.forward(ub_d, ut_d, um_d, uti_d, torch.float32)
+        r16, p16 = up.engine.forward(ub_d, ut_d, um_d, uti_d, torch.bfloat16)
+        vm = um_d.bool()
+        bf16_rel = float(((p16 - p32)[vm].norm() / p32[vm].norm()).item())
 
     if rank != 0:
         if world > 1:
@@ -329,10 +339,12 @@ def main():
         'clocks': clocks,
         'roofline': roofline,
         'cpu_baseline': cpu,
-        'uplift': {'value': up_value, 'unit': 'trajectories/s', 'dtype': 'f32', 'batch_per_gpu': UPLIFT_BATCH, 'ms_per_step': ms_up / args.steps,
-                   'e2e': {'value': up_e2e, 'unit': 'trajectories/s', 'h2d_bytes_per_step': int(sum(a.numel() * 4 for a in (ub, ut, um, uti))),
+        'uplift': {'value': up_res['bf16'][0], 'unit': 'trajectories/s', 'dtype': 'bf16', 'batch_per_gpu': UPLIFT_BATCH, 'ms_per_step': up_res['bf16'][2],
+                   'e2e': {'value': up_res['bf16'][1], 'unit': 'trajectories/s', 'h2d_bytes_per_step': int(sum(a.numel() * 4 for a in (ub, ut, um, uti))),
                            'd2h_bytes_per_step': UPLIFT_BATCH * (3 + 150) * 4},
-                   'tflops': UPLIFT_GFLOP_PER_TRAJ * up_value / 1e3, 'gpu_launches': up.engine.last_launches() + 1},
+                   'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['bf16'][0] / 1e3, 'tensor_frac': UPLIFT_GFLOP_PER_TRAJ * up_res['bf16'][0] / 1e3 / world / pk['bf16_tflops_sustained'],
+                   'gpu_launches': up_res['bf16'][3], 'bf16_vs_f32_rel_l2': bf16_rel,
+                   'f32': {'value': up_res['f32'][0], 'e2e': up_res['f32'][1], 'ms_per_step': up_res['f32'][2], 'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['f32'][0] / 1e3}},
     }
     print(json.dumps(line))
     if world > 1:

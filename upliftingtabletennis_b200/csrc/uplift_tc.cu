@@ -10,8 +10,11 @@
 //   * GEMM A operands (LayerNorm output, attention output, ReLU(fc1)) are written as bf16 into 128-byte-swizzled
 //     K-major shared tiles, B operands are the weight matrices' own (out, in) rows streamed by TMA from one
 //     [layers*768][128] bf16 matrix through a 3-slot ring, accumulators go to TMEM columns 0..383;
-//   * bias + RoPE + bf16 packing of q/k/v and the 14x14 / 50x50 masked safe-softmax attention run on CUDA cores
-//     out of shared memory.
+//   * attention runs on the tensor cores as well: per head, scores = Q_h K_h^T (128 x 128 block, the rows' own
+//     sequence block is the valid part) land in TMEM, the row-owning thread applies masks + safe softmax and writes
+//     un-normalised probabilities as a bf16 A operand, O_h = P V_h accumulates into TMEM and is scaled by 1/sum in
+//     the epilogue (V is stored transposed, keys contiguous, so it is a K-major B operand);
+//   * bias + RoPE + bf16 packing of q/k/v run on CUDA cores straight out of TMEM.
 #include <cuda.h>
 
 #include "uplift.h"
@@ -60,12 +63,22 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
   d |= (uint64_t)2 << 61;                // SWIZZLE_128B
   return d;
 }
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;       // 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                // SWIZZLE_64B
+  return d;
+}
+constexpr uint32_t IDESC_128x32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 constexpr uint32_t IDESC_128x128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = IDESC_128x128) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(IDESC_128x128), "r"(accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -103,8 +116,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&p);
 }
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // byte offset of element (row, col) of a [128 x 128] bf16 A/B operand stored as two 128-byte-swizzled K-halves
 __device__ __forceinline__ uint32_t a_off(int row, int col) {
@@ -157,9 +168,11 @@ template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_constant__ CUtensorMap wmap, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sQ = sA + SA_BYTES;                  // [128][384] bf16; its first 32 KB doubles as the fc2 A operand
-  uint8_t* sW = sQ + SQ_BYTES;
+  uint8_t* sA = smem;                           // LN output / probabilities P / attention output (A operands, 2 x SW128 halves)
+  uint8_t* sQh = sA + SA_BYTES;                 // 4 heads x [128 rows][64 B] SW64 (q); later the fc2 A operand
+  uint8_t* sKh = sQh + 32768;                   // 4 heads x [128 rows][64 B] SW64 (k)
+  uint8_t* sVt = sKh + 32768;                   // 4 heads x [32 dims][128 keys] as 2 SW128 halves (v transposed)
+  uint8_t* sW = sVt + 32768;
   __shared__ float sMask[ROWS];
   __shared__ float sTime[ROWS];
   __shared__ uint64_t bars[4];                  // full[3], mma
@@ -189,9 +202,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   const int g_row = row / SSTRIDE, s_row = row - g_row * SSTRIDE;
   const long long seq_row = seq0 + g_row;
   const bool valid = g_row < G && s_row < S && seq_row < n_seq;
-  float t_row = __int_as_float(0x7fc00000);     // NaN: no rotation (cls token / padding row)
   if (tid < ROWS) {
-    float m = NEG_INF;
+    float m = NEG_INF, t_row = __int_as_float(0x7fc00000);     // NaN time: no rotation (cls token / padding row)
     if (valid) {
       m = 0.f;
       if (MODE == MODE_POS) {
@@ -216,7 +228,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr uint32_t COL_X = 384;
+  constexpr uint32_t COL_X = 384, COL_S = 0, COL_O = 128, COL_PROJ = 256, COL_FC1 = 0, COL_FC2 = 128;
+  const int k_lo = g_row * SSTRIDE, k_hi = (g_row < G) ? k_lo + S : k_lo;      // this row's key block
+  const bool q_live = sMask[row] == 0.f;
 
   // rotary table of this thread's row (both warp groups keep a copy): angle = rint(t / 0.002) * inv_freq
   float rc[NF], rs[NF];
@@ -262,6 +276,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_phase ^= 1;
     tc_fence_after();
   };
+  // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  Row threads only; v is local to the call.
+  auto residual_ln = [&](bool add, uint32_t col_delta, const float* bias, const float* lnw, const float* lnb, bool do_ln, float* out_global) {
+    float v[D];
+#pragma unroll
+    for (int c = 0; c < D; c += 32) {
+      tmem_ld32(lane_base + COL_X + c, v + c);
+      if (add) {
+        float a[32];
+        tmem_ld32(lane_base + col_delta + c, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + (bias ? __ldg(bias + c + j) : 0.f);
+        tmem_st32(lane_base + COL_X + c, v + c);
+      }
+    }
+    if (add) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (do_ln) ln_row_to_sA(v, row, sA, lnw, lnb);
+    if (out_global) {
+#pragma unroll
+      for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(out_global + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+  };
 
   if (tid == 0) {
     issue_load(0);
@@ -270,7 +305,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   }
 
   // ---- prologue: residual rows -> TMEM, first LayerNorm -> sA --------------------------------
-  float v[D];
   if (row_thread) {
     const float* src = nullptr;
     if (valid) {
@@ -283,19 +317,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
         src = s_row == 0 ? p.cls : p.second_in + (seq_row * T + (s_row - 1)) * D;
       }
     }
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      float a[32];
 #pragma unroll
-    for (int c = 0; c < D; c += 4) {
-      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (src) q = __ldg(reinterpret_cast<const float4*>(src + c));
-      v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+      for (int j = 0; j < 32; j += 4) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src) q = __ldg(reinterpret_cast<const float4*>(src + c + j));
+        a[j] = q.x; a[j + 1] = q.y; a[j + 2] = q.z; a[j + 3] = q.w;
+      }
+      tmem_st32(lane_base + COL_X + c, a);
     }
-#pragma unroll
-    for (int c = 0; c < D; c += 32) tmem_st32(lane_base + COL_X + c, v + c);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    ln_row_to_sA(v, row, sA, p.layers[0].ln1w, p.layers[0].ln1b);
+    residual_ln(false, 0, nullptr, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
   }
 
-  const float scale = 0.17677669529663687f;
+  const float scale = 0.17677669529663687f;     // 1/sqrt(32)
   for (int l = 0; l < p.n_layers; ++l) {
     const LayerW lw = p.layers[l];
     const int g0 = l * 6;
@@ -316,135 +353,152 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       issue_load(g0 + 4);
       issue_load(g0 + 5);
     }
-    // ---- q/k/v epilogue: bias, RoPE (q, k), bf16 -> sQ; warps 0-3 take columns 0..191, warps 4-7 192..383 --------
+    // ---- q/k/v epilogue: bias, RoPE (q, k), bf16 operands; warps 0-3 take columns 0..191, warps 4-7 192..383 -----
     {
       const int cbase = (warp >> 2) * 192;
 #pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + 192; c0 += 32) {
+      for (int c0 = cbase; c0 < cbase + 192; c0 += 32) {        // one head of q, k or v per step
         float a[32];
         tmem_ld32(lane_base + c0, a);
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] += __ldg(lw.qkvb + c0 + j);
-        if (c0 < 256) {           // one head of q or k: rotate pairs (2f, 2f+1)
+        const int hh = (c0 >> 5) & 3;
+        if (c0 < 256) {
 #pragma unroll
-          for (int f = 0; f < NF; ++f) {
+          for (int f = 0; f < NF; ++f) {                         // rotate pairs (2f, 2f+1)
             const float x0 = a[2 * f], x1 = a[2 * f + 1];
             a[2 * f] = x0 * rc[f] - x1 * rs[f];
             a[2 * f + 1] = x0 * rs[f] + x1 * rc[f];
           }
-        }
-        uint4* dst = reinterpret_cast<uint4*>(sQ + (size_t)row * 768 + c0 * 2);
+          uint8_t* base = (c0 < 128 ? sQh : sKh) + hh * 8192 + row * 64;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          dst[q4] = make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
-                               pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+          for (int q4 = 0; q4 < 4; ++q4)                         // 64-byte swizzle: 16-byte chunk ^= (row >> 1) & 3
+            *reinterpret_cast<uint4*>(base + ((q4 ^ ((row >> 1) & 3)) << 4)) =
+                make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                           pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+        } else {
+          // v transposed: element (dim n, key = row) of head hh; keys contiguous, two 128-byte-swizzled halves
+          uint8_t* base = sVt + hh * 8192 + (row >> 6) * 4096;
+          const int b = (row & 63) * 2;
+#pragma unroll
+          for (int n = 0; n < 32; ++n)
+            *reinterpret_cast<__nv_bfloat16*>(base + n * 128 + ((((b >> 4) ^ (n & 7)) << 4) | (b & 15))) = __float2bfloat16_rn(a[n]);
+        }
       }
     }
-    tc_fence_before();
-    __syncthreads();
-    // ---- attention on CUDA cores: one warp per (row, head); writes the bf16 A operand of the projection --------
-    for (int item = warp; item < ROWS * HEADS; item += TC_THREADS / 32) {
-      const int r = item >> 2, hh = item & 3;
-      const int gr = r / SSTRIDE;
-      const int k0 = gr * SSTRIDE;
-      const float mq = sMask[r];
-      const uint4* qp = reinterpret_cast<const uint4*>(sQ + (size_t)r * 768 + hh * 64);
-      uint4 qv[4];
+    // ---- attention per head on the tensor cores ---------------------------------------------------
+    float inv_sum[HEADS];
+#pragma unroll 1
+    for (int hh = 0; hh < HEADS; ++hh) {
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQh + hh * 8192), ka = smem_u32(sKh + hh * 8192);
+        umma(tmem + COL_S, make_desc_sw64(qa), make_desc_sw64(ka), 0u);
+        umma(tmem + COL_S, make_desc_sw64(qa + 32), make_desc_sw64(ka + 32), 1u);
+        umma_commit(bar_mma);
+      }
+      mma_sync();
+      if (row_thread) {
+        // masks + safe softmax of this row over its own sequence block; un-normalised bf16 probabilities -> sA
+        float mx = NEG_INF;
+#pragma unroll 1
+        for (int c = 0; c < ROWS; c += 32) {
+          float a[32];
+          tmem_ld32(lane_base + COL_S + c, a);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) qv[i] = qp[i];
-      float sc[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = lane + 32 * u;
-        float val = NEG_INF;
-        if (j < S && gr < G) {
-          const uint4* kp = reinterpret_cast<const uint4*>(sQ + (size_t)(k0 + j) * 768 + 256 + hh * 64);
-          float acc = 0.f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 kv = kp[i];
-            const uint32_t qa[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w}, ka[4] = {kv.x, kv.y, kv.z, kv.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              acc = fmaf(bf_lo(qa[w]), bf_lo(ka[w]), acc);
-              acc = fmaf(bf_hi(qa[w]), bf_hi(ka[w]), acc);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int key = c + j;
+            if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) mx = fmaxf(mx, a[j] * scale);
           }
-          val = acc * scale + (sMask[k0 + j] + mq);
         }
-        sc[u] = val;
-      }
-      float mx = fmaxf(sc[0], sc[1]);
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < ROWS; c += 32) {
+          float a[32];
+          tmem_ld32(lane_base + COL_S + c, a);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      float e0 = 0.f, e1 = 0.f, inv = 0.f;
-      if (mx != NEG_INF) {
-        e0 = sc[0] == NEG_INF ? 0.f : __expf(sc[0] - mx);
-        e1 = sc[1] == NEG_INF ? 0.f : __expf(sc[1] - mx);
-        float sum = e0 + e1;
+          for (int j = 0; j < 32; ++j) {
+            const int key = c + j;
+            float e = 0.f;
+            if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) e = __expf(a[j] * scale - mx);
+            sum += e;
+            a[j] = e;
+          }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        inv = 1.f / sum;
-      }
-      e0 *= inv;
-      e1 *= inv;
-      float acc = 0.f;
-      if (gr < G) {
-        const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(sQ) + (size_t)k0 * 384 + 256 + hh * HD + lane;
-        for (int j = 0; j < S; ++j) {
-          const float pj = __shfl_sync(0xffffffffu, j < 32 ? e0 : e1, j & 31);
-          acc = fmaf(pj, __bfloat162float(vp[(size_t)j * 384]), acc);
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(sA + a_off(row, c + 8 * q4)) =
+                make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                           pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
         }
+        inv_sum[hh] = sum > 0.f ? 1.f / sum : 0.f;      // fully masked row -> zero output (safe softmax)
       }
-      *reinterpret_cast<__nv_bfloat16*>(sA + a_off(r, hh * HD + lane)) = __float2bfloat16_rn(acc);
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sA), va = smem_u32(sVt + hh * 8192);
+#pragma unroll
+        for (int k16 = 0; k16 < 8; ++k16)
+          umma(tmem + COL_O + hh * HD, make_desc_sw128(pa + (k16 >> 2) * 16384 + (k16 & 3) * 32),
+               make_desc_sw128(va + (k16 >> 2) * 4096 + (k16 & 3) * 32), k16 != 0 ? 1u : 0u, IDESC_128x32);
+        umma_commit(bar_mma);
+      }
+      mma_sync();       // P (sA) is free again, O_h is complete
+    }
+    // ---- attention output: O_h / sum -> bf16 A operand of the projection --------------------------------
+    if (row_thread) {
+#pragma unroll
+      for (int hh = 0; hh < HEADS; ++hh) {
+        float a[32];
+        tmem_ld32(lane_base + COL_O + hh * HD, a);
+        const float is = inv_sum[hh];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(sA + a_off(row, hh * HD + 8 * q4)) =
+              make_uint4(pack_bf16(a[8 * q4] * is, a[8 * q4 + 1] * is), pack_bf16(a[8 * q4 + 2] * is, a[8 * q4 + 3] * is),
+                         pack_bf16(a[8 * q4 + 4] * is, a[8 * q4 + 5] * is), pack_bf16(a[8 * q4 + 6] * is, a[8 * q4 + 7] * is));
+      }
     }
     // ---- projection GEMM (no bias, model.py:268) -------------------------------------------
     proxy_fence();
+    tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      gemm(g0 + 3, smem_u32(sA), 0);
+      gemm(g0 + 3, smem_u32(sA), COL_PROJ);
       umma_commit(bar_mma);
     }
     mma_sync();
     if (tid == 0) issue_load(g0 + 6);
     // ---- x += proj ; LayerNorm 2 -> sA ---------------------------------------------------
-    if (row_thread) {
-#pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        float a[32];
-        tmem_ld32(lane_base + c, a);
-        tmem_ld32(lane_base + COL_X + c, v + c);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[c + j] += a[j];
-        tmem_st32(lane_base + COL_X + c, v + c);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      ln_row_to_sA(v, row, sA, lw.ln2w, lw.ln2b);
-    }
+    if (row_thread) residual_ln(true, COL_PROJ, nullptr, lw.ln2w, lw.ln2b, true, nullptr);
     // ---- fc1 GEMM ---------------------------------------------------------------------------
     proxy_fence();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      gemm(g0 + 4, smem_u32(sA), 128);
+      gemm(g0 + 4, smem_u32(sA), COL_FC1);
       umma_commit(bar_mma);
     }
     mma_sync();
     if (tid == 0) issue_load(g0 + 7);
-    // ---- ReLU(fc1 + b) -> bf16 A operand in the q/k/v buffer; warps 0-3 columns 0..63, warps 4-7 64..127 ----------
+    // ---- ReLU(fc1 + b) -> bf16 A operand (in the q buffer); warps 0-3 columns 0..63, warps 4-7 64..127 ----------
     {
       const int cbase = (warp >> 2) * 64;
 #pragma unroll 1
       for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
         float a[32];
-        tmem_ld32(lane_base + 128 + c0, a);
+        tmem_ld32(lane_base + COL_FC1 + c0, a);
 #pragma unroll
         for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j] + __ldg(lw.fc1b + c0 + j), 0.f);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(sQ + a_off(row, c0 + 8 * q4)) =
+          *reinterpret_cast<uint4*>(sQh + a_off(row, c0 + 8 * q4)) =
               make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
                          pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
       }
@@ -455,39 +509,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      gemm(g0 + 5, smem_u32(sQ), 256);
+      gemm(g0 + 5, smem_u32(sQh), COL_FC2);
       umma_commit(bar_mma);
     }
     mma_sync();
     if (tid == 0) issue_load(g0 + 8);
-    // ---- x += fc2 + b ; next layer's LayerNorm 1 -> sA ---------------------------------------
+    // ---- x += fc2 + b ; next layer's LayerNorm 1 -> sA, or the stage's output rows ---------------------
     if (row_thread) {
-#pragma unroll
-      for (int c = 0; c < D; c += 32) {
-        float a[32];
-        tmem_ld32(lane_base + 256 + c, a);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + __ldg(lw.fc2b + c + j);
-        tmem_st32(lane_base + COL_X + c, v + c);
+      const bool last = l + 1 == p.n_layers;
+      float* dst = nullptr;
+      if (last && valid) {
+        if (MODE == MODE_POS) {
+          if (s_row == 0) dst = p.out_rows + seq_row * D;
+        } else if (MODE == MODE_TEMPORAL) {
+          dst = p.out_rows + (seq_row * T + s_row) * D;
+        } else if (s_row == 0) {
+          dst = p.out_rows + seq_row * D;
+        }
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      if (l + 1 < p.n_layers) ln_row_to_sA(v, row, sA, p.layers[l + 1].ln1w, p.layers[l + 1].ln1b);
-    }
-  }
-
-  // ---- epilogue: residual rows back to global memory ---------------------------------------------
-  if (row_thread && valid) {
-    float* dst = nullptr;
-    if (MODE == MODE_POS) {
-      if (s_row == 0) dst = p.out_rows + seq_row * D;
-    } else if (MODE == MODE_TEMPORAL) {
-      dst = p.out_rows + (seq_row * T + s_row) * D;
-    } else if (s_row == 0) {
-      dst = p.out_rows + seq_row * D;
-    }
-    if (dst) {
-#pragma unroll
-      for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      const LayerW& nx = p.layers[last ? l : l + 1];
+      residual_ln(true, COL_FC2, lw.fc2b, nx.ln1w, nx.ln1b, !last, dst);
     }
   }
   tc_fence_before();

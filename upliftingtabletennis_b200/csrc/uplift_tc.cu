@@ -26,7 +26,7 @@ constexpr int TC_THREADS = 256;
 constexpr int ROWS = 128;
 constexpr int CHUNK_BYTES = 32768;                 // 128 weight rows x 128 K bf16 = two 16 KB K-halves
 constexpr int SA_BYTES = 32768, SQ_BYTES = 128 * 384 * 2, SW_BYTES = 3 * CHUNK_BYTES;
-constexpr int TC_SMEM = 1024 + SA_BYTES + SQ_BYTES + SW_BYTES;
+constexpr int TC_SMEM = SA_BYTES + SQ_BYTES + SW_BYTES;
 constexpr int LAYER_ROWS = 768;                    // qkv 384 | proj 128 | fc1 128 | fc2 128
 
 enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
@@ -137,37 +137,10 @@ struct TcParams {
   float* out_rows;                // POS/TEMPORAL: X; SECOND: [batch][128] cls rows
 };
 
-// LayerNorm of the row held in v[128] -> bf16 A operand row
-__device__ __forceinline__ void ln_row_to_sA(const float* v, int row, uint8_t* sA, const float* __restrict__ g, const float* __restrict__ b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < D; ++i) s += v[i];
-  const float mean = s * (1.f / D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < D; ++i) {
-    const float d = v[i] - mean;
-    q = fmaf(d, d, q);
-  }
-  const float rstd = rsqrtf(q * (1.f / D) + 1e-5f);
-#pragma unroll
-  for (int c = 0; c < D; c += 8) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i = c + 2 * j;
-      const float y0 = (v[i] - mean) * rstd * __ldg(g + i) + __ldg(b + i);
-      const float y1 = (v[i + 1] - mean) * rstd * __ldg(g + i + 1) + __ldg(b + i + 1);
-      w[j] = pack_bf16(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_constant__ CUtensorMap wmap, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled operand tiles need 1024-byte alignment
   uint8_t* sA = smem;                           // LN output / probabilities P / attention output (A operands, 2 x SW128 halves)
   uint8_t* sQh = sA + SA_BYTES;                 // 4 heads x [128 rows][64 B] SW64 (q); later the fc2 A operand
   uint8_t* sKh = sQh + 32768;                   // 4 heads x [128 rows][64 B] SW64 (k)
@@ -175,6 +148,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   uint8_t* sW = sVt + 32768;
   __shared__ float sMask[ROWS];
   __shared__ float sTime[ROWS];
+  __shared__ float2 sRed[ROWS];                 // per-row (sum, sum of squares) exchange between the two column halves
   __shared__ uint64_t bars[4];                  // full[3], mma
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(bars), bar_mma = bar_full + 24;
@@ -276,27 +250,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_phase ^= 1;
     tc_fence_after();
   };
-  // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  Row threads only; v is local to the call.
+  // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  ALL threads: warps w and w+4 own the two 64-column halves
+  // of row `row` and exchange their partial (sum, sum of squares) through shared memory.
+  const int chalf = (warp >> 2) * 64;
   auto residual_ln = [&](bool add, uint32_t col_delta, const float* bias, const float* lnw, const float* lnb, bool do_ln, float* out_global) {
-    float v[D];
+    float v[64];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < D; c += 32) {
-      tmem_ld32(lane_base + COL_X + c, v + c);
+    for (int c = 0; c < 64; c += 32) {
+      tmem_ld32(lane_base + COL_X + chalf + c, v + c);
       if (add) {
         float a[32];
-        tmem_ld32(lane_base + col_delta + c, a);
+        tmem_ld32(lane_base + col_delta + chalf + c, a);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + (bias ? __ldg(bias + c + j) : 0.f);
-        tmem_st32(lane_base + COL_X + c, v + c);
+        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + (bias ? __ldg(bias + chalf + c + j) : 0.f);
+        tmem_st32(lane_base + COL_X + chalf + c, v + c);
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s1 += v[c + j];
+        s2 = fmaf(v[c + j], v[c + j], s2);
       }
     }
     if (add) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (do_ln) ln_row_to_sA(v, row, sA, lnw, lnb);
     if (out_global) {
 #pragma unroll
-      for (int c = 0; c < D; c += 4) *reinterpret_cast<float4*>(out_global + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(out_global + chalf + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+    }
+    if (!do_ln) return;
+    if (warp >= 4) sRed[row] = make_float2(s1, s2);
+    __syncthreads();
+    if (warp < 4) {
+      const float2 o = sRed[row];
+      s1 += o.x;
+      s2 += o.y;
+      sRed[row] = make_float2(s1, s2);
+    }
+    __syncthreads();
+    const float2 t = sRed[row];
+    const float mean = t.x * (1.f / D);
+    const float var = fmaxf(t.y * (1.f / D) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = c + 2 * j;
+        const float y0 = (v[i] - mean) * rstd * __ldg(lnw + chalf + i) + __ldg(lnb + chalf + i);
+        const float y1 = (v[i + 1] - mean) * rstd * __ldg(lnw + chalf + i + 1) + __ldg(lnb + chalf + i + 1);
+        w[j] = pack_bf16(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(sA + a_off(row, chalf + c)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   };
+  // valid keys of this row inside its warp's 64-column score window (fixed for the whole stage)
+  const int r0 = (warp & 3) * 32;
+  const int c_start = MODE == MODE_POS ? min(((r0 / SSTRIDE) * SSTRIDE) & ~7, 64) : (r0 >> 6) * 64;
+  unsigned long long key_bits = 0ull;
+  for (int j = 0; j < 64; ++j) {
+    const int key = c_start + j;
+    if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) key_bits |= 1ull << j;
+  }
 
   if (tid == 0) {
     issue_load(0);
@@ -305,7 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   }
 
   // ---- prologue: residual rows -> TMEM, first LayerNorm -> sA --------------------------------
-  if (row_thread) {
+  {
     const float* src = nullptr;
     if (valid) {
       if (MODE == MODE_POS) {
@@ -318,15 +333,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       }
     }
 #pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
+    for (int c = 0; c < 64; c += 32) {
       float a[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src) q = __ldg(reinterpret_cast<const float4*>(src + c + j));
+        if (src) q = __ldg(reinterpret_cast<const float4*>(src + chalf + c + j));
         a[j] = q.x; a[j + 1] = q.y; a[j + 2] = q.z; a[j + 3] = q.w;
       }
-      tmem_st32(lane_base + COL_X + c, a);
+      tmem_st32(lane_base + COL_X + chalf + c, a);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     residual_ln(false, 0, nullptr, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
@@ -402,38 +417,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       }
       mma_sync();
       if (row_thread) {
-        // masks + safe softmax of this row over its own sequence block; un-normalised bf16 probabilities -> sA
+        // masks + safe softmax of this row over its warp's 64-column window; un-normalised bf16 probabilities -> sA
+        float e[64];
+        tmem_ld32(lane_base + COL_S + c_start, e);
+        tmem_ld32(lane_base + COL_S + c_start + 32, e + 32);
         float mx = NEG_INF;
-#pragma unroll 1
-        for (int c = 0; c < ROWS; c += 32) {
-          float a[32];
-          tmem_ld32(lane_base + COL_S + c, a);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = c + j;
-            if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) mx = fmaxf(mx, a[j] * scale);
-          }
+        for (int j = 0; j < 64; ++j) {
+          e[j] *= scale;
+          if ((key_bits >> j) & 1ull) mx = fmaxf(mx, e[j]);
         }
         float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < ROWS; c += 32) {
-          float a[32];
-          tmem_ld32(lane_base + COL_S + c, a);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = c + j;
-            float e = 0.f;
-            if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) e = __expf(a[j] * scale - mx);
-            sum += e;
-            a[j] = e;
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(sA + a_off(row, c + 8 * q4)) =
-                make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
-                           pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+        for (int j = 0; j < 64; ++j) {
+          e[j] = ((key_bits >> j) & 1ull) ? __expf(e[j] - mx) : 0.f;
+          sum += e[j];
         }
         inv_sum[hh] = sum > 0.f ? 1.f / sum : 0.f;      // fully masked row -> zero output (safe softmax)
+#pragma unroll
+        for (int jj = 0; jj < 64; jj += 8)
+          *reinterpret_cast<uint4*>(sA + a_off(row, c_start + jj)) =
+              make_uint4(pack_bf16(e[jj], e[jj + 1]), pack_bf16(e[jj + 2], e[jj + 3]), pack_bf16(e[jj + 4], e[jj + 5]), pack_bf16(e[jj + 6], e[jj + 7]));
+        for (int c = 0; c < c_start; c += 8) *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(0, 0, 0, 0);
+        for (int c = c_start + 64; c < ROWS; c += 8) *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(0, 0, 0, 0);
       }
       proxy_fence();
       tc_fence_before();
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_sync();
     if (tid == 0) issue_load(g0 + 6);
     // ---- x += proj ; LayerNorm 2 -> sA ---------------------------------------------------
-    if (row_thread) residual_ln(true, COL_PROJ, nullptr, lw.ln2w, lw.ln2b, true, nullptr);
+    residual_ln(true, COL_PROJ, nullptr, lw.ln2w, lw.ln2b, true, nullptr);
     // ---- fc1 GEMM ---------------------------------------------------------------------------
     proxy_fence();
     tc_fence_before();
@@ -515,7 +521,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_sync();
     if (tid == 0) issue_load(g0 + 8);
     // ---- x += fc2 + b ; next layer's LayerNorm 1 -> sA, or the stage's output rows ---------------------
-    if (row_thread) {
+    {
       const bool last = l + 1 == p.n_layers;
       float* dst = nullptr;
       if (last && valid) {

@@ -196,18 +196,25 @@ def _uplifting_transform(ball_coords, table_coords, times):
 # ---- public classes ---------------------------------------------------------------------------------
 class _Detector:
     frames_per_stack = 1
-    chunk = 32                     # stacks per network launch (bounds the activation workspace)
+    chunk = 8                      # stacks per network pass: bounds the workspace and lets uploads overlap compute
 
-    def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps):
-        """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None."""
+    def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps, ready=None):
+        """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None.
+        `ready`: [(last frame index, event)] from _upload -- a chunk starts as soon as its frames have arrived, so the
+        host->device copy of later frames overlaps the network on earlier ones."""
         w, h = self.model.resolution
         dt = self.model.compute_dtype
         pos, hms = [], []
+        main = torch.cuda.current_stream()
+        waited = 0
         for s0 in range(0, n_stacks, self.chunk):
             ns = min(self.chunk, n_stacks - s0)
             f0 = s0 * stack_stride
-            x = ops.preprocess_stacks(frames_u8[f0:f0 + (ns - 1) * stack_stride + self.frames_per_stack], self.frames_per_stack,
-                                      stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
+            f_hi = f0 + (ns - 1) * stack_stride + self.frames_per_stack - 1
+            while ready is not None and waited < len(ready) and (waited == 0 or ready[waited - 1][0] < f_hi):
+                main.wait_event(ready[waited][1])
+                waited += 1
+            x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
             hm = self.model.heatmaps_from_nhwc16(x)
             # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian
             pos.append(ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table'))
@@ -216,9 +223,9 @@ class _Detector:
         return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
 
     def _upload(self, images, dev):
-        """Upload each distinct frame once.  numpy frames are staged through a cached pinned buffer; torch CPU
-        tensors (e.g. already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA tensor and, per
-        input image, its row in it."""
+        """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames are staged through a cached
+        pinned buffer; torch CPU tensors (e.g. already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA
+        tensor, per input image its row in it, and [(frame index, event)] marking how far the copy has got."""
         slots, order, uniq = {}, [], []
         for im in images:
             k = id(im)
@@ -228,18 +235,30 @@ class _Detector:
             order.append(slots[k])
         shape = (len(uniq),) + tuple(uniq[0].shape)
         out = torch.empty(shape, dtype=torch.uint8, device=dev)
-        if all(isinstance(u, torch.Tensor) for u in uniq):
+        all_torch = all(isinstance(u, torch.Tensor) for u in uniq)
+        view = None
+        if not all_torch:
+            stage = getattr(self, '_stage', None)
+            if stage is None or stage.shape[1:] != shape[1:] or stage.shape[0] < shape[0]:
+                stage = self._stage = torch.empty(shape, dtype=torch.uint8).pin_memory()
+            view = stage.numpy()
+        copy_stream = getattr(self, '_copy_stream', None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        ready = []
+        with torch.cuda.stream(copy_stream):
             for i, u in enumerate(uniq):
-                out[i].copy_(u, non_blocking=True)
-            return out, order
-        stage = getattr(self, '_stage', None)
-        if stage is None or stage.shape[1:] != shape[1:] or stage.shape[0] < shape[0]:
-            stage = self._stage = torch.empty(shape, dtype=torch.uint8).pin_memory()
-        view = stage[:shape[0]].numpy()
-        for i, u in enumerate(uniq):
-            view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
-        out.copy_(stage[:shape[0]], non_blocking=True)
-        return out, order
+                if all_torch:
+                    out[i].copy_(u, non_blocking=True)
+                else:
+                    view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
+                    out[i].copy_(self._stage[i], non_blocking=True)
+                if i % 4 == 3 or i == len(uniq) - 1:
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    ready.append((i, ev))
+        return out, order, ready
 
 
 class BallDetector(_Detector):
@@ -257,15 +276,17 @@ class BallDetector(_Detector):
         """images: list (length B) of (prev, curr, next) HWC uint8 BGR frames.
         Returns pred_pos (B, 3) float64 [x, y, 1.0] and the heatmaps (B, 1, h, w) float32 (None if return_heatmaps=False)."""
         flat = [im for triple in images for im in (triple[0], triple[1], triple[2])]
-        frames, order = self._upload(flat, self.device)
+        frames, order, ready = self._upload(flat, self.device)
         consecutive = all(order[3 * i + j] == i + j for i in range(len(images)) for j in range(3))
         if consecutive:                 # a sliding window over one clip (TableTennisPipeline.predict): every frame uploaded once
             stride = 1
         else:
-            frames = frames[torch.tensor(order, device=self.device)] if order != list(range(len(flat))) else frames
             stride = 3
+            if order != list(range(len(flat))):
+                torch.cuda.current_stream().wait_event(ready[-1][1])
+                frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
-            pos, hm = self._run(frames, stride, len(images), return_heatmaps)
+            pos, hm = self._run(frames, stride, len(images), return_heatmaps, ready)
         pos = pos[:, 0].cpu().numpy()
         return pos, (hm.cpu().numpy() if return_heatmaps else None)
 
@@ -287,11 +308,12 @@ class TableDetector(_Detector):
 
     def predict(self, images, return_heatmaps=True):
         """images: list of HWC uint8 BGR frames -> pred_pos (B, 13, 3) float64, heatmaps (B, 1, 13, h, w)."""
-        frames, order = self._upload(list(images), self.device)
+        frames, order, ready = self._upload(list(images), self.device)
         if order != list(range(len(images))):
-            frames = frames[torch.tensor(order, device=self.device)]
+            torch.cuda.current_stream().wait_event(ready[-1][1])
+            frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
-            pos, hm = self._run(frames, 1, len(images), return_heatmaps)
+            pos, hm = self._run(frames, 1, len(images), return_heatmaps, ready)
         return pos.cpu().numpy(), (hm[:, None].cpu().numpy() if return_heatmaps else None)
 
     def calibrate_camera(self, keypoints):

@@ -1,0 +1,98 @@
+"""BASELINE.json's full sizes (1080p stacks at 1280x704, batch 32; 50 000 trajectories) checked through
+size-independent properties, plus a sampled comparison with the oracle.  Needs a B200: run with `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hrnet as ohr
+from oracle import preprocess as opre
+from oracle import uplift as oup
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def test_detector_batch32_1080p_properties(dev):
+    """Config 2: 34 consecutive 1080p frames -> 32 stacks -> WASB @1280x704 -> decode."""
+    from upliftingtabletennis_b200 import ops, synthetic
+    from upliftingtabletennis_b200._lib import lib
+    from upliftingtabletennis_b200.detector import WASBNet
+    frames_np = synthetic.frames_1080p(34, seed=42)
+    frames = torch.from_numpy(frames_np).to(dev)
+    m = WASBNet().to(dev).eval()
+    sd = ohr.random_state_dict(9, 3, seed=91)
+    m.load_state_dict(sd)
+    m.compute_dtype = torch.bfloat16
+    x = ops.preprocess_stacks(frames, 3, 1, 32, 1280, 704, layout='nhwc16', dtype=torch.bfloat16)
+    # pre-processing of stack 17 is bit-identical to the oracle at full size
+    ref17 = opre.preprocess_stack(list(frames_np[17:20]), 1280, 704)
+    x32 = ops.preprocess_stacks(frames[17:20], 3, 1, 1, 1280, 704, layout='nchw')
+    assert np.array_equal(x32[0].cpu().numpy(), ref17)
+    hm = m.heatmaps_from_nhwc16(x)
+    assert hm.shape == (32, 1, 704, 1280) and torch.isfinite(hm).all()
+    # (1) batch-composition independence: a stack gives the same heatmap alone, and under any sub-batch size
+    for sb in (1, 3, 8):
+        lib.ttk_hrnet_set_subbatch(m.engine.h, sb)
+        assert torch.equal(m.heatmaps_from_nhwc16(x[5:14]), hm[5:14]), sb
+    lib.ttk_hrnet_set_subbatch(m.engine.h, 4)
+    # (2) determinism
+    assert torch.equal(m.heatmaps_from_nhwc16(x), hm)
+    # (3) stacks 3 and 4 share two frames but not their output; identical stacks give identical output
+    xx = torch.cat([x[3:4], x[3:4], x[4:5]])
+    h3 = m.heatmaps_from_nhwc16(xx)
+    assert torch.equal(h3[0], h3[1]) and not torch.equal(h3[0], h3[2])
+    # (4) bf16 tensor-core path vs the fp32 path and the CPU oracle on one full-size stack
+    m.compute_dtype = torch.float32
+    h32 = m.heatmaps_from_nhwc16(ops.preprocess_stacks(frames[17:20], 3, 1, 1, 1280, 704, layout='nhwc16', dtype=torch.float32))
+    ref = ohr.wasb_forward(sd, torch.from_numpy(ref17)[None]).numpy()
+    tol = 1e-4 * np.abs(ref).max() + 1e-5
+    assert np.abs(h32.cpu().numpy() - ref).max() <= tol
+    rel = np.linalg.norm(hm[17:18].cpu().numpy() - ref) / np.linalg.norm(ref)
+    assert rel < 3e-2, rel
+    # (5) decode of all 32 maps: argmax identical to torch, positions inside the image, both variants agree on real peaks
+    pos, idx, _ = ops.decode_heatmaps(hm[:, 0], 1920, 1080, 'table', return_debug=True)
+    assert torch.equal(idx.long(), hm.view(32, -1).argmax(dim=1))
+    p = pos.cpu().numpy()
+    assert np.all(p[:, 2] == 1.0) and np.all(p[:, 0] > -2) and np.all(p[:, 0] < 1922) and np.all(p[:, 1] > -2) and np.all(p[:, 1] < 1082)
+
+
+def test_uplift_50k_trajectories_properties(dev):
+    """Config 4: 50 000 synthetic trajectories, fp32 and bf16."""
+    from upliftingtabletennis_b200 import ops, synthetic
+    from upliftingtabletennis_b200.uplift import get_model
+    n = 50000
+    ball, table, mask, times = (torch.from_numpy(a).to(dev) for a in synthetic.trajectories(n, seed=5))
+    sd = oup.random_state_dict(77)
+    m = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+    m.load_state_dict(sd)
+    m._sync()
+    out = {}
+    for dt in (torch.float32, torch.bfloat16):
+        rot, pos = m.engine.forward(ball, table, mask, times, dt)
+        assert torch.isfinite(rot).all() and torch.isfinite(pos).all()
+        # permutation equivariance / batch-composition independence on a shuffled subset
+        perm = torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(1))[:3001]
+        r2, p2 = m.engine.forward(ball[perm], table[perm], mask[perm], times[perm], dt)
+        if dt == torch.float32:
+            assert torch.equal(r2, rot[perm]) and torch.equal(p2, pos[perm])
+        else:   # the tensor core sums a row's products in an order that depends on where its keys sit in the tile
+            assert float((r2 - rot[perm]).abs().max()) < 1e-5 and float((p2 - pos[perm]).abs().max()) < 1e-5
+        out[dt] = (rot, pos)
+    # sampled comparison with the CPU oracle
+    pick = torch.arange(0, n, 997, device=dev)
+    r_ref, p_ref = oup.uplift_forward(sd, *(a[pick].cpu() for a in (ball, table, mask, times)))
+    r32, p32 = out[torch.float32]
+    np.testing.assert_allclose(p32[pick].cpu().numpy(), p_ref.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(r32[pick].cpu().numpy(), r_ref.numpy(), rtol=1e-4, atol=1e-4)
+    r16, p16 = out[torch.bfloat16]
+    vm = mask[pick].bool().cpu().numpy()
+    rel = np.linalg.norm(p16[pick].cpu().numpy()[vm] - p_ref.numpy()[vm]) / np.linalg.norm(p_ref.numpy()[vm])
+    assert rel < 3e-2, rel
+    # the local-axis rotation is norm preserving in the x-y plane
+    loc = ops.rotation_local(r32, p32)
+    np.testing.assert_allclose(loc.norm(dim=1).cpu().numpy(), r32.norm(dim=1).cpu().numpy(), rtol=1e-4)

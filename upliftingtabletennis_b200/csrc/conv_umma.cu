@@ -157,6 +157,7 @@ struct KArgs {
   int rsh[3];
   int nres;
   int res_tma;                 // res[0] (shift 0) arrives through shared memory
+  int dual;                    // 1x1 only: K-chunk kc is read from tensor map m[kc] (two concatenated inputs)
   int n, h, w_img, cout_total;
   int relu;
   int tiles_x, tiles_y, total;
@@ -226,7 +227,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           mbar_expect_tx(bar_full + 8 * s, C::NBOX * C::BOX_BYTES);
           const uint32_t dst = smem_u32(sA + s * C::STAGE_BYTES);
           if (S == 1) {
-            tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
+            if (KS == 1 && a.dual)
+              tma_load_4d(dst, &maps.m[kc], bar_full + 8 * s, 0, tx * BW, ty * R, img);     // channels beyond the tensor are zero filled
+            else
+              tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
           } else {
 #pragma unroll
             for (int px = 0; px < 2; ++px)
@@ -501,6 +505,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   k.nres = a.nres;
   k.res_tma = res_tma ? 1 : 0;
+  k.dual = 0;
   k.n = a.n;
   k.h = a.hout;
   k.w_img = a.wout;
@@ -520,7 +525,61 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   return TTK_OK;
 }
 
+int launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st) {
+  constexpr int R = 2, STAGES = 3;
+  using C = Cfg<1, 1, 128, 128, R, STAGES, 0>;
+  EncodeFn encode = get_encode();
+  if (!encode) return TTK_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1, 1, 128, 128, R, STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr = true;
+  }
+  KMaps maps;
+  cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)R, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const void* ins[2] = {a.in, a.in2};
+  const int cins[2] = {a.cin, a.cin2};
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[4] = {(cuuint64_t)cins[i], (cuuint64_t)a.win, (cuuint64_t)a.hin, (cuuint64_t)a.n};
+    cuuint64_t strides[3] = {(cuuint64_t)cins[i] * 2, (cuuint64_t)a.win * cins[i] * 2, (cuuint64_t)a.hin * a.win * cins[i] * 2};
+    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ins[i]), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return TTK_ERR_UNSUPPORTED;      // e.g. a driver that rejects a box wider than the tensor
+  }
+  maps.m[2] = maps.m[3] = maps.res = maps.m[0];
+  KArgs k;
+  k.w = w_dual;
+  k.bias = bias_dual;
+  k.out = (__nv_bfloat16*)a.out;
+  for (int i = 0; i < 3; ++i) {
+    k.res[i] = nullptr;
+    k.rsh[i] = 0;
+  }
+  k.nres = 0;
+  k.res_tma = 0;
+  k.dual = 1;
+  k.n = a.n;
+  k.h = a.hout;
+  k.w_img = a.wout;
+  k.cout_total = a.cout;
+  k.relu = a.relu;
+  k.tiles_x = ttk_cdiv(a.wout, BW);
+  k.tiles_y = ttk_cdiv(a.hout, R);
+  k.total = k.tiles_x * k.tiles_y * a.n;
+  const int gx = std::max(1, std::min(k.total, ttk_num_sms()));
+  conv_umma_kernel<1, 1, 128, 128, R, STAGES, 0><<<gx, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}
+
 }  // namespace
+
+int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st) {
+  if (a.cin != 32 || a.cin2 != 64 || a.cout != 128) return TTK_ERR_UNSUPPORTED;
+  return launch_dual(w_dual, bias_dual, a, st);
+}
 
 // Weights for the tensor-core path: bf16 rows of KC input channels (K-major), zero padded, per output-channel slice:
 //   fused 3x3 stride 1 : [slice][k-chunk][kx][ky][cout_tile][KC]   (B = the three vertical taps side by side)

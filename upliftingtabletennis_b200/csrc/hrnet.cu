@@ -194,6 +194,15 @@ void build_ops(Builder& B) {
     ys = out;
     pre.assign(kBranchCh, kBranchCh + nb);
   }
+  for (int o = 0; o + 1 < (int)h->ops.size(); ++o) {
+    const TtkOp& ds = h->ops[o];
+    const TtkOp& c3 = h->ops[o + 1];
+    if (ds.type == OP_CONV && c3.type == OP_CONV && ds.conv == B.by_name.at("layer1.0.downsample.0") &&
+        c3.conv == B.by_name.at("layer1.0.conv3") && c3.nres == 1 && c3.res[0] == ds.out) {
+      h->dual_ds_op = o;
+      h->dual_c3_op = o + 1;
+    }
+  }
   TtkOp fin;
   fin.type = OP_FINAL;
   fin.in = ys[0];
@@ -488,6 +497,13 @@ int profile_mark(ttk_hrnet* h, int oi, int bs, int H, int W, size_t elem, cudaSt
     r.flops = 2.0 * opix * c.cin * c.cout * c.k * c.k;
     r.bytes = (numel(op.in) + numel(op.out)) * elem + (double)c.cin_p * c.cout_p * c.k * c.k * elem;
     for (int k = 0; k < op.nres; ++k) r.bytes += numel(op.res[k]) * elem;
+    if (elem == 2 && h->dual_ready && h->use_dual && !h->force_simt && oi == h->dual_c3_op) {
+      // fused bottleneck tail: the projection shortcut's GEMM rides along and its output tensor never exists
+      const TtkOp& ds = h->ops[h->dual_ds_op];
+      const TtkConv& dc = h->convs[ds.conv];
+      r.flops += 2.0 * opix * dc.cin * dc.cout;
+      r.bytes += numel(ds.in) * elem + (double)dc.cin_p * dc.cout_p * elem - numel(op.res[0]) * elem;
+    }
   } else if (op.type == OP_SUM) {
     r.flops = numel(op.out) * op.nres;
     r.bytes = (numel(op.in) + numel(op.out)) * elem;
@@ -500,10 +516,37 @@ int profile_mark(ttk_hrnet* h, int oi, int bs, int H, int W, size_t elem, cudaSt
   return TTK_OK;
 }
 
+// [kc=2][cout 128][64] bf16: chunk 0 = conv3 weights (32 input channels, zero padded), chunk 1 = projection shortcut (64)
+int prepare_dual(ttk_hrnet* h) {
+  if (h->dual_ds_op < 0) return TTK_OK;
+  const TtkConv& ds = h->convs[h->ops[h->dual_ds_op].conv];
+  const TtkConv& c3 = h->convs[h->ops[h->dual_c3_op].conv];
+  if (ds.w_host.empty() || c3.w_host.empty()) return TTK_OK;
+  std::vector<__nv_bfloat16> w((size_t)2 * 128 * 64, __float2bfloat16_rn(0.f));
+  std::vector<float> b(128);
+  for (int co = 0; co < 128; ++co) {
+    for (int ci = 0; ci < 32; ++ci) w[((size_t)0 * 128 + co) * 64 + ci] = __float2bfloat16_rn(c3.w_host[(size_t)co * 32 + ci]);
+    for (int ci = 0; ci < 64; ++ci) w[((size_t)1 * 128 + co) * 64 + ci] = __float2bfloat16_rn(ds.w_host[(size_t)co * 64 + ci]);
+    b[co] = c3.b_host[co] + ds.b_host[co];
+  }
+  if (!h->w_dual) TTK_CUDA(cudaMalloc((void**)&h->w_dual, w.size() * sizeof(__nv_bfloat16)));
+  TTK_CUDA(cudaMemcpy(h->w_dual, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  if (!h->bias_dual) TTK_CUDA(cudaMalloc((void**)&h->bias_dual, 128 * sizeof(float)));
+  TTK_CUDA(cudaMemcpy(h->bias_dual, b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
+  h->dual_ready = true;
+  return TTK_OK;
+}
+
 template <typename T>
 int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, char* ws, bool umma, cudaStream_t st) {
+  bool dual_skipped = false;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const TtkOp& op = h->ops[oi];
+    // bottleneck fusion (tensor-core path): the projection shortcut is folded into conv3's GEMM
+    if (umma && h->dual_ready && h->use_dual && (int)oi == h->dual_ds_op) {
+      dual_skipped = true;
+      continue;
+    }
     if (h->profile) {
       int rc = profile_mark(h, (int)oi, bs, H, W, sizeof(T), st);
       if (rc) return rc;
@@ -533,7 +576,34 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
       a.cout = cv.cout_p;
       a.relu = op.relu ? 1 : 0;
       int rc = TTK_ERR_UNSUPPORTED;
-      if (umma) rc = ttk_conv_umma_launch(cv, a, st);
+      if (dual_skipped && (int)oi == h->dual_c3_op) {
+        const TtkOp& ds = h->ops[h->dual_ds_op];
+        ConvLaunch d = a;
+        d.nres = 0;
+        d.in2 = ptr(ds.in);
+        d.cin2 = h->convs[ds.conv].cin_p;
+        rc = ttk_conv_umma_launch_dual(h->w_dual, h->bias_dual, d, st);
+        if (rc == TTK_ERR_UNSUPPORTED) {      // driver refused the maps: run the two convolutions separately from now on
+          h->use_dual = 0;
+          ConvLaunch s0;
+          const TtkConv& dcv = h->convs[ds.conv];
+          const TtkTensor& dti = h->tensors[ds.in];
+          const TtkTensor& dto = h->tensors[ds.out];
+          s0.in = ptr(ds.in);
+          s0.out = ptr(ds.out);
+          s0.nres = 0;
+          for (int r = 0; r < 3; ++r) { s0.res[r] = nullptr; s0.res_shift[r] = 0; }
+          s0.n = bs; s0.hin = H >> dti.shift; s0.win = W >> dti.shift; s0.hout = H >> dto.shift; s0.wout = W >> dto.shift;
+          s0.cin = dcv.cin_p; s0.cout = dcv.cout_p; s0.relu = 0;
+          rc = ttk_conv_umma_launch(dcv, s0, st);
+          if (rc == TTK_ERR_UNSUPPORTED) rc = launch_conv_simt<T>(dcv, s0, sizeof(T) == 2, st);
+          if (rc != TTK_OK) return rc;
+          h->launches++;
+          rc = ttk_conv_umma_launch(cv, a, st);
+        }
+      } else if (umma) {
+        rc = ttk_conv_umma_launch(cv, a, st);
+      }
       if (rc == TTK_ERR_UNSUPPORTED) rc = launch_conv_simt<T>(cv, a, sizeof(T) == 2, st);
       if (rc != TTK_OK) return rc;
       h->launches++;
@@ -610,6 +680,8 @@ extern "C" void ttk_hrnet_destroy(ttk_hrnet* h) {
     cudaFree(c.bias);
     cudaFree(c.w_umma);
   }
+  cudaFree(h->w_dual);
+  cudaFree(h->bias_dual);
   cudaFree(h->final_w);
   cudaFree(h->final_b);
   delete h;
@@ -659,6 +731,9 @@ extern "C" int ttk_hrnet_set_conv(ttk_hrnet* h, int i, const float* w_host, cons
         wr[((size_t)t * c.cin_p + ci) * c.cout_p + co] = bf16_round(v);
       }
   }
+  c.w_host.assign(w_host, w_host + (size_t)c.cout * c.cin * kk);
+  c.b_host.assign(b_host, b_host + c.cout);
+  h->dual_ready = false;
   int rc = upload(&c.w_f32, w);
   if (rc) return rc;
   rc = upload(&c.w_bfr, wr);
@@ -690,6 +765,10 @@ extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int
     }
   h->launches = 0;
   h->recs.clear();
+  if (!h->dual_ready && dtype == TTK_BF16) {
+    int rc = prepare_dual(h);
+    if (rc) return rc;
+  }
   if (batch == 0) return TTK_OK;
   TTK_CHECK_ARG(x_dev && heatmaps_dev && workspace_dev, "ttk_hrnet_forward: null pointer");
   const size_t elem = dtype == TTK_BF16 ? 2 : 4;

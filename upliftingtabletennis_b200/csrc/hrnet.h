@@ -13,7 +13,8 @@ struct TtkConv {
   float* w_f32 = nullptr;       // device, [k*k][cin_p][cout_p] float32 (SIMT path)
   float* w_bfr = nullptr;       // device, same layout, values rounded to bf16 (SIMT path on bf16 storage)
   float* bias = nullptr;        // device, [cout_p] float32
-  __nv_bfloat16* w_umma = nullptr;  // device, tcgen05 B-operand image: [k*k][cout_p][cin_p] bf16 (K-major per tap)
+  __nv_bfloat16* w_umma = nullptr;  // device, tcgen05 B-operand image (see ttk_conv_umma_pack)
+  std::vector<float> w_host, b_host; // folded weights as set by the host (used to build fused variants)
 };
 
 struct TtkTensor {
@@ -43,6 +44,8 @@ struct ConvLaunch {
   int n, hin, win, hout, wout;
   int cin, cout;       // padded
   int relu;
+  const void* in2 = nullptr;   // second input of a K-concatenated 1x1 convolution (fused projection shortcut)
+  int cin2 = 0;
 };
 
 struct ttk_hrnet {
@@ -57,6 +60,12 @@ struct ttk_hrnet {
   // final 1x1 conv weights: [out_count][16] + bias[out_count], float32 device
   float* final_w = nullptr;
   float* final_b = nullptr;
+  // bottleneck fusion: conv3 (1x1, 32->128) and the projection shortcut (1x1, 64->128) as ONE K-concatenated GEMM
+  int dual_ds_op = -1, dual_c3_op = -1;
+  __nv_bfloat16* w_dual = nullptr;
+  float* bias_dual = nullptr;
+  bool dual_ready = false;
+  int use_dual = 1;
   // optional per-launch timing (ttk_hrnet_set_profile): events bracket every launch on the caller's stream
   int profile = 0;
   std::vector<cudaEvent_t> events;     // pool, events[i] precedes launch i
@@ -68,3 +77,5 @@ struct ttk_hrnet {
 // Returns TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel (caller falls back to SIMT on bf16).
 int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st);
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host);
+// out = relu(W3 a + Wd x + bias): a.in = a (32 ch), a.in2 = x (64 ch); returns TTK_ERR_UNSUPPORTED if the driver rejects the maps
+int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st);

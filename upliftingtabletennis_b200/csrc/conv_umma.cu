@@ -618,7 +618,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   TTK_UMMA(3, 1, 64, 64, 2, 2, 0)     // stem conv2, quarter-resolution branch
   TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
   TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
-  TTK_UMMA(3, 1, 128, 16, 2, 2, 0)    // transition1.0
+  TTK_UMMA(3, 1, 128, 16, 3, 2, 0)    // transition1.0
   TTK_UMMA(3, 1, 128, 64, 2, 1, 0)    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
   // 3x3 stride 2 (transitions and fuse down-paths)
   TTK_UMMA(3, 2, 128, 32, 1, 2, 0)

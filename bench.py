@@ -33,6 +33,7 @@ SRC = (1080, 1920)
 WASB_GFLOP_PER_STACK = 344.07        # SURVEY.md section 8d (2*MAC, convs only)
 UPLIFT_GFLOP_PER_TRAJ = 0.753
 UPLIFT_BATCH = 4096
+WORKLOAD = 'configs[1]: WASB ball-detect (1280x704 input, 344 GFLOP/stack) + heatmap decode on synthetic 1920x1080 3-frame stacks, batch %d per GPU' % BATCH
 
 
 def peaks():
@@ -42,6 +43,15 @@ def peaks():
         return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']),
                 'source': 'measured (MEASURED_PEAKS.json)'}
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def ncu_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if that kernel was not captured."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(kernel_name, {}).get('dram_bytes_per_launch')
 
 
 class ClockSampler:
@@ -124,7 +134,7 @@ def run_reference(args, rank, world):
     line = {'impl': 'reference', 'metric': 'frames_per_sec_detect_decode', 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'configs[1]: WASB ball-detect + decode on 1920x1080 3-frame stacks, 1280x704 input; bounded sample of %d stacks per step (B=1 per forward like interface.py)' % per_step},
+            'config': {'workload': WORKLOAD, 'sample': 'each step = %d stacks of that workload, B=1 per forward like interface.py:102-119' % per_step},
             'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                              'sample': '%d steps x %d stacks through oracle/ (numpy resize + CPU torch fp32 WASB + SciPy L-BFGS-B decode)' % (args.steps, per_step)},
             'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -303,7 +313,7 @@ def main():
         'peak': pk['hbm_gbs'] if hbm_bound else pk['bf16_tflops_sustained'],
         'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
         'frac': (achieved_gbs / pk['hbm_gbs']) if hbm_bound else (achieved_tf / pk['bf16_tflops_sustained']),
-        'traffic': None,
+        'traffic': ncu_traffic(name),
         'peak_source': pk['source'] + (', copy bandwidth' if hbm_bound else ', sustained bf16 (kernel timed inside a long step)'),
         'intensity_flop_per_byte': intensity, 'ridge_flop_per_byte': ridge,
         'algorithmic_bytes_per_launch': top[2] / top[3], 'algorithmic_flops_per_launch': top[1] / top[3],
@@ -330,7 +340,7 @@ def main():
         'metric': 'frames_per_sec_detect_decode', 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': args.dtype, 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: WASB ball-detect (1280x704, 344 GFLOP/stack) + heatmap decode on synthetic 1920x1080 3-frame stacks, batch %d per GPU' % BATCH,
+        'config': {'workload': WORKLOAD,
                    'parallelism': 'clip-sharded x%d, NCCL all_gather of (x,y,v) records' % world, 'l2': 'inputs (211 MB of frames) and activations exceed the 126 MB L2',
                    'weights': 'random-init (seeded), BN folded'},
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(frames_pinned.numel()), 'd2h_bytes_per_step': BATCH * 3 * 8,

@@ -80,8 +80,13 @@ def test_uplift_50k_trajectories_properties(dev):
         r2, p2 = m.engine.forward(ball[perm], table[perm], mask[perm], times[perm], dt)
         if dt == torch.float32:
             assert torch.equal(r2, rot[perm]) and torch.equal(p2, pos[perm])
-        else:   # the tensor core sums a row's products in an order that depends on where its keys sit in the tile
-            assert float((r2 - rot[perm]).abs().max()) < 1e-5 and float((p2 - pos[perm]).abs().max()) < 1e-5
+        else:
+            # The tensor core sums a row's products in an order that depends on where its keys sit in the 128-row tile;
+            # the 1-ulp fp32 differences occasionally flip a bf16 rounding and then grow through the remaining layers,
+            # so in bf16 a trajectory is batch-composition independent only to within the path's own error bound.
+            same = ((p2 - pos[perm]).abs().amax(dim=(1, 2)) == 0).float().mean().item()
+            assert same > 0.8, same
+            assert float((p2 - pos[perm]).norm() / pos[perm].norm()) < 1e-2 and float((r2 - rot[perm]).norm() / rot[perm].norm()) < 1e-2
         out[dt] = (rot, pos)
     # sampled comparison with the CPU oracle
     pick = torch.arange(0, n, 997, device=dev)

@@ -83,8 +83,8 @@ TTK_API int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int he
                       float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* kernels launched by the last ttk_hrnet_forward on this handle (for bench accounting) */
 TTK_API int ttk_hrnet_last_launches(const ttk_hrnet* h);
-/* Images processed per pass through the layer plan (default 4: amortises launch and pipeline fill costs while
- * a thin layer's tensors still largely stay in the 126 MB L2).  Bounds the activation workspace. */
+/* Images processed per pass through the layer plan (default 16; measured 760 / 877 / 962 / 1002 frames/s at
+ * 2 / 4 / 8 / 16: per-launch fixed costs outweigh L2 residency of thin layers).  Bounds the activation workspace. */
 TTK_API int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images);
 /* Measurement aid (bench.py): when enabled, ttk_hrnet_forward brackets every kernel launch with CUDA
  * events on `stream`.  After the caller synchronised the stream, ttk_hrnet_profile_read returns, per

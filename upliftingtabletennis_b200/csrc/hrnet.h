@@ -54,7 +54,7 @@ struct ttk_hrnet {
   std::vector<TtkTensor> tensors;
   std::vector<TtkOp> ops;
   int input_tensor = -1;
-  int subbatch = 4;
+  int subbatch = 16;
   int launches = 0;
   int force_simt = 0;           // bf16 storage through the SIMT kernels (debug / cross-check of the tcgen05 path)
   // final 1x1 conv weights: [out_count][16] + bias[out_count], float32 device

@@ -196,7 +196,7 @@ def _uplifting_transform(ball_coords, table_coords, times):
 # ---- public classes ---------------------------------------------------------------------------------
 class _Detector:
     frames_per_stack = 1
-    chunk = 8                      # stacks per network pass: bounds the workspace and lets uploads overlap compute
+    chunk = 16                     # stacks per network pass: bounds the workspace and lets uploads overlap compute
 
     def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps, ready=None):
         """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None.

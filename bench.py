@@ -184,11 +184,21 @@ def main():
     heat = torch.empty((BATCH, 1, H, W), dtype=torch.float32, device=dev)
     gathered = torch.empty((world * BATCH, 3), dtype=torch.float64, device=dev) if world > 1 else None
 
-    def step_device(gather=True):
+    stage_ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step_device(gather=True, mark=False):
+        if mark:
+            stage_ev[0].record()
         ops.preprocess_stacks(frames_dev, 3, 1, BATCH, W, H, layout='nhwc16', dtype=cdt, out=x)
+        if mark:
+            stage_ev[1].record()
         det.model._sync()
         engine.forward_nhwc16(x, out=heat)
+        if mark:
+            stage_ev[2].record()
         pos = ops.decode_heatmaps(heat, SRC[1], SRC[0], 'table')
+        if mark:
+            stage_ev[3].record()
         if world > 1 and gather:
             dist.all_gather_into_tensor(gathered, pos.view(BATCH, 3))
         return pos
@@ -270,6 +280,17 @@ def main():
     # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream ----------
     pk = peaks()
     check = _lib.check
+    # bandwidth-bound stages either side of the network, timed in place inside a step (events on the launching stream)
+    step_device(gather=False, mark=True)
+    torch.cuda.synchronize()
+    pre_ms, dec_ms = stage_ev[0].elapsed_time(stage_ev[1]), stage_ev[2].elapsed_time(stage_ev[3])
+    pre_bytes = frames_dev.numel() + x.numel() * x.element_size()
+    dec_bytes = heat.numel() * 4 + BATCH * 24
+    stages = {'preprocess': {'ms': pre_ms, 'algorithmic_bytes': pre_bytes, 'gbs': pre_bytes / (pre_ms * 1e-3) / 1e9,
+                             'hbm_frac': pre_bytes / (pre_ms * 1e-3) / 1e9 / peaks()['hbm_gbs']},
+              'decode': {'ms': dec_ms, 'algorithmic_bytes': dec_bytes, 'gbs': dec_bytes / (dec_ms * 1e-3) / 1e9,
+                         'hbm_frac': dec_bytes / (dec_ms * 1e-3) / 1e9 / peaks()['hbm_gbs'],
+                         'note': 'argmax (one read of every heatmap value) + per-map L-BFGS-B fit; the %d-map batch is smaller than L2' % BATCH}}
     check(lib.ttk_hrnet_set_profile(engine.h, 1))
     step_device(gather=False)
     torch.cuda.synchronize()
@@ -348,6 +369,7 @@ def main():
         'gpu_launches': launches * args.steps,
         'clocks': clocks,
         'roofline': roofline,
+        'stages': stages,
         'cpu_baseline': cpu,
         'uplift': {'value': up_res['bf16'][0], 'unit': 'trajectories/s', 'dtype': 'bf16', 'batch_per_gpu': UPLIFT_BATCH, 'ms_per_step': up_res['bf16'][2],
                    'e2e': {'value': up_res['bf16'][1], 'unit': 'trajectories/s', 'h2d_bytes_per_step': int(sum(a.numel() * 4 for a in (ub, ut, um, uti))),

@@ -5,6 +5,7 @@
 //
 // HBM-bound: every heatmap value is read exactly once with 128-bit loads
 // (H*W*4 bytes per map); the fit is O(10^3) flops per map.
+#define TTK_WARP_COOPERATIVE_LOSS 1     // the fit runs warp-wide: 9 lanes evaluate the 9 window terms
 #include "lbfgsb4.h"
 #include "ttk_internal.h"
 
@@ -118,8 +119,7 @@ __global__ void __launch_bounds__(32) decode_finalize_kernel(const float* __rest
     const Best p = partial[(size_t)map * chunks + c];
     if (beats(p.v, p.i, b.v, b.i)) b = p;
   }
-  b = warp_best(b);
-  if (threadIdx.x != 0) return;
+  b = warp_best(b);          // every lane holds the winner
   const int idx = b.i;
   const int y = idx / W, x = idx - y * W;
   const float* m = maps + (size_t)map * H * W;
@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(32) decode_finalize_kernel(const float* __rest
       yi = (double)__fsub_rn(__fmul_rn(__fadd_rn(ys, 0.5f), (float)scale_y), 0.5f);
     }
   }
+  if (threadIdx.x != 0) return;
   out_xyv[map * 3 + 0] = xi;
   out_xyv[map * 3 + 1] = yi;
   out_xyv[map * 3 + 2] = 1.0;   // visibility is always 1 (helper_tabledetection.py:142)

@@ -47,6 +47,24 @@ TTK_HD static inline double ttk_gauss_loss(const TtkGaussObjective* o, const dou
     sy = sy > 0.5 ? sy : 0.5;
   }
   const double dsx = 2.0 * (sx * sx), dsy = 2.0 * (sy * sy);
+#if defined(__CUDA_ARCH__) && defined(TTK_WARP_COOPERATIVE_LOSS)
+  // Device: the whole warp runs the optimiser in lock step (identical data, no divergence); lane l < 9 evaluates window
+  // element l and the 9 terms are summed in the same pairwise order as the scalar path below.
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double t = 0.0;
+  if (lane < 9) {
+    const double dx = (double)(lane % 3) - x0, dy = (double)(lane / 3) - y0;
+    const double g = exp(-((dx * dx) / dsx + (dy * dy) / dsy));
+    const double r = g - o->w[lane];
+    t = r * r;
+  }
+  const double a = t + __shfl_down_sync(full, t, 1);
+  const double b = a + __shfl_down_sync(full, a, 2);
+  const double c = b + __shfl_down_sync(full, b, 4);
+  const double s = __shfl_sync(full, c, 0) + __shfl_sync(full, t, 8);
+  return s / 9.0;
+#else
   double t[9];
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i) {
@@ -57,6 +75,7 @@ TTK_HD static inline double ttk_gauss_loss(const TtkGaussObjective* o, const dou
     }
   const double s = (((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]))) + t[8];
   return s / 9.0;
+#endif
 }
 
 // f and SciPy's 2-point finite-difference gradient (5 evaluations)

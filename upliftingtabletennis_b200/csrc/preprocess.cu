@@ -101,80 +101,87 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restri
 // coalesced 128-bit loads (the per-pixel taps overlap heavily: 1.5 source pixels per output pixel at 1080p -> 704p)
 // and the 12 byte-taps per frame are then read from shared memory.  Needs 16-byte aligned source rows.
 constexpr int PRE_ROW_BYTES = 1536;      // >= (256 outputs * max scale 1.6 + 3) * 3 bytes + alignment slack
+constexpr int PRE_ROWS = 1;              // output rows per block (more rows per block measured slower: the row loop serialises load and compute)
+constexpr int LUT_COPIES = 8;            // normalisation table replicated so that random look-ups spread over the banks
 template <int F, int MODE>
 __global__ void __launch_bounds__(256) preprocess_smem_kernel(const uint8_t* __restrict__ frames, int src_h, int src_w,
                                                               int stack_stride, int dst_h, int dst_w, double scale_x,
                                                               double scale_y, const float* __restrict__ lut,
                                                               void* __restrict__ out) {
-  __shared__ float s_lut[768];
+  __shared__ float s_lut[768 * LUT_COPIES];                    // [entry][copy]
   __shared__ __align__(16) uint8_t s_rows[F * 2 * PRE_ROW_BYTES];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) s_lut[i] = lut[i];
+  for (int i = threadIdx.x; i < 768 * LUT_COPIES; i += blockDim.x) s_lut[i] = lut[i / LUT_COPIES];
   const int x0 = blockIdx.x * blockDim.x;
   const int x = x0 + threadIdx.x;
-  const int y = blockIdx.y;
   const int s = blockIdx.z;
   const int x_last = min(x0 + (int)blockDim.x, dst_w) - 1;
   const AxisTap t_first = axis_tap(x0, src_w, scale_x), t_last = axis_tap(x_last, src_w, scale_x);
-  const AxisTap ty = axis_tap(y, src_h, scale_y);
+  const AxisTap tx = axis_tap(min(x, dst_w - 1), src_w, scale_x);
   const int byte_lo = (t_first.s0 * 3) & ~15;                 // 16-byte aligned start within the source row
   const int byte_hi = (t_last.s1 + 1) * 3;                     // exclusive
   const int nvec = (byte_hi - byte_lo + 15) >> 4;
   const size_t row_bytes = (size_t)src_w * 3;
-  for (int i = threadIdx.x; i < F * 2 * nvec; i += blockDim.x) {
-    const int v = i % nvec, r = (i / nvec) & 1, f = i / (2 * nvec);
-    const uint8_t* img = frames + (size_t)(s * stack_stride + f) * src_h * row_bytes;
-    const uint8_t* src = img + (size_t)(r ? ty.s1 : ty.s0) * row_bytes + byte_lo + 16 * v;
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (byte_lo + 16 * v + 16 <= (int)row_bytes) {
-      q = __ldg(reinterpret_cast<const uint4*>(src));
-    } else {                                                    // ragged end of the row
-      uint8_t tmp[16];
-      for (int b = 0; b < 16; ++b) tmp[b] = (byte_lo + 16 * v + b < (int)row_bytes) ? __ldg(src + b) : 0;
-      q = *reinterpret_cast<uint4*>(tmp);
-    }
-    *reinterpret_cast<uint4*>(s_rows + (f * 2 + r) * PRE_ROW_BYTES + 16 * v) = q;
-  }
-  __syncthreads();
-  if (x >= dst_w) return;
-  const AxisTap tx = axis_tap(x, src_w, scale_x);
   const int o0 = tx.s0 * 3 - byte_lo, o1 = tx.s1 * 3 - byte_lo;
-  float v[3 * F];
-#pragma unroll
-  for (int f = 0; f < F; ++f) {
-    const uint8_t* r0 = s_rows + (f * 2) * PRE_ROW_BYTES;
-    const uint8_t* r1 = r0 + PRE_ROW_BYTES;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const int h0 = r0[o0 + c] * tx.a0 + r0[o1 + c] * tx.a1;
-      const int h1 = r1[o0 + c] * tx.a0 + r1[o1 + c] * tx.a1;
-      const int acc = ((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16);
-      const int u8 = min(255, max(0, (acc + 2) >> 2));
-      v[f * 3 + c] = s_lut[c * 256 + u8];
+  const float* my_lut = s_lut + (threadIdx.x & (LUT_COPIES - 1));
+  for (int ry = 0; ry < PRE_ROWS; ++ry) {
+    const int y = blockIdx.y * PRE_ROWS + ry;
+    if (y >= dst_h) break;
+    const AxisTap ty = axis_tap(y, src_h, scale_y);
+    __syncthreads();                                            // previous row's taps are consumed (and the LUT is loaded)
+    for (int i = threadIdx.x; i < F * 2 * nvec; i += blockDim.x) {
+      const int v = i % nvec, r = (i / nvec) & 1, f = i / (2 * nvec);
+      const uint8_t* img = frames + (size_t)(s * stack_stride + f) * src_h * row_bytes;
+      const uint8_t* src = img + (size_t)(r ? ty.s1 : ty.s0) * row_bytes + byte_lo + 16 * v;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (byte_lo + 16 * v + 16 <= (int)row_bytes) {
+        q = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {                                                  // ragged end of the row
+        uint8_t tmp[16];
+        for (int b = 0; b < 16; ++b) tmp[b] = (byte_lo + 16 * v + b < (int)row_bytes) ? __ldg(src + b) : 0;
+        q = *reinterpret_cast<uint4*>(tmp);
+      }
+      *reinterpret_cast<uint4*>(s_rows + (f * 2 + r) * PRE_ROW_BYTES + 16 * v) = q;
     }
-  }
-  if (MODE == 0) {
-    float* o = (float*)out + (size_t)s * (3 * F) * dst_h * dst_w + (size_t)y * dst_w + x;
+    __syncthreads();
+    if (x >= dst_w) continue;
+    float v[3 * F];
 #pragma unroll
-    for (int c = 0; c < 3 * F; ++c) o[(size_t)c * dst_h * dst_w] = v[c];
-  } else if (MODE == 1) {
-    float4* o = (float4*)((float*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
-    float w[16];
+    for (int f = 0; f < F; ++f) {
+      const uint8_t* r0 = s_rows + (f * 2) * PRE_ROW_BYTES;
+      const uint8_t* r1 = r0 + PRE_ROW_BYTES;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) w[c] = c < 3 * F ? v[c] : 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-  } else {
-    uint4* o = (uint4*)((__nv_bfloat16*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
-    uint32_t w[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float lo = 2 * c < 3 * F ? v[2 * c] : 0.f;
-      const float hi = 2 * c + 1 < 3 * F ? v[2 * c + 1] : 0.f;
-      __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-      w[c] = *reinterpret_cast<uint32_t*>(&p);
+      for (int c = 0; c < 3; ++c) {
+        const int h0 = r0[o0 + c] * tx.a0 + r0[o1 + c] * tx.a1;
+        const int h1 = r1[o0 + c] * tx.a0 + r1[o1 + c] * tx.a1;
+        const int acc = ((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16);
+        const int u8 = min(255, max(0, (acc + 2) >> 2));
+        v[f * 3 + c] = my_lut[(c * 256 + u8) * LUT_COPIES];
+      }
     }
-    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (MODE == 0) {
+      float* o = (float*)out + (size_t)s * (3 * F) * dst_h * dst_w + (size_t)y * dst_w + x;
+#pragma unroll
+      for (int c = 0; c < 3 * F; ++c) o[(size_t)c * dst_h * dst_w] = v[c];
+    } else if (MODE == 1) {
+      float4* o = (float4*)((float*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
+      float w[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) w[c] = c < 3 * F ? v[c] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[q] = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    } else {
+      uint4* o = (uint4*)((__nv_bfloat16*)out + ((size_t)(s * dst_h + y) * dst_w + x) * 16);
+      uint32_t w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float lo = 2 * c < 3 * F ? v[2 * c] : 0.f;
+        const float hi = 2 * c + 1 < 3 * F ? v[2 * c + 1] : 0.f;
+        __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+        w[c] = *reinterpret_cast<uint32_t*>(&p);
+      }
+      o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
   }
 }
 
@@ -185,6 +192,7 @@ int launch(int mode, dim3 grid, cudaStream_t st, const uint8_t* frames, int src_
   const bool staged = !(src_h == dst_h && src_w == dst_w) && ((size_t)src_w * 3) % 16 == 0 && ((uintptr_t)frames & 15) == 0 &&
                       (256.0 * sx + 4.0) * 3.0 + 32.0 <= PRE_ROW_BYTES;
   if (staged) {
+    grid.y = ttk_cdiv(dst_h, PRE_ROWS);
     if (mode == 0)
       preprocess_smem_kernel<F, 0><<<grid, 256, 0, st>>>(frames, src_h, src_w, stack_stride, dst_h, dst_w, sx, sy, lut, out);
     else if (mode == 1)

@@ -118,6 +118,33 @@ TTK_API int ttk_heatmap_decode(const float* heatmaps_dev, int n_maps, int height
                        float* out_win_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Trajectory filters between decode and uplift (device versions).
+ *
+ * ttk_filter_ball replaces filter_trajectory_ball (inference/utils.py:70-102): keep frame t when both
+ * detectors report the ball visible (== 1) and their positions differ by at most threshold_px
+ * (NaN distances are kept, like `diff > 20` in the reference).  pos*_dev: n_frames x 3 float64 (x, y, v).
+ * Outputs are compacted in frame order: out_xy n x 2 float64, out_idx n int64, out_times n float64
+ * (= t / fps); capacity n_frames each.  out_offsets_dev[2] int32 = {0, n}: the prefix-sum format
+ * ttk_trajectory_pack consumes, so the count never has to visit the host.
+ */
+TTK_API int ttk_filter_ball(const double* pos1_dev, const double* pos2_dev, int n_frames, double fps, double threshold_px,
+                    double* out_xy_dev, int64_t* out_idx_dev, double* out_times_dev, int32_t* out_offsets_dev,
+                    void* stream);
+
+/* ttk_filter_table replaces filter_trajectory_table (inference/utils.py:137-169) and
+ * _filter_keypoints_with_dbscan (:172-232; scikit-learn DBSCAN semantics, see csrc/filters.cu):
+ * per keypoint, frames where both detectors see it and agree within (<) agree_px are clustered with
+ * DBSCAN(eps, min_samples); the centroid of the largest cluster is returned as (x, y, 1), or
+ * (-1, -1, 0) when fewer than 3 frames qualify.  pos*_dev: n_clips x n_frames x n_keypoints x 3
+ * float64; out_dev: n_clips x n_keypoints x 3 float64.  The reference calls it with
+ * agree_px = 10, eps = 10, min_samples = 3.
+ */
+TTK_API size_t ttk_filter_table_workspace_bytes(int n_clips, int n_frames, int n_keypoints);
+TTK_API int ttk_filter_table(const double* pos1_dev, const double* pos2_dev, int n_clips, int n_frames, int n_keypoints,
+                     double agree_px, double eps, int min_samples, double* out_dev, void* workspace_dev,
+                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Trajectory packing: pixel -> [0,1] normalisation, pad/crop to seq_len, mask.
  * Replaces _uplifting_transform (inference/utils.py:268-309), batched over clips.
  * ball_xy_dev: sum(lengths) x 2 float64 (concatenated clips), times_dev: sum(lengths) float64,

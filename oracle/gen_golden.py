@@ -212,6 +212,61 @@ def gen_tails():
                         utl_mask=ml.numpy(), rot=rot, pos=pos, rot_local=rloc, Mext=Mext, Mint=Mint, p3=p3, proj=proj)
 
 
+def synthetic_keypoint_tracks(rng, T, K=13):
+    """Two detectors' (T,K,3) keypoint tracks: a stable cluster per keypoint, outlier bursts, a second smaller or equally
+    large cluster, chains of points one eps apart, disagreeing frames, invisible frames, and keypoints with < 3 survivors."""
+    base = np.stack([rng.uniform(100, 1800, K), rng.uniform(100, 1000, K)], axis=1)
+    p1 = np.zeros((T, K, 3))
+    p1[:, :, :2] = base[None] + rng.normal(0, 2.0, (T, K, 2))
+    p1[:, :, 2] = 1.0
+    for k in range(K):
+        mode = k % 7
+        if mode == 1:                                   # a second cluster of the same size far away (tie -> first seen)
+            half = T // 2
+            p1[half:2 * half, k, :2] = base[k] + 300 + (p1[:half, k, :2] - base[k])
+        elif mode == 2:                                 # scattered outliers (noise points)
+            sel = rng.choice(T, max(T // 5, 1), replace=False)
+            p1[sel, k, :2] += rng.uniform(-400, 400, (len(sel), 2))
+        elif mode == 3:                                 # a chain: consecutive points 7 px apart (one long thin cluster)
+            p1[:, k, 0] = base[k, 0] + 7.0 * np.arange(T)
+            p1[:, k, 1] = base[k, 1]
+        elif mode == 4:                                 # sparse: everything is noise -> mean of all points
+            p1[:, k, :2] = base[k] + 40.0 * np.stack([np.arange(T) % 7, np.arange(T) // 7], axis=1)
+        elif mode == 5:                                 # border points between two clusters
+            p1[:, k, 0] = base[k, 0] + np.where(np.arange(T) % 2 == 0, 0.0, 16.0) + rng.normal(0, 0.5, T)
+            p1[:, k, 1] = base[k, 1] + rng.normal(0, 0.5, T)
+            p1[T // 2, k, 0] = base[k, 0] + 8.0
+    p2 = p1.copy()
+    p2[:, :, :2] += rng.normal(0, 3.0, (T, K, 2))
+    p2[rng.uniform(0, 1, (T, K)) < 0.1, 2] = 0          # aux detector misses
+    p1[rng.uniform(0, 1, (T, K)) < 0.05, 2] = 0
+    p2[rng.uniform(0, 1, (T, K)) < 0.1, :2] += 30       # disagreement
+    p1[:, K - 1, 2] = 0                                 # never visible
+    p1[2:, K - 2, 2] = 0                                # two survivors only
+    return p1, p2
+
+
+def gen_filters():
+    """filter_trajectory_table (inference/utils.py:137-232, scikit-learn DBSCAN) on synthetic two-detector tracks."""
+    from inference.utils import filter_trajectory_table, filter_trajectory_ball
+    rng = np.random.default_rng(700)
+    out = {}
+    for i, T in enumerate((3, 24, 120, 300)):
+        p1, p2 = synthetic_keypoint_tracks(rng, T)
+        out['t%d_p1' % i], out['t%d_p2' % i] = p1, p2
+        out['t%d_out' % i] = np.asarray(filter_trajectory_table(p1, p2), dtype=np.float64)
+    T = 1500                                            # longer than one compaction pass of the ball kernel
+    b1 = np.concatenate([rng.uniform(0, 1920, (T, 1)), rng.uniform(0, 1080, (T, 1)), np.ones((T, 1))], axis=1)
+    b2 = b1.copy()
+    b2[:, :2] += rng.normal(0, 11, (T, 2))
+    b2[rng.uniform(0, 1, T) < 0.1, 2] = 0
+    b1[rng.uniform(0, 1, T) < 0.1, 2] = 0
+    b1[7, 0] = np.nan                                   # NaN distance is kept by `diff > 20`
+    fpos, fidx, ftimes = filter_trajectory_ball(b1, b2, 120)
+    out.update(b1=b1, b2=b2, bfps=120.0, bpos=fpos, bidx=fidx, btimes=ftimes)
+    np.savez_compressed(os.path.join(GOLDEN, 'filters.npz'), **out)
+
+
 def write_checkpoints(w, res=(160, 88)):
     """Reference-format checkpoints with oracle weights, small detector resolution."""
     from oracle import hrnet as oh, uplift as ou
@@ -254,11 +309,15 @@ def main():
     w = setup_reference()
     sys.path.insert(0, ROOT)
     torch.set_num_threads(os.cpu_count())
-    for fn in (gen_preprocess, gen_hrnet, gen_decode, gen_uplift, gen_tails):
+    only = set(sys.argv[1:])
+    for fn in (gen_preprocess, gen_hrnet, gen_decode, gen_uplift, gen_tails, gen_filters):
+        if only and fn.__name__ not in only:
+            continue
         fn()
         print('wrote', fn.__name__)
-    gen_interface(w)
-    print('wrote gen_interface')
+    if not only or 'gen_interface' in only:
+        gen_interface(w)
+        print('wrote gen_interface')
 
 
 if __name__ == '__main__':

@@ -74,7 +74,7 @@ def test_uplifting_model_predict(weights, golden):
 def test_full_pipeline_runs(weights, golden):
     """TableTennisPipeline.predict end to end on a short synthetic clip, compared with the oracle chained by hand."""
     from oracle import decode as odec, hrnet as ohr, preprocess as opre, tails as otl, uplift as oup
-    from upliftingtabletennis_b200.interface import TableTennisPipeline, filter_trajectory_table
+    from upliftingtabletennis_b200.interface import TableTennisPipeline
     g = golden('interface')
     frames = list(g['frames'])
     pipe = TableTennisPipeline()
@@ -88,7 +88,7 @@ def test_full_pipeline_runs(weights, golden):
     thm = ohr.hrnet_forward(sd_t, torch.from_numpy(tst)).numpy()
     tpos, _, _ = odec.decode_heatmaps(thm.reshape(-1, 88, 160), 1920, 1080, odec.TABLE)
     tpos = tpos.reshape(len(frames), 13, 3)
-    table = filter_trajectory_table(tpos, tpos)
+    table = otl.filter_trajectory_table(tpos, tpos).astype(np.float64)
     b, t, ti, m = otl.uplifting_transform(fpos, table, ftimes)
     rot, pos = oup.uplift_forward(sd_u, *(torch.from_numpy(a) for a in (b, t, m, ti)))
     n = int(m.sum())

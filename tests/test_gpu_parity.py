@@ -288,3 +288,58 @@ def test_uplift_bf16_tensor_core_bound(dev, golden, name):
     assert rel_rot < 5e-2, rel_rot
     # and the fp32 path is untouched by switching back and forth
     np.testing.assert_allclose(p32.cpu().numpy(), p_ref.numpy(), rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
+
+
+def test_filters_golden_bit_exact(dev, golden):
+    """Device trajectory filters against the reference's outputs: bit exact."""
+    from upliftingtabletennis_b200 import ops
+    g = golden('filters')
+    for i in range(4):
+        out = ops.filter_table(torch.from_numpy(g['t%d_p1' % i]).to(dev), torch.from_numpy(g['t%d_p2' % i]).to(dev))
+        assert np.array_equal(out.cpu().numpy(), g['t%d_out' % i]), i
+    xy, idx, tm, offs = ops.filter_ball(torch.from_numpy(g['b1']).to(dev), torch.from_numpy(g['b2']).to(dev), float(g['bfps']))
+    n = int(offs[1].item())
+    assert int(offs[0].item()) == 0 and n == len(g['bidx'])
+    assert np.array_equal(xy[:n].cpu().numpy(), g['bpos'], equal_nan=True)
+    assert np.array_equal(idx[:n].cpu().numpy(), g['bidx']) and np.array_equal(tm[:n].cpu().numpy(), g['btimes'])
+    # the count stays on the device: offsets feed trajectory_pack directly
+    t = np.concatenate([np.random.default_rng(0).uniform(0, 1000, (13, 2)), np.ones((13, 1))], axis=1)
+    b, tb, ti, mk = ops.trajectory_pack(xy, tm, offs, torch.from_numpy(t).to(dev)[None])
+    rb, rt, rti, rmk = otl.uplifting_transform(g['bpos'], t, g['btimes'])
+    assert np.array_equal(b.cpu().numpy(), rb, equal_nan=True) and np.array_equal(ti.cpu().numpy(), rti) and np.array_equal(mk.cpu().numpy(), rmk)
+
+
+def test_filters_vs_oracle_random_and_edges(dev):
+    from upliftingtabletennis_b200 import ops
+    from oracle.gen_golden import synthetic_keypoint_tracks
+    rng = np.random.default_rng(77)
+    clips = []
+    for T in (1, 2, 5, 64, 64, 700):
+        p1, p2 = synthetic_keypoint_tracks(rng, T)
+        if T == 64:
+            p1[:, :, :2] = np.round(p1[:, :, :2])       # integer coordinates: distances exactly on eps and on the 10 px bound
+            p2[:, :, :2] = np.round(p2[:, :, :2])
+        out = ops.filter_table(torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev)).cpu().numpy()
+        assert np.array_equal(out, otl.filter_trajectory_table(p1, p2).astype(np.float64)), T
+        if T == 64:
+            clips.append((p1, p2))
+    # batched over clips (the sharded multi-clip pipeline): same answers as clip by clip
+    a, b = np.stack([c[0] for c in clips]), np.stack([c[1] for c in clips])
+    out = ops.filter_table(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)).cpu().numpy()
+    for i, (p1, p2) in enumerate(clips):
+        assert np.array_equal(out[i], otl.filter_trajectory_table(p1, p2).astype(np.float64))
+    # ball filter: nothing survives -> n = 0 (the reference raises IndexError at :98; the device op reports the empty result)
+    p = np.concatenate([rng.uniform(0, 100, (10, 2)), np.zeros((10, 1))], axis=1)
+    xy, idx, tm, offs = ops.filter_ball(torch.from_numpy(p).to(dev), torch.from_numpy(p).to(dev), 50.0)
+    assert offs.cpu().tolist() == [0, 0]
+    for T in (1, 1024, 1025, 5000):
+        p1 = np.concatenate([rng.uniform(0, 1920, (T, 2)), (rng.uniform(0, 1, (T, 1)) > 0.2).astype(np.float64)], axis=1)
+        p2 = p1.copy()
+        p2[:, :2] += rng.normal(0, 12, (T, 2))
+        p1[0, 2] = p2[0, 2] = 1.0
+        p2[0, :2] = p1[0, :2]
+        xy, idx, tm, offs = ops.filter_ball(torch.from_numpy(p1).to(dev), torch.from_numpy(p2).to(dev), 59.94)
+        rp, ri, rt = otl.filter_trajectory_ball(p1, p2, 59.94)
+        n = int(offs[1].item())
+        assert n == len(ri) and np.array_equal(xy[:n].cpu().numpy(), rp) and np.array_equal(idx[:n].cpu().numpy(), ri)
+        assert np.array_equal(tm[:n].cpu().numpy(), rt)

@@ -133,3 +133,23 @@ def test_interface_golden(golden):
     # the local axes come from pos[1]-pos[0] (a small difference of fp32 positions), which amplifies
     # summation-order noise; the rotation itself is pinned tightly in test_tails_golden
     np.testing.assert_allclose(otl.transform_rotationaxes(rot.numpy(), pos.numpy())[0], g['spin'], rtol=1e-3, atol=1e-3)
+
+
+def test_filters_golden(golden):
+    """filter_trajectory_table / DBSCAN restatement and the ball filter against the reference's outputs."""
+    g = golden('filters')
+    for i in range(4):
+        out = otl.filter_trajectory_table(g['t%d_p1' % i], g['t%d_p2' % i]).astype(np.float64)
+        assert np.array_equal(out, g['t%d_out' % i]), i
+    pos, idx, tm = otl.filter_trajectory_ball(g['b1'], g['b2'], float(g['bfps']))
+    assert np.array_equal(pos, g['bpos'], equal_nan=True) and np.array_equal(idx, g['bidx']) and np.array_equal(tm, g['btimes'])
+
+
+def test_dbscan_restatement_matches_sklearn():
+    sk = pytest.importorskip('sklearn.cluster')
+    rng = np.random.default_rng(5)
+    for trial in range(30):
+        n = int(rng.integers(3, 120))
+        pts = rng.uniform(0, 60, (n, 2)) if trial % 2 else np.round(rng.uniform(0, 40, (n, 2)))   # integer grid: exact eps ties
+        ref = sk.DBSCAN(eps=10, min_samples=3).fit(pts).labels_
+        assert np.array_equal(otl.dbscan_labels(pts, 10, 3), ref), trial

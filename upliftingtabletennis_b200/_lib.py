@@ -44,6 +44,9 @@ def _load():
         'ttk_hrnet_profile_read': (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         'ttk_decode_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_heatmap_decode': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
+        'ttk_filter_ball': (i32, [vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
+        'ttk_filter_table_workspace_bytes': (sz, [i32, i32, i32]),
+        'ttk_filter_table': (i32, [vp, vp, i32, i32, i32, C.c_double, C.c_double, i32, vp, vp, sz, vp]),
         'ttk_trajectory_pack': (i32, [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
         'ttk_uplift_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
         'ttk_uplift_destroy': (None, [vp]),

@@ -136,49 +136,24 @@ def load_uplifting_model(model_path):
 
 
 # ---- glue (inference/utils.py) ------------------------------------------------------------------
+def _f64_cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(_device())
+
+
 def filter_trajectory_ball(pred_positions1, pred_positions2, fps):
-    """inference/utils.py:70-102: keep frames where both detectors see the ball and agree within 20 px."""
-    fps = float(fps)
-    diff = np.linalg.norm(pred_positions1[:, :2] - pred_positions2[:, :2], axis=1)
-    keep = ~((diff > 20) | (pred_positions1[:, 2] != BALL_VISIBLE) | (pred_positions2[:, 2] != BALL_VISIBLE))
-    idx = np.nonzero(keep)[0]
-    valid = np.array([pred_positions1[t] for t in idx])[:, :2]      # IndexError on an empty trajectory, like the reference (:98)
-    return valid, idx, np.array([float(t / fps) for t in idx])
-
-
-def _filter_keypoints_with_dbscan(detections, eps=10, min_samples=5):
-    """inference/utils.py:172-232: centroid of the largest DBSCAN cluster (scikit-learn, as in the reference)."""
-    from collections import Counter
-    from sklearn.cluster import DBSCAN
-    detections = np.asarray(detections)
-    if detections.shape[0] < min_samples:
-        return np.mean(detections, axis=0) if detections.shape[0] > 0 else None
-    labels = DBSCAN(eps=eps, min_samples=min_samples).fit(detections).labels_
-    valid = [l for l in labels if l != -1]
-    if not valid:
-        return np.mean(detections, axis=0)
-    best = Counter(valid).most_common(1)[0][0]
-    return np.mean(detections[labels == best], axis=0)
+    """inference/utils.py:70-102: keep frames where both detectors see the ball and agree within 20 px
+    (ttk_filter_ball; numpy in, numpy out like the reference)."""
+    xy, idx, times, offs = ops.filter_ball(_f64_cuda(pred_positions1), _f64_cuda(pred_positions2), float(fps))
+    n = int(offs[1].item())
+    if n == 0:       # the reference slices np.array([])[:, :2] here (:98)
+        raise IndexError('too many indices for array: array is 1-dimensional, but 2 were indexed')
+    return xy[:n].cpu().numpy(), idx[:n].cpu().numpy(), times[:n].cpu().numpy()
 
 
 def filter_trajectory_table(pred_positions1, pred_positions2):
-    """inference/utils.py:137-169: two-model agreement (< 10 px) then DBSCAN(eps=10, min_samples=3) per keypoint."""
-    T = pred_positions1.shape[0]
-    out = []
-    for n in range(pred_positions1.shape[1]):
-        xs, ys = [], []
-        for t in range(T):
-            if pred_positions1[t, n, 2] == KEYPOINT_VISIBLE and pred_positions2[t, n, 2] == KEYPOINT_VISIBLE:
-                d = np.linalg.norm([pred_positions1[t, n, 0] - pred_positions2[t, n, 0], pred_positions1[t, n, 1] - pred_positions2[t, n, 1]])
-                if d < 10:
-                    xs.append(pred_positions1[t, n, 0])
-                    ys.append(pred_positions1[t, n, 1])
-        if len(xs) < 3:
-            out.append([-1, -1, KEYPOINT_INVISIBLE])
-        else:
-            p = _filter_keypoints_with_dbscan(np.stack([xs, ys], axis=1), eps=10, min_samples=3)
-            out.append([p[0], p[1], KEYPOINT_VISIBLE] if p is not None else [-1, -1, KEYPOINT_INVISIBLE])
-    return np.array(out)
+    """inference/utils.py:137-232: two-model agreement (< 10 px), then the centroid of the largest
+    DBSCAN(eps=10, min_samples=3) cluster per keypoint (ttk_filter_table; numpy in, numpy out)."""
+    return ops.filter_table(_f64_cuda(pred_positions1), _f64_cuda(pred_positions2)).cpu().numpy()
 
 
 def _uplifting_transform(ball_coords, table_coords, times):
@@ -275,6 +250,11 @@ class BallDetector(_Detector):
     def predict(self, images, return_heatmaps=True):
         """images: list (length B) of (prev, curr, next) HWC uint8 BGR frames.
         Returns pred_pos (B, 3) float64 [x, y, 1.0] and the heatmaps (B, 1, h, w) float32 (None if return_heatmaps=False)."""
+        pos, hm = self.predict_device(images, return_heatmaps)
+        return pos.cpu().numpy(), (hm.cpu().numpy() if return_heatmaps else None)
+
+    def predict_device(self, images, return_heatmaps=False):
+        """predict() without the device->host copy: positions (B, 3) float64 and heatmaps stay CUDA tensors."""
         flat = [im for triple in images for im in (triple[0], triple[1], triple[2])]
         frames, order, ready = self._upload(flat, self.device)
         consecutive = all(order[3 * i + j] == i + j for i in range(len(images)) for j in range(3))
@@ -287,8 +267,7 @@ class BallDetector(_Detector):
                 frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
             pos, hm = self._run(frames, stride, len(images), return_heatmaps, ready)
-        pos = pos[:, 0].cpu().numpy()
-        return pos, (hm.cpu().numpy() if return_heatmaps else None)
+        return pos[:, 0], hm
 
     def filter_trajectory(self, ball_positions, ball_positions_aux, fps):
         return filter_trajectory_ball(ball_positions, ball_positions_aux, fps)
@@ -308,13 +287,17 @@ class TableDetector(_Detector):
 
     def predict(self, images, return_heatmaps=True):
         """images: list of HWC uint8 BGR frames -> pred_pos (B, 13, 3) float64, heatmaps (B, 1, 13, h, w)."""
+        pos, hm = self.predict_device(images, return_heatmaps)
+        return pos.cpu().numpy(), (hm[:, None].cpu().numpy() if return_heatmaps else None)
+
+    def predict_device(self, images, return_heatmaps=False):
         frames, order, ready = self._upload(list(images), self.device)
         if order != list(range(len(images))):
             torch.cuda.current_stream().wait_event(ready[-1][1])
             frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
             pos, hm = self._run(frames, 1, len(images), return_heatmaps, ready)
-        return pos.cpu().numpy(), (hm[:, None].cpu().numpy() if return_heatmaps else None)
+        return pos, hm
 
     def calibrate_camera(self, keypoints):
         return calibrate_camera(keypoints)
@@ -373,20 +356,23 @@ class TableTennisPipeline:
         self.KEYPOINT_VISIBLE = self.table_detector.KEYPOINT_VISIBLE
 
     def predict(self, images, fps):
+        """interface.py:263-289.  Detections, both filters, the normalise/pad step and the transformer stay on the
+        device: the only host visit is the final result (and T' for slicing it, as in the reference)."""
         image_triples = [(images[i - 1], images[i], images[i + 1]) for i in range(1, len(images) - 1)]
-        ball_positions, _ = self.ball_detector.predict(image_triples, return_heatmaps=False)
+        ball_positions, _ = self.ball_detector.predict_device(image_triples)
         if self.ball_detector_aux is self.ball_detector:
             ball_positions_aux = ball_positions
         else:
-            ball_positions_aux, _ = self.ball_detector_aux.predict(image_triples, return_heatmaps=False)
-        filtered_ball_positions, valid_indices_ball, times_ball = self.ball_detector.filter_trajectory(ball_positions, ball_positions_aux, fps)
-        table_keypoints, _ = self.table_detector.predict(images, return_heatmaps=False)
+            ball_positions_aux, _ = self.ball_detector_aux.predict_device(image_triples)
+        ball_xy, _, times_ball, offsets = ops.filter_ball(ball_positions, ball_positions_aux, float(fps))
+        table_keypoints, _ = self.table_detector.predict_device(images)
         if self.table_detector_aux is self.table_detector:
             table_keypoints_aux = table_keypoints
         else:
-            table_keypoints_aux, _ = self.table_detector_aux.predict(images, return_heatmaps=False)
-        filtered_table_keypoints = self.table_detector_aux.filter_trajectory(table_keypoints, table_keypoints_aux)
-        ball_coords, table_coords, times, mask = _uplifting_transform(filtered_ball_positions, filtered_table_keypoints, times_ball)
+            table_keypoints_aux, _ = self.table_detector_aux.predict_device(images)
+        filtered_table_keypoints = ops.filter_table(table_keypoints, table_keypoints_aux)
+        ball_coords, table_coords, times, mask = ops.trajectory_pack(ball_xy, times_ball, offsets, filtered_table_keypoints[None],
+                                                                    SEQ_LEN, WIDTH, HEIGHT)
         return self.uplifting_model.predict_without_normalization(ball_coords, table_coords, mask, times)
 
     def calibrate_camera(self, keypoints):

@@ -107,3 +107,36 @@ def project(points, mext, mint):
     out = torch.empty((pts.shape[0], 2), dtype=dt, device=pts.device)
     check(lib.ttk_project(ptr(pts), ptr(me), ptr(mi), pts.shape[0], 1 if f64 else 0, ptr(out), stream_ptr()))
     return out
+
+
+def filter_ball(pos1, pos2, fps, threshold=20.0):
+    """filter_trajectory_ball (inference/utils.py:70-102) on the device.  pos1/pos2: (T, 3) float64 CUDA (x, y, v).
+    Returns compacted xy (T, 2) f64, idx (T,) int64, times (T,) f64 (the first n rows are valid) and offsets (2,) int32
+    = [0, n] -- n stays on the device; `trajectory_pack` takes `offsets` directly."""
+    _lib.require_device()
+    assert pos1.is_cuda and pos1.dtype == torch.float64 and pos1.shape == pos2.shape and pos1.dim() == 2 and pos1.shape[1] == 3
+    pos1, pos2 = pos1.contiguous(), pos2.contiguous()
+    T, dev = pos1.shape[0], pos1.device
+    xy = torch.empty((T, 2), dtype=torch.float64, device=dev)
+    idx = torch.empty((T,), dtype=torch.int64, device=dev)
+    times = torch.empty((T,), dtype=torch.float64, device=dev)
+    offs = torch.empty((2,), dtype=torch.int32, device=dev)
+    check(lib.ttk_filter_ball(ptr(pos1), ptr(pos2), T, float(fps), float(threshold), ptr(xy), ptr(idx), ptr(times), ptr(offs),
+                              stream_ptr()))
+    return xy, idx, times, offs
+
+
+def filter_table(pos1, pos2, agree=10.0, eps=10.0, min_samples=3):
+    """filter_trajectory_table + DBSCAN (inference/utils.py:137-232) on the device.  pos1/pos2: (T, K, 3) or
+    (clips, T, K, 3) float64 CUDA -> (K, 3) / (clips, K, 3) float64 CUDA."""
+    _lib.require_device()
+    assert pos1.is_cuda and pos1.dtype == torch.float64 and pos1.shape == pos2.shape and pos1.dim() in (3, 4) and pos1.shape[-1] == 3
+    single = pos1.dim() == 3
+    a, b = (p.contiguous().view((1,) + tuple(p.shape)) if single else p.contiguous() for p in (pos1, pos2))
+    n, T, K, _ = a.shape
+    out = torch.empty((n, K, 3), dtype=torch.float64, device=a.device)
+    ws_bytes = lib.ttk_filter_table_workspace_bytes(n, T, K)
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=a.device)
+    check(lib.ttk_filter_table(ptr(a), ptr(b), n, T, K, float(agree), float(eps), int(min_samples), ptr(out), ptr(ws), ws_bytes,
+                               stream_ptr()))
+    return out[0] if single else out

@@ -101,6 +101,34 @@ TTK_API int ttk_hrnet_profile_count(const ttk_hrnet* h);
 TTK_API int ttk_hrnet_profile_read(ttk_hrnet* h, int i, int* op_type, int* conv_index, float* ms, double* flops, double* bytes);
 
 /* ---------------------------------------------------------------------------------------
+ * ViTPose-small heatmap detector (SURVEY.md section 8 row a4' / 8f row 4): ViT backbone
+ * (patch 16, dim 384, depth 12, 12 heads) + two transposed convolutions + 1x1 conv.
+ * Replaces VitPose.forward (balldetection/models/vitpose.py:92-103, tabledetection/models/vitpose.py),
+ * ViT.forward (vit_pose/vit_models/backbone/vit.py:375-389) and TopdownHeatmapSimpleHead.forward
+ * (vit_pose/vit_models/head/topdown_heatmap_simple_head.py:188-193); weights from load_model
+ * (inference/inference_balldetection.py:40-61).
+ */
+typedef struct ttk_vit ttk_vit;
+/* in_ch 9 (ball: 3 stacked frames) or 3 (table); out_ch 1 or 13; height x width: the fixed input
+ * resolution (the position embedding is tied to it: 640 x 1152 for balldetection/config.py:82-83). */
+TTK_API int ttk_vit_create(int in_ch, int out_ch, int height, int width, ttk_vit** out);
+TTK_API void ttk_vit_destroy(ttk_vit* h);
+TTK_API int ttk_vit_num_params(const ttk_vit* h);
+/* name: state-dict key of the reference module; numel: element count (row-major, as stored by torch). */
+TTK_API int ttk_vit_param_info(const ttk_vit* h, int i, char* name, int* numel);
+TTK_API int ttk_vit_set_param(ttk_vit* h, int i, const float* data_host, int numel);
+/* returns the token count; hp/wp (may be NULL) receive the token grid.  Heatmaps are 4hp x 4wp. */
+TTK_API int ttk_vit_tokens(const ttk_vit* h, int* hp, int* wp);
+TTK_API int ttk_vit_set_subbatch(ttk_vit* h, int images);
+TTK_API size_t ttk_vit_workspace_bytes(const ttk_vit* h, int batch, int dtype);
+/* x_dev: batch x in_ch x height x width float32 (NCHW, the reference's input tensor);
+ * heatmaps_dev: batch x out_ch x 4hp x 4wp float32.  dtype TTK_F32: float32 SIMT kernels (parity with
+ * the CPU reference); TTK_BF16: bf16 operands on tcgen05 tensor cores, float32 accumulate/residual. */
+TTK_API int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dtype, float* heatmaps_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+TTK_API int ttk_vit_last_launches(const ttk_vit* h);
+
+/* ---------------------------------------------------------------------------------------
  * Heatmap decode: first-max argmax + 3x3 zero-padded window + bounded Gaussian fit +
  * heatmap->image rescale.  Replaces extract_position_torch_gaussian,
  * tabledetection/helper_tabledetection.py:50-156 (variant TABLE; interface.py:116,169) and
@@ -154,6 +182,29 @@ TTK_API int ttk_filter_table(const double* pos1_dev, const double* pos2_dev, int
 TTK_API int ttk_trajectory_pack(const double* ball_xy_dev, const double* times_dev, const int32_t* offsets_dev,
                         const double* table_dev, int n_clips, int seq_len, double img_w, double img_h,
                         float* ball_out, float* table_out, float* times_out, float* mask_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Camera calibration from the 13 table keypoints.
+ * Replaces calibrate_camera (inference/utils.py:312-329) = calc_cameramatrices(use_ransac=True)
+ * (dataprocessing/regress_cameramatrices.py:119-231) with the DLT start of dataprocessing/my_dlt.py:
+ * DLT on the visible keypoints, n_hypotheses BFGS fits of (fx, fy, t, euler xyz) on keys 10, 11 + the
+ * sampled keys, inlier count at inlier_threshold_px, refit on the inliers of the first best hypothesis.
+ * The optimiser is SciPy's BFGS restated (csrc/calib.h).
+ *
+ * keypoints_dev    : n_clips x 13 x 3 float64 (x, y, v); v == 1 marks a visible keypoint (>= 6 needed)
+ * world_points_dev : 13 x 3 float64 table model (uplifting/helper.py:36-50)
+ * samples_dev      : n_clips x n_hypotheses x n_sample int32, 1-based keypoint ids per hypothesis --
+ *                    the reference draws them with numpy's Generator(42).choice (:138-143), the host
+ *                    computes the same table
+ * mint_out_dev     : n_clips x 3 x 4, mext_out_dev: n_clips x 4 x 4 float64 (what the reference returns)
+ * info_out_dev     : n_clips x 4 int32: inlier count, best hypothesis, BFGS status of the refit
+ *                    (0 converged, 1 maxiter, 2 precision loss, 3 nan), DLT ok
+ */
+TTK_API size_t ttk_calibrate_workspace_bytes(int n_clips, int n_hypotheses);
+TTK_API int ttk_calibrate_camera(const double* keypoints_dev, const double* world_points_dev, const int32_t* samples_dev,
+                         int n_clips, int n_hypotheses, int n_sample, int image_width, int image_height,
+                         double inlier_threshold_px, double* mint_out_dev, double* mext_out_dev, int32_t* info_out_dev,
+                         void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Uplifting transformer (MultiStageModel 'multistage' / 'connectstage', size 'large',

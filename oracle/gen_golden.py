@@ -267,6 +267,57 @@ def gen_filters():
     np.savez_compressed(os.path.join(GOLDEN, 'filters.npz'), **out)
 
 
+def gen_calibration():
+    """calibrate_camera (inference/utils.py:312-329: DLT + 100-hypothesis RANSAC-BFGS + refit) on synthetic table keypoints."""
+    from inference.utils import calibrate_camera
+    from dataprocessing.regress_cameramatrices import DLT, points3d, regress_cameramatrices, calc_cameramatrices
+    from oracle import calibration as oc
+    rng = np.random.default_rng(800)
+    out = {}
+    cases = [dict(noise=0.7, n_outliers=1, n_invisible=1), dict(noise=0.3, n_outliers=2, n_invisible=0),
+             dict(noise=1.5, n_outliers=0, n_invisible=3), dict(noise=0.0, n_outliers=0, n_invisible=0)]
+    for i, kw in enumerate(cases):
+        kp, Mint_true, Mext_true = oc.synthetic_keypoints(rng, **kw)
+        Mint, Mext = calibrate_camera(kp)
+        # the same call as calibrate_camera makes (inference/utils.py:322-327), for the inlier count it discards
+        kd = {j + 1: [(kp[j, 0], kp[j, 1])] for j in range(13) if kp[j, 2] == 1}
+        Mint_b, Mext_b, num_inliers = calc_cameramatrices(kd, resolution=(1920, 1080), use_lm=False, use_ransac=True, use_prints=False)
+        assert np.array_equal(Mint, Mint_b) and np.array_equal(Mext, Mext_b)
+        lst = [(j + 1, (kp[j, 0], kp[j, 1])) for j in range(13) if kp[j, 2] == 1]
+        K, Rt = DLT(lst, points3d)
+        # one plain regression on all points from the DLT start (regress_cameramatrices.py:38-116)
+        Mi1, Me1 = regress_cameramatrices((1920, 1080), lst, points3d, startmatrices=(K, Rt), use_prints=False)
+        out.update({'kp%d' % i: kp, 'Mint%d' % i: Mint, 'Mext%d' % i: Mext, 'true_Mint%d' % i: Mint_true, 'true_Mext%d' % i: Mext_true,
+                    'num_inliers%d' % i: num_inliers, 'dlt_K%d' % i: K, 'dlt_Rt%d' % i: Rt, 'reg_Mint%d' % i: Mi1, 'reg_Mext%d' % i: Me1})
+    out['n'] = len(cases)
+    np.savez_compressed(os.path.join(GOLDEN, 'calibration.npz'), **out)
+
+
+def gen_vitpose(w):
+    """VitPose-small (balldetection/models/vitpose.py:47-103; table variant tabledetection/models/vitpose.py) on a small input."""
+    from oracle import vitpose as ov
+    os.makedirs(os.path.join(w, 'initialization', 'vitpose'), exist_ok=True)
+    torch.save({'model': {}}, os.path.join(w, 'initialization', 'vitpose', 'mae_pretrain_vit_small.pth'))     # MAE init file (:57-66)
+    from balldetection.models.vitpose import VitPose
+    from tabledetection.models.vitpose import VitPose as TableVitPose
+    rng = np.random.default_rng(900)
+    res = (96, 64)                                    # (W, H): 6 x 4 tokens
+    m = VitPose(in_frames=3, model_size='small', resolution=res).eval()
+    m.load_state_dict(ov.random_state_dict(41, 9, 24, 1), strict=True)
+    x = rng.standard_normal((2, 9, 64, 96)).astype(np.float32)
+    with torch.no_grad():
+        y, none = m(torch.from_numpy(x))
+    assert none is None
+    t = TableVitPose(model_size='small', resolution=res).eval()
+    t.load_state_dict(ov.random_state_dict(42, 3, 24, 13), strict=True)
+    xt = rng.standard_normal((1, 3, 64, 96)).astype(np.float32)
+    with torch.no_grad():
+        yt = t(torch.from_numpy(xt))
+    yt = yt[0] if isinstance(yt, tuple) else yt
+    np.savez_compressed(os.path.join(GOLDEN, 'vitpose.npz'), ball_seed=41, ball_x=x, ball_y=y.numpy(), table_seed=42, table_x=xt,
+                        table_y=yt.numpy())
+
+
 def write_checkpoints(w, res=(160, 88)):
     """Reference-format checkpoints with oracle weights, small detector resolution."""
     from oracle import hrnet as oh, uplift as ou
@@ -310,11 +361,14 @@ def main():
     sys.path.insert(0, ROOT)
     torch.set_num_threads(os.cpu_count())
     only = set(sys.argv[1:])
-    for fn in (gen_preprocess, gen_hrnet, gen_decode, gen_uplift, gen_tails, gen_filters):
+    for fn in (gen_preprocess, gen_hrnet, gen_decode, gen_uplift, gen_tails, gen_filters, gen_calibration):
         if only and fn.__name__ not in only:
             continue
         fn()
         print('wrote', fn.__name__)
+    if not only or 'gen_vitpose' in only:
+        gen_vitpose(w)
+        print('wrote gen_vitpose')
     if not only or 'gen_interface' in only:
         gen_interface(w)
         print('wrote gen_interface')

@@ -343,3 +343,58 @@ def test_filters_vs_oracle_random_and_edges(dev):
         n = int(offs[1].item())
         assert n == len(ri) and np.array_equal(xy[:n].cpu().numpy(), rp) and np.array_equal(idx[:n].cpu().numpy(), ri)
         assert np.array_equal(tm[:n].cpu().numpy(), rt)
+
+
+def test_calibration_golden(dev, golden):
+    """calibrate_camera against the reference's outputs.  The reference's fit is chaotic
+    (tests/test_calib_host.py), so parity is stated on what the matrices are used for: the RANSAC inlier count must be
+    identical, the reprojection objective over the inliers within 5 %, each inlier's reprojection error within 1 px,
+    and on noise-free keypoints the matrices themselves agree to 1e-4 relative."""
+    from oracle import calibration as oc
+    from upliftingtabletennis_b200 import ops
+    from upliftingtabletennis_b200.interface import calibrate_camera
+    g = golden('calibration')
+    for i in range(int(g['n'])):
+        kp = g['kp%d' % i]
+        Mi, Me = calibrate_camera(kp)
+        assert Mi.shape == (3, 4) and Me.shape == (4, 4) and Mi.dtype == np.float64
+        assert Mi[0, 2] == 960 and Mi[1, 2] == 540 and np.array_equal(Me[3], [0, 0, 0, 1])
+        _, _, info = ops.calibrate_camera(torch.from_numpy(kp[None]).to(dev), torch.from_numpy(ops.ransac_sample_table(kp[None])).to(dev))
+        assert int(info[0, 0]) == int(g['num_inliers%d' % i]), i
+        e, e_ref = oc.reprojection_error(kp, Mi, Me), oc.reprojection_error(kp, g['Mint%d' % i], g['Mext%d' % i])
+        sel = np.argsort(e_ref)[:int(g['num_inliers%d' % i])]
+        assert e[sel].sum() <= 1.05 * e_ref[sel].sum() + 1e-3, (i, e[sel].sum(), e_ref[sel].sum())
+        assert np.abs(e - e_ref)[sel].max() < 1.0, i
+    np.testing.assert_allclose(Mi, g['Mint3'], rtol=1e-4, atol=1e-6)        # case 3: exact projections, unique optimum
+    np.testing.assert_allclose(Me, g['Mext3'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(Mi, g['true_Mint3'], rtol=1e-4, atol=1e-6)
+
+
+def test_calibration_batch_and_edges(dev):
+    from oracle import calibration as oc
+    from upliftingtabletennis_b200 import ops
+    from upliftingtabletennis_b200.interface import calibrate_camera
+    rng = np.random.default_rng(3)
+    spec = [(int(rng.integers(0, 3)), int(rng.integers(0, 3))) for _ in range(48)]
+    kps = np.stack([oc.synthetic_keypoints(rng, noise=0.5, n_outliers=o, n_invisible=v)[0] for o, v in spec])
+    mint, mext, info = ops.calibrate_camera(torch.from_numpy(kps).to(dev), torch.from_numpy(ops.ransac_sample_table(kps)).to(dev))
+    mint, mext, info = mint.cpu().numpy(), mext.cpu().numpy(), info.cpu().numpy()
+    good = 0
+    for j, (o, v) in enumerate(spec):
+        assert info[j, 3] == 1
+        e = np.sort(oc.reprojection_error(kps[j], mint[j], mext[j]))
+        assert (e[:info[j, 0]] < 3.5).all()                       # what RANSAC called an inlier is explained by the final model
+        good += int(info[j, 0] >= 13 - o - v)
+    assert good >= 44, good                                       # all non-outlier keypoints recovered (RANSAC may miss a few clips)
+    # a clip calibrated alone gives the same answer as inside a batch (hypotheses are independent)
+    Mi, Me = calibrate_camera(kps[5])
+    assert np.array_equal(Mi, mint[5]) and np.array_equal(Me, mext[5])
+    # key 10 invisible: the reference still samples 4 other keys; fewer than 6 visible keypoints: AssertionError (:211)
+    kp = kps[0].copy()
+    kp[:, 2] = 1
+    kp[9] = [-1, -1, 0]
+    Mi, Me = calibrate_camera(kp)
+    assert np.isfinite(Mi).all() and np.isfinite(Me).all()
+    kp[:8, 2] = 0
+    with pytest.raises(AssertionError):
+        calibrate_camera(kp)

@@ -42,11 +42,23 @@ def _load():
         'ttk_hrnet_debug_conv': (i32, [vp, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
         'ttk_hrnet_profile_count': (i32, [vp]),
         'ttk_hrnet_profile_read': (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        'ttk_vit_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
+        'ttk_vit_destroy': (None, [vp]),
+        'ttk_vit_num_params': (i32, [vp]),
+        'ttk_vit_param_info': (i32, [vp, i32, C.c_char_p, C.POINTER(i32)]),
+        'ttk_vit_set_param': (i32, [vp, i32, vp, i32]),
+        'ttk_vit_tokens': (i32, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        'ttk_vit_set_subbatch': (i32, [vp, i32]),
+        'ttk_vit_workspace_bytes': (sz, [vp, i32, i32]),
+        'ttk_vit_forward': (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
+        'ttk_vit_last_launches': (i32, [vp]),
         'ttk_decode_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_heatmap_decode': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
         'ttk_filter_ball': (i32, [vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
         'ttk_filter_table_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_filter_table': (i32, [vp, vp, i32, i32, i32, C.c_double, C.c_double, i32, vp, vp, sz, vp]),
+        'ttk_calibrate_workspace_bytes': (sz, [i32, i32]),
+        'ttk_calibrate_camera': (i32, [vp, vp, vp, i32, i32, i32, i32, i32, C.c_double, vp, vp, vp, vp, sz, vp]),
         'ttk_trajectory_pack': (i32, [vp, vp, vp, vp, i32, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
         'ttk_uplift_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
         'ttk_uplift_destroy': (None, [vp]),

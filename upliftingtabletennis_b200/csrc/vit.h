@@ -1,0 +1,67 @@
+// ViTPose detector internals shared by vit.cu (plan, fp32 parity kernels), gemm_umma.cu (bf16 tcgen05 GEMM) and
+// attn_umma.cu (bf16 tcgen05 flash attention).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "ttk_internal.h"
+
+enum { VIT_ACT_NONE = 0, VIT_ACT_GELU = 1, VIT_ACT_RELU = 2 };
+
+// C[m][n] = act(sum_k A[m][k] W[n][k] + bias[n]) (+ R[m][n]); rows of C optionally scattered to the 2x up-sampled grid of a
+// transposed convolution: m = (img, y, x) on an up_h x up_w grid -> row (img, 2y + py, 2x + px) of a 2up_h x 2up_w grid.
+struct GemmArgs {
+  const void* A;          // [M][K]  (f32 or bf16, K contiguous)
+  const void* W;          // [N][K]
+  const float* bias;      // [N] or null
+  const float* R;         // [M][N] float32 residual or null (may alias C when C is float32)
+  void* C;                // [M][N] f32 or bf16
+  int M, N, K;
+  int act;
+  int c_bf16;             // output type
+  int up_h, up_w, py, px; // up_w == 0: no scatter
+};
+
+struct VitParam {
+  std::string name;
+  std::vector<int> shape;
+  size_t numel;
+  std::vector<float> host;
+  bool set = false;
+};
+
+struct ttk_vit {
+  int in_ch, out_ch, height, width, hp, wp, tokens;
+  std::vector<VitParam> params;
+  bool ready = false;
+  int launches = 0;
+  int subbatch = 8;
+  // prepared device weights (float32 and bf16 copies of every GEMM operand)
+  float* f32_pool = nullptr;
+  __nv_bfloat16* bf16_pool = nullptr;
+  struct Lin {
+    size_t w_off, b_off;    // offsets (elements) into the pools; bias always float32
+    int n, k;
+  };
+  Lin patch;
+  size_t pos_off;           // [tokens][384] float32: pos_embed[1:] + pos_embed[:1]
+  struct Block {
+    size_t ln1w, ln1b, ln2w, ln2b;
+    Lin qkv, proj, fc1, fc2;
+  };
+  std::vector<Block> blocks;
+  size_t lnfw, lnfb;
+  Lin deconv[2][4];         // [layer][parity py*2+px], BN folded, K = 4 taps x Cin
+  size_t final_w, final_b;  // [out_ch][256], [out_ch]
+  int find(const std::string& n) const {
+    for (size_t i = 0; i < params.size(); ++i)
+      if (params[i].name == n) return (int)i;
+    return -1;
+  }
+};
+
+// gemm_umma.cu: bf16 operands through TMA, tcgen05.mma, fp32 accumulation in TMEM.  Returns TTK_ERR_UNSUPPORTED for shapes
+// it has no kernel for (the caller then reports the error; there is no silent fallback).
+int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st);
+// attn_umma.cu: softmax(q k^T / sqrt(32)) v per (image, head) on tensor cores.  qkv [T][3*dim] bf16, out [T][dim] bf16.
+int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, int images, int tokens, int heads, int head_dim, cudaStream_t st);

@@ -15,6 +15,7 @@ import torch
 
 from . import ops
 from .detector import MyHRNet, WASBNet
+from .vitpose import TableVitPose, VitPose
 from .uplift import get_model as get_uplifting_model
 
 HEIGHT, WIDTH = 1080, 1920          # inference/utils.py:22
@@ -83,16 +84,19 @@ class _DetectorTransform:
 def _unsupported(model_name):
     return NotImplementedError(
         f"model '{model_name}': its architecture is not part of the reference repository (segformer++ is fetched from "
-        "KieDani/SegformerPlusPlus at construction time) or has no B200 kernels yet (vitpose); available: 'wasb' / 'hrnet'")
+        "KieDani/SegformerPlusPlus at construction time); available: 'wasb' / 'hrnet' / 'vitpose'")
 
 
 def load_ball_model(model_path):
     load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
     info = load_dict['additional_info']
     model_name, resolution, in_frames = info['model_name'], info['image_resolution'], info['in_frames']
-    if model_name != 'wasb':
+    if model_name == 'wasb':                 # get_model, balldetection/train.py:249-271
+        model = WASBNet(in_frames=in_frames, resolution=resolution, pretraining=False)
+    elif model_name == 'vitpose':
+        model = VitPose(in_frames=in_frames, model_size='small', resolution=resolution, pretraining=False)
+    else:
         raise _unsupported(model_name)
-    model = WASBNet(in_frames=in_frames, resolution=resolution, pretraining=False)
     model.load_state_dict(load_dict['model_state_dict'])
     model.eval()
     print(f'Loaded BallDetection model: {model_name} with resolution {resolution}')
@@ -104,9 +108,12 @@ def load_table_model(model_path):
     load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
     info = load_dict['additional_info']
     model_name, resolution = info['model_name'], info['image_resolution']
-    if model_name != 'hrnet':
+    if model_name == 'hrnet':                # get_model, tabledetection/train.py:205-225
+        model = MyHRNet(resolution=resolution, pretraining=False)
+    elif model_name == 'vitpose':
+        model = TableVitPose(model_size='small', resolution=resolution, pretraining=False)
+    else:
         raise _unsupported(model_name)
-    model = MyHRNet(resolution=resolution, pretraining=False)
     model.load_state_dict(load_dict['model_state_dict'])
     model.eval()
     print(f'Loaded tabledetection model: {model_name} with resolution {resolution}')
@@ -189,8 +196,12 @@ class _Detector:
             while ready is not None and waited < len(ready) and (waited == 0 or ready[waited - 1][0] < f_hi):
                 main.wait_event(ready[waited][1])
                 waited += 1
-            x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
-            hm = self.model.heatmaps_from_nhwc16(x)
+            if getattr(self.model, 'input_layout', 'nhwc16') == 'nchw':       # ViTPose: the reference's NCHW float32 tensor
+                x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nchw')
+                hm = self.model.heatmaps(x)
+            else:
+                x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
+                hm = self.model.heatmaps_from_nhwc16(x)
             # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian
             pos.append(ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table'))
             if return_heatmaps:
@@ -307,9 +318,19 @@ class TableDetector(_Detector):
 
 
 def calibrate_camera(table_coords):
-    """inference/utils.py:312-329 (DLT + RANSAC-BFGS, dataprocessing/regress_cameramatrices.py): SURVEY.md section 8f row 3,
-    not on the predict path -- not built yet."""
-    raise NotImplementedError('camera calibration (SURVEY.md section 8f, row 3) is not part of this build yet')
+    """inference/utils.py:312-329: DLT start + 100-hypothesis RANSAC of BFGS fits + refit on the inliers
+    (dataprocessing/regress_cameramatrices.py), all hypotheses concurrently on the GPU (ttk_calibrate_camera).
+    table_coords (13, 3) -> Mint (3, 4), Mext (4, 4) float64 numpy, like the reference returns."""
+    kp = np.ascontiguousarray(table_coords, dtype=np.float64).reshape(1, 13, 3)
+    samples = ops.ransac_sample_table(kp)
+    dev = _device()
+    mint, mext, info = ops.calibrate_camera(torch.from_numpy(kp).to(dev), torch.from_numpy(samples).to(dev), WIDTH, HEIGHT)
+    info = info.cpu().numpy()[0]
+    if not info[3]:
+        raise ValueError("Intrinsic matrix K has K[2,2] close to zero, indicating a degenerate camera.")     # my_dlt.py:128
+    if info[0] == 0:
+        raise ValueError("RANSAC failed to find a valid model.")
+    return mint[0].cpu().numpy(), mext[0].cpu().numpy()
 
 
 class UpliftingModel:

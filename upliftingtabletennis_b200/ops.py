@@ -140,3 +140,50 @@ def filter_table(pos1, pos2, agree=10.0, eps=10.0, min_samples=3):
     check(lib.ttk_filter_table(ptr(a), ptr(b), n, T, K, float(agree), float(eps), int(min_samples), ptr(out), ptr(ws), ws_bytes,
                                stream_ptr()))
     return out[0] if single else out
+
+
+TABLE_HEIGHT, TABLE_WIDTH, TABLE_LENGTH = 0.76, 1.525, 2.74          # uplifting/helper.py:32-34
+TABLE_POINTS = np.array([                                           # uplifting/helper.py:36-50
+    [-TABLE_LENGTH / 2, TABLE_WIDTH / 2, TABLE_HEIGHT], [-TABLE_LENGTH / 2, -TABLE_WIDTH / 2, TABLE_HEIGHT],
+    [0.0, TABLE_WIDTH / 2, TABLE_HEIGHT], [0.0, -TABLE_WIDTH / 2, TABLE_HEIGHT],
+    [TABLE_LENGTH / 2, TABLE_WIDTH / 2, TABLE_HEIGHT], [TABLE_LENGTH / 2, -TABLE_WIDTH / 2, TABLE_HEIGHT],
+    [0.0, TABLE_WIDTH / 2 + 0.1525, TABLE_HEIGHT], [0.0, -(TABLE_WIDTH / 2 + 0.1525), TABLE_HEIGHT],
+    [0.0, 0.0, TABLE_HEIGHT], [0.0, TABLE_WIDTH / 2 + 0.1525, TABLE_HEIGHT + 0.1525],
+    [0.0, -(TABLE_WIDTH / 2 + 0.1525), TABLE_HEIGHT + 0.1525], [-TABLE_LENGTH / 2, 0, TABLE_HEIGHT],
+    [TABLE_LENGTH / 2, 0, TABLE_HEIGHT]], dtype=np.float64)
+RANSAC_ITERATIONS, RANSAC_POINTS, RANSAC_FIXED_KEYS, RANSAC_THRESHOLD = 100, 6, (10, 11), 3.5     # regress_cameramatrices.py:129-136
+
+
+def ransac_sample_table(keypoints_host):
+    """Hypothesis table of regress_cameramatrices_ransac (:138-143) for (n, 13, 3) host keypoints: (n, 100, 4) int32
+    1-based ids, drawn like the reference (numpy Generator(seed=42).choice over the visible non-fixed keys, per clip).
+    Data independent host logic; raises like the reference when fewer than 6 keypoints are visible."""
+    tables = []
+    for kp in keypoints_host:
+        keys = [i + 1 for i in range(len(kp)) if kp[i][2] == 1]
+        assert len(keys) >= 6, 'not enough points for DLT'
+        rnd = np.random.default_rng(seed=42)
+        pool = [k for k in keys if k not in RANSAC_FIXED_KEYS]
+        tables.append([[int(s) for s in rnd.choice(pool, size=RANSAC_POINTS - len(RANSAC_FIXED_KEYS), replace=False)]
+                       for _ in range(RANSAC_ITERATIONS)])
+    return np.asarray(tables, dtype=np.int32)
+
+
+def calibrate_camera(keypoints, samples, width=1920, height=1080, threshold=RANSAC_THRESHOLD):
+    """calibrate_camera (inference/utils.py:312-329) for a batch of clips.  keypoints (n, 13, 3) float64 CUDA,
+    samples (n, H, S) int32 CUDA from `ransac_sample_table`.  Returns Mint (n, 3, 4), Mext (n, 4, 4) float64 and
+    info (n, 4) int32 [inliers, best hypothesis, BFGS status of the refit, DLT ok], all CUDA."""
+    _lib.require_device()
+    assert keypoints.is_cuda and keypoints.dtype == torch.float64 and keypoints.dim() == 3 and keypoints.shape[1:] == (13, 3)
+    assert samples.is_cuda and samples.dtype == torch.int32 and samples.dim() == 3 and samples.shape[0] == keypoints.shape[0]
+    kp, smp = keypoints.contiguous(), samples.contiguous()
+    n, dev = kp.shape[0], kp.device
+    world = torch.from_numpy(TABLE_POINTS).to(dev)
+    mint = torch.empty((n, 3, 4), dtype=torch.float64, device=dev)
+    mext = torch.empty((n, 4, 4), dtype=torch.float64, device=dev)
+    info = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    ws_bytes = lib.ttk_calibrate_workspace_bytes(n, smp.shape[1])
+    ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+    check(lib.ttk_calibrate_camera(ptr(kp), ptr(world), ptr(smp), n, smp.shape[1], smp.shape[2], int(width), int(height),
+                                   float(threshold), ptr(mint), ptr(mext), ptr(info), ptr(ws), ws_bytes, stream_ptr()))
+    return mint, mext, info

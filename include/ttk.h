@@ -127,6 +127,14 @@ TTK_API size_t ttk_vit_workspace_bytes(const ttk_vit* h, int batch, int dtype);
 TTK_API int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dtype, float* heatmaps_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 TTK_API int ttk_vit_last_launches(const ttk_vit* h);
+/* Test hooks: the detector's two building blocks on caller buffers (dtype TTK_F32: float32 SIMT kernels, TTK_BF16: tcgen05).
+ * GEMM: C[m][n] = act(sum_k A[m][k] W[n][k] + bias[n]) (+ R[m][n]); act 0 none, 1 GELU (erf), 2 ReLU; A, W in `dtype`;
+ * C bf16 when c_bf16 else float32; up_w > 0 scatters row (img, y, x) of an up_h x up_w grid to (img, 2y+py, 2x+px) of the 2x grid.
+ * Attention: qkv [images*tokens][1152] in `dtype` -> out [images*tokens][384] (12 heads of 32), scratch for the bf16 path. */
+TTK_API int ttk_vit_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* res_dev, void* c_dev, int m, int n,
+                       int k, int act, int c_bf16, int up_h, int up_w, int py, int px, int dtype, void* stream);
+TTK_API int ttk_vit_debug_attention(const void* qkv_dev, void* out_dev, void* scratch_dev, size_t scratch_bytes, int images, int tokens,
+                            int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Heatmap decode: first-max argmax + 3x3 zero-padded window + bounded Gaussian fit +

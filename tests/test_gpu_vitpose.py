@@ -56,3 +56,101 @@ def test_vitpose_fp32_vs_oracle(dev, res, batch):
         top2 = np.partition(flat, -2)[-2:]
         if top2[1] - top2[0] > 2 * (1e-4 * np.abs(ref).max() + 1e-5):
             assert int(y[b, 0].flatten().argmax()) == int(flat.argmax())
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 tensor-core path: the two tcgen05 kernels against torch on the same bf16 operands, then the whole detector
+# ------------------------------------------------------------------------------------------------
+def _gemm(dev, M, N, K, act, res, c_bf16, up=None, seed=0):
+    from upliftingtabletennis_b200 import _lib
+    from upliftingtabletennis_b200._lib import lib, check, ptr, stream_ptr
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.bfloat16).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(torch.bfloat16).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    R = torch.randn(M, N, generator=g).to(dev) if res else None
+    ref = A.float() @ W.float().t() + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if act == 2:
+        ref = torch.relu(ref)
+    if res:
+        ref = ref + R
+    rows = M
+    up_h = up_w = py = px = 0
+    if up:
+        up_h, up_w, py, px = up
+        rows = 4 * M
+    C = torch.full((rows, N), float('nan'), dtype=torch.bfloat16 if c_bf16 else torch.float32, device=dev)
+    check(lib.ttk_vit_debug_gemm(ptr(A), ptr(W), ptr(bias), ptr(R) if res else None, ptr(C), M, N, K, act, int(c_bf16), up_h, up_w, py, px,
+                                 _lib.BF16, stream_ptr()))
+    torch.cuda.synchronize()
+    if up:
+        m = torch.arange(M, device=dev)
+        x, y, img = m % up_w, (m // up_w) % up_h, m // (up_w * up_h)
+        idx = (img * 2 * up_h + 2 * y + py) * 2 * up_w + 2 * x + px
+        out = C[idx]
+        mask = torch.ones(rows, dtype=torch.bool, device=dev)
+        mask[idx] = False
+        assert torch.isnan(C[mask].float()).all()           # rows of the other parities are untouched
+    else:
+        out = C
+    err = (out.float() - ref).abs().max().item()
+    tol = (2e-2 if c_bf16 else 2e-3) * ref.abs().max().item()
+    assert err <= tol, (M, N, K, err, tol)
+
+
+@pytest.mark.parametrize('M,N,K,act,res,c_bf16', [
+    (2880, 384, 2304, 0, True, False),       # patch embedding of one image (+ position table as residual)
+    (5760, 1152, 384, 0, False, True),       # qkv
+    (5760, 1536, 384, 1, False, True),       # fc1 + GELU
+    (5760, 384, 1536, 0, True, False),       # fc2 + residual, float32 stream
+    (300, 384, 384, 0, True, False),         # partial M tile
+    (24, 1152, 384, 0, False, True),         # fewer rows than one tile
+    (130, 128, 64, 2, False, True),          # BN = 128 path, single K block
+])
+def test_gemm_umma(dev, M, N, K, act, res, c_bf16):
+    _gemm(dev, M, N, K, act, res, c_bf16)
+
+
+def test_gemm_umma_deconv_scatter(dev):
+    _gemm(dev, 2 * 40 * 72, 256, 1536, 2, False, True, up=(40, 72, 1, 0))
+    _gemm(dev, 5 * 7 * 3, 256, 1024, 2, False, True, up=(5, 7, 0, 1))
+
+
+@pytest.mark.parametrize('images,tokens', [(1, 2880), (2, 24), (3, 60), (2, 128), (1, 300)])
+def test_attention_umma(dev, images, tokens):
+    from upliftingtabletennis_b200 import _lib
+    from upliftingtabletennis_b200._lib import lib, check, ptr, stream_ptr
+    g = torch.Generator(device='cpu').manual_seed(tokens)
+    qkv = (torch.randn(images * tokens, 1152, generator=g) * 1.5).to(torch.bfloat16).to(dev)
+    out = torch.full((images * tokens, 384), float('nan'), dtype=torch.bfloat16, device=dev)
+    scratch = torch.empty((images * 384 * (tokens + 8) * 2,), dtype=torch.uint8, device=dev)
+    check(lib.ttk_vit_debug_attention(ptr(qkv), ptr(out), ptr(scratch), scratch.numel(), images, tokens, _lib.BF16, stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().view(images, tokens, 3, 12, 32).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax((q * 32 ** -0.5) @ k.transpose(-2, -1), dim=-1) @ v
+    ref = ref.transpose(1, 2).reshape(images * tokens, 384)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    # and the float32 kernel against the same reference
+    out32 = torch.empty((images * tokens, 384), dtype=torch.float32, device=dev)
+    check(lib.ttk_vit_debug_attention(ptr(qkv.float().contiguous()), ptr(out32), None, 0, images, tokens, _lib.F32, stream_ptr()))
+    assert (out32 - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-5
+
+
+def test_vitpose_bf16_bound(dev, golden):
+    """bf16 tensor-core path, reported separately: relative L2 error of the heatmap against the float32 oracle."""
+    from upliftingtabletennis_b200.vitpose import VitPose
+    for res, batch in (((96, 64), 2), ((1152, 640), 1)):
+        hp, wp = ov.tokens_hw(res[1], res[0])
+        sd = ov.random_state_dict(7, 9, hp * wp, 1)
+        m = VitPose(in_frames=3, resolution=res).to(dev).eval()
+        m.load_state_dict(sd, strict=True)
+        x = np.random.default_rng(1).standard_normal((batch, 9, res[1], res[0])).astype(np.float32)
+        y32, _ = m(torch.from_numpy(x).to(dev))
+        m.compute_dtype = torch.bfloat16
+        y16, _ = m(torch.from_numpy(x).to(dev))
+        assert torch.isfinite(y16).all()
+        rel = ((y16 - y32).norm() / y32.norm()).item()
+        assert rel < 3e-2, (res, rel)

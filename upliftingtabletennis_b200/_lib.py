@@ -52,6 +52,8 @@ def _load():
         'ttk_vit_workspace_bytes': (sz, [vp, i32, i32]),
         'ttk_vit_forward': (i32, [vp, vp, i32, i32, vp, vp, sz, vp]),
         'ttk_vit_last_launches': (i32, [vp]),
+        'ttk_vit_debug_gemm': (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+        'ttk_vit_debug_attention': (i32, [vp, vp, vp, sz, i32, i32, i32, vp]),
         'ttk_decode_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_heatmap_decode': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
         'ttk_filter_ball': (i32, [vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),

@@ -1,7 +1,282 @@
-// bf16 tcgen05 flash attention for the ViTPose detector (placeholder until the kernel lands in the next commit).
+// Multi-head self-attention of the ViTPose backbone on the 5th-generation tensor cores (flash-attention schedule):
+//   out = softmax((q * 32^-0.5) k^T) v per (image, head)      vit_pose/vit_models/backbone/vit.py:160-176 (Attention.forward)
+// qkv [images * tokens][3 * 384] bf16 as the qkv GEMM wrote it (q | k | v, head h at columns h*32 of each third).
+//
+// One CTA = one (image, head, 128-query tile); it walks the key tiles (128 keys) once:
+//   S   = Q K_j^T           tcgen05.mma 128 x 128 x 32, Q / K_j tiles staged by TMA (64-byte swizzle), S in TMEM (128 columns)
+//   P_j = exp2(S*c - m)     thread r owns query row r: two passes over its TMEM row (row maximum, then exponentials), running
+//                           maximum / sum in registers, P_j written as a bf16 K-major A operand (128-byte swizzle) in shared memory
+//   O_j = P_j V_j           tcgen05.mma 128 x 32 x 128; V is staged TRANSPOSED ([dim][key], from a small transpose kernel) so that it
+//                           is an ordinary K-major B operand; O_j lands in TMEM (32 columns) and is folded into the thread's
+//                           float32 accumulator with the usual exp2(m_old - m_new) correction.
+// Warps 0-3 are the softmax / correction warps (TMEM lane quarter = warp), warp 4 issues TMA and MMA.  The kernel needs 160 TMEM
+// columns (256 allocated) and ~90 KB of shared memory, so two CTAs share an SM and one CTA's exponentials overlap the other's MMAs.
+// The exponentials (128 x 128 per tile on the 16/clk MUFU) bound the kernel, not the tensor pipe (head dimension 32).
+#include "umma_prims.h"
 #include "vit.h"
 
-int ttk_attention_umma(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, cudaStream_t) {
-  ttk_set_error("ttk_attention_umma: the bf16 tensor-core path of the ViT detector is not built yet");
-  return TTK_ERR_UNSUPPORTED;
+namespace {
+
+using namespace umma;
+
+constexpr int HD = 32, BQ = 128, BKEY = 128, NST = 3, THREADS = 160;
+constexpr int Q_BYTES = BQ * HD * 2;                 // 8 KB, 64-byte rows
+constexpr int K_BYTES = BKEY * HD * 2;               // 8 KB
+constexpr int V_BYTES = 2 * HD * 128;                // two 64-key chunks of [32 dims][128 B]
+constexpr int KV_BYTES = K_BYTES + V_BYTES;
+constexpr int P_BYTES = 2 * BQ * 128;                // two 64-key chunks of [128 rows][128 B]
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * KV_BYTES + P_BYTES + 256;
+constexpr int TMEM_COLS = 256;
+
+struct AttnMaps {
+  CUtensorMap qkv;     // [images][tokens][3*dim], box {32, 128, 1}, SWIZZLE_64B
+  CUtensorMap vt;      // [images][heads*32][tokens], box {64, 32, 1}, SWIZZLE_128B
+};
+
+// V^T: vt[img][head*32 + d][token] = qkv[img][token][2*dim + head*32 + d]
+__global__ void __launch_bounds__(256) v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, int tokens, int tok_pad, int dim,
+                                                          __nv_bfloat16* __restrict__ vt) {
+  __shared__ __nv_bfloat16 tile[64][HD + 2];
+  const int t0 = blockIdx.x * 64, head = blockIdx.y, img = blockIdx.z;
+  const int heads = dim / HD;
+  for (int i = threadIdx.x; i < 64 * HD; i += 256) {
+    const int t = i / HD, d = i % HD;
+    tile[t][d] = t0 + t < tokens ? qkv[((size_t)img * tokens + t0 + t) * 3 * dim + 2 * dim + head * HD + d] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * HD; i += 256) {
+    const int d = i / 64, t = i % 64;
+    if (t0 + t < tok_pad) vt[((size_t)img * heads * HD + head * HD + d) * tok_pad + t0 + t] = tile[t][d];
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid_constant__ AttnMaps maps, __nv_bfloat16* __restrict__ out,
+                                                                    int tokens, int dim) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Q_BYTES;
+  uint8_t* sP = sKV + NST * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
+  const uint32_t bar_kv_full = smem_u32(bars), bar_kv_empty = bar_kv_full + 8 * NST, bar_q = bar_kv_empty + 8 * NST, bar_s_full = bar_q + 8,
+                 bar_s_empty = bar_s_full + 8, bar_p_full = bar_s_empty + 8, bar_o_full = bar_p_full + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
+  const int nk = (tokens + BKEY - 1) / BKEY;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_kv_full + 8 * s, 1);
+      mbar_init(bar_kv_empty + 8 * s, 1);
+    }
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_empty, 4);
+    mbar_init(bar_p_full, 4);
+    mbar_init(bar_o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + BKEY;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      auto load_kv = [&](int j) {
+        const uint32_t s = j % NST;
+        mbar_expect_tx(bar_kv_full + 8 * s, KV_BYTES);
+        const uint32_t dst = smem_u32(sKV + s * KV_BYTES);
+        tma_load_3d(dst, &maps.qkv, bar_kv_full + 8 * s, dim + head * HD, j * BKEY, img);
+        tma_load_3d(dst + K_BYTES, &maps.vt, bar_kv_full + 8 * s, j * BKEY, head * HD, img);
+        tma_load_3d(dst + K_BYTES + HD * 128, &maps.vt, bar_kv_full + 8 * s, j * BKEY + 64, head * HD, img);
+      };
+      auto issue_s = [&](int j) {
+        const uint32_t s = j % NST;
+        mbar_wait(bar_kv_full + 8 * s, (j / NST) & 1);
+        fence_after();
+        const uint32_t a0 = smem_u32(sQ), b0 = smem_u32(sKV + s * KV_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < HD / 16; ++k16)
+          mma(tS, make_desc(a0 + k16 * 32, 512, 4), make_desc(b0 + k16 * 32, 512, 4), make_idesc(BQ, BKEY), k16 ? 1u : 0u);
+        commit(bar_s_full);
+      };
+      mbar_expect_tx(bar_q, Q_BYTES);
+      tma_load_3d(smem_u32(sQ), &maps.qkv, bar_q, head * HD, q0, img);
+      for (int j = 0; j < NST && j < nk; ++j) load_kv(j);
+      mbar_wait(bar_q, 0);
+      issue_s(0);
+      for (int j = 0; j < nk; ++j) {
+        if (j + 1 < nk) {
+          mbar_wait(bar_s_empty, j & 1);           // softmax has read S_j out of TMEM
+          fence_after();
+          issue_s(j + 1);
+        }
+        mbar_wait(bar_p_full, j & 1);              // P_j is in shared memory (and O_{j-1} has been consumed)
+        fence_after();
+        const uint32_t s = j % NST;
+        const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < BKEY / 16; ++k16)
+          mma(tO, make_desc(p0 + (k16 >> 2) * (BQ * 128) + (k16 & 3) * 32, 1024, 2), make_desc(v0 + (k16 >> 2) * (HD * 128) + (k16 & 3) * 32, 1024, 2),
+              make_idesc(BQ, HD), k16 ? 1u : 0u);
+        commit(bar_kv_empty + 8 * s);
+        commit(bar_o_full);
+        if (j + NST < nk) {                          // refill this stage once P_j V_j has read it
+          mbar_wait(bar_kv_empty + 8 * s, (j / NST) & 1);
+          load_kv(j + NST);
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;               // query row of this thread = TMEM lane
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;      // 32^-0.5 * log2(e)
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    const uint32_t p_row = smem_u32(sP) + row * 128;
+    for (int j = 0; j < nk; ++j) {
+      const int valid = min(BKEY, tokens - j * BKEY);                    // keys of this tile that exist
+      mbar_wait(bar_s_full, j & 1);
+      fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKEY; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_base + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+      }
+      const float m_new = fmaxf(m_run, mx * sl2);
+      const float alpha = exp2f(m_run - m_new);                          // 0 on the first tile
+      // O_{j-1} is complete before P_{j-1} may be overwritten
+      if (j > 0) {
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        fence_after();
+        uint32_t v[32];
+        tmem_ld32(tO + lane_base, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+      }
+      // pass 2: exponentials, row sum, P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKEY; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_base + c, v);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = (c + 2 * i < valid) ? exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new)) : 0.f;
+          const float p1 = (c + 2 * i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new)) : 0.f;
+          lsum += p0 + p1;
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        const uint32_t chunk = p_row + (c >> 6) * (BQ * 128);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t unit = ((c & 63) >> 3) + u;
+          const uint32_t ad = chunk + ((unit ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      alpha_prev = alpha;
+      fence_before();                                // TMEM reads of S_j done -> S may be overwritten
+      fence_async_smem();                            // P_j visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_s_empty);
+        mbar_arrive(bar_p_full);
+      }
+    }
+    mbar_wait(bar_o_full, (nk - 1) & 1);
+    fence_after();
+    {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_base, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+    }
+    if (q0 + row < tokens) {
+      const float inv = 1.f / l_run;
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
+        pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)img * tokens + q0 + row) * dim + head * HD);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) op[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace
+
+size_t ttk_attention_umma_scratch_bytes(int images, int tokens, int heads, int head_dim) {
+  const size_t tok_pad = (size_t)(tokens + 7) / 8 * 8;
+  return (size_t)images * heads * head_dim * tok_pad * 2;
+}
+
+int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_scratch, int images, int tokens, int heads, int head_dim,
+                       cudaStream_t st) {
+  if (head_dim != HD || images <= 0 || tokens <= 0 || images > 65535) {
+    ttk_set_error("ttk_attention_umma: unsupported shape (head_dim %d, tokens %d, images %d)", head_dim, tokens, images);
+    return TTK_ERR_UNSUPPORTED;
+  }
+  const int dim = heads * HD, tok_pad = (tokens + 7) / 8 * 8;
+  EncodeFn enc = get_encode();
+  if (!enc) {
+    ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return TTK_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  __nv_bfloat16* vt = (__nv_bfloat16*)vt_scratch;
+  v_transpose_kernel<<<dim3(ttk_cdiv(tok_pad, 64), heads, images), 256, 0, st>>>(qkv, tokens, tok_pad, dim, vt);
+  TTK_LAUNCH_CHECK();
+  AttnMaps maps;
+  cuuint32_t es[3] = {1, 1, 1};
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)3 * dim, (cuuint64_t)tokens, (cuuint64_t)images};
+    cuuint64_t strides[2] = {(cuuint64_t)3 * dim * 2, (cuuint64_t)tokens * 3 * dim * 2};
+    cuuint32_t box[3] = {HD, BQ, 1};
+    if (enc(&maps.qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(qkv), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      ttk_set_error("ttk_attention_umma: tensor map (qkv) failed");
+      return TTK_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)dim, (cuuint64_t)images};
+    cuuint64_t strides[2] = {(cuuint64_t)tok_pad * 2, (cuuint64_t)dim * tok_pad * 2};
+    cuuint32_t box[3] = {64, HD, 1};
+    if (enc(&maps.vt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      ttk_set_error("ttk_attention_umma: tensor map (v^T) failed");
+      return TTK_ERR_CUDA;
+    }
+  }
+  attention_umma_kernel<<<dim3(ttk_cdiv(tokens, BQ), heads, images), THREADS, SMEM_BYTES, st>>>(maps, out, tokens, dim);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
 }

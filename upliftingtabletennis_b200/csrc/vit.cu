@@ -567,7 +567,7 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
       if ((rc = gemm(w.A, B.qkv, nullptr, w.QKV, T, VIT_ACT_NONE, bf)) != TTK_OK) return rc;
       ++h->launches;
       if (bf) {
-        if ((rc = ttk_attention_umma((const __nv_bfloat16*)w.QKV, (__nv_bfloat16*)w.ATT, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
+        if ((rc = ttk_attention_umma((const __nv_bfloat16*)w.QKV, (__nv_bfloat16*)w.ATT, w.A, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
       } else {
         attention_f32_kernel<<<dim3(ttk_cdiv(h->tokens, 8), HEADS, n), 256, 0, st>>>((const float*)w.QKV, h->tokens, (float*)w.ATT);
       }
@@ -607,5 +607,31 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
       final_conv_kernel<float><<<ttk_cdiv((long long)n * hw_out, 8), 256, 0, st>>>((const float*)feat, fptr(h->final_w), fptr(h->final_b), n, hw_out, h->out_ch, heat);
     TTK_LAUNCH_CHECK();
   }
+  return TTK_OK;
+}
+
+// ---- test hooks: the two tensor-core kernels on caller buffers -----------------------------------------------------------------
+extern "C" int ttk_vit_debug_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* res_dev, void* c_dev, int m,
+                                  int n, int k, int act, int c_bf16, int up_h, int up_w, int py, int px, int dtype, void* stream) {
+  TTK_CHECK_ARG(a_dev && w_dev && c_dev && m > 0 && n > 0 && k > 0, "ttk_vit_debug_gemm: bad arguments");
+  GemmArgs g;
+  g.A = a_dev, g.W = w_dev, g.bias = bias_dev, g.R = res_dev, g.C = c_dev, g.M = m, g.N = n, g.K = k, g.act = act, g.c_bf16 = c_bf16;
+  g.up_h = up_h, g.up_w = up_w, g.py = py, g.px = px;
+  if (dtype == TTK_BF16) return ttk_gemm_umma(g, (cudaStream_t)stream);
+  TTK_CHECK_ARG(n % 64 == 0 && k % 16 == 0 && !c_bf16, "ttk_vit_debug_gemm: the float32 kernel needs N %% 64 == 0 and K %% 16 == 0");
+  gemm_f32_kernel<<<dim3(n / 64, ttk_cdiv(m, 64)), 256, 0, (cudaStream_t)stream>>>(g);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}
+
+extern "C" int ttk_vit_debug_attention(const void* qkv_dev, void* out_dev, void* scratch_dev, size_t scratch_bytes, int images, int tokens,
+                                       int dtype, void* stream) {
+  TTK_CHECK_ARG(qkv_dev && out_dev && images > 0 && tokens > 0, "ttk_vit_debug_attention: bad arguments");
+  if (dtype == TTK_BF16) {
+    TTK_CHECK_ARG(scratch_dev && scratch_bytes >= ttk_attention_umma_scratch_bytes(images, tokens, HEADS, HD), "ttk_vit_debug_attention: scratch too small");
+    return ttk_attention_umma((const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, scratch_dev, images, tokens, HEADS, HD, (cudaStream_t)stream);
+  }
+  attention_f32_kernel<<<dim3(ttk_cdiv(tokens, 8), HEADS, images), 256, 0, (cudaStream_t)stream>>>((const float*)qkv_dev, tokens, (float*)out_dev);
+  TTK_LAUNCH_CHECK();
   return TTK_OK;
 }

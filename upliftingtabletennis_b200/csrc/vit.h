@@ -64,4 +64,7 @@ struct ttk_vit {
 // it has no kernel for (the caller then reports the error; there is no silent fallback).
 int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st);
 // attn_umma.cu: softmax(q k^T / sqrt(32)) v per (image, head) on tensor cores.  qkv [T][3*dim] bf16, out [T][dim] bf16.
-int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, int images, int tokens, int heads, int head_dim, cudaStream_t st);
+// vt_scratch: ttk_attention_umma_scratch_bytes(...) bytes for the transposed V operand.
+size_t ttk_attention_umma_scratch_bytes(int images, int tokens, int heads, int head_dim);
+int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_scratch, int images, int tokens, int heads, int head_dim,
+                       cudaStream_t st);

@@ -143,16 +143,22 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       const int valid = min(BKEY, tokens - j * BKEY);                    // keys of this tile that exist
       mbar_wait(bar_s_full, j & 1);
       fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKEY; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_base + c, v);
-        tmem_wait_ld();
+      // the whole score row into registers, then S is free for the next Q K^T (which overlaps the exponentials below)
+      uint32_t sv[BKEY];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c + i < valid) ? __uint_as_float(v[i]) : -INFINITY);
+      for (int c = 0; c < BKEY; c += 32) tmem_ld32(tS + lane_base + c, sv + c);
+      tmem_wait_ld();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_empty);
+      if (valid < BKEY) {                                                // last key tile only (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < BKEY; ++i)
+          if (i >= valid) sv[i] = 0xff800000u;                           // -inf
       }
+      float mx = __uint_as_float(sv[0]);
+#pragma unroll
+      for (int i = 1; i < BKEY; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
       const float m_new = fmaxf(m_run, mx * sl2);
       const float alpha = exp2f(m_run - m_new);                          // 0 on the first tile
       // O_{j-1} is complete before P_{j-1} may be overwritten
@@ -165,18 +171,15 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
 #pragma unroll
         for (int d = 0; d < HD; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
       }
-      // pass 2: exponentials, row sum, P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
+      // exponentials, row sum, P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
       float lsum = 0.f;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BKEY; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_base + c, v);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = (c + 2 * i < valid) ? exp2f(fmaf(__uint_as_float(v[2 * i]), sl2, -m_new)) : 0.f;
-          const float p1 = (c + 2 * i + 1 < valid) ? exp2f(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m_new)) : 0.f;
+          const float p0 = exp2f(fmaf(__uint_as_float(sv[c + 2 * i]), sl2, -m_new));
+          const float p1 = exp2f(fmaf(__uint_as_float(sv[c + 2 * i + 1]), sl2, -m_new));
           lsum += p0 + p1;
           __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&b2);
@@ -192,13 +195,9 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       l_run = l_run * alpha + lsum;
       m_run = m_new;
       alpha_prev = alpha;
-      fence_before();                                // TMEM reads of S_j done -> S may be overwritten
       fence_async_smem();                            // P_j visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar_s_empty);
-        mbar_arrive(bar_p_full);
-      }
+      if (lane == 0) mbar_arrive(bar_p_full);
     }
     mbar_wait(bar_o_full, (nk - 1) & 1);
     fence_after();

@@ -16,6 +16,7 @@ namespace {
 using namespace umma;
 
 constexpr int BM = 128, BK = 64, THREADS = 192;
+constexpr int STG_ROW = 144;        // bytes per staged output row (128 + 16 padding: conflict-free 16-byte accesses)
 
 struct GemmMaps {
   CUtensorMap a, w;
@@ -27,7 +28,7 @@ struct GCfg {
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = BN == 128 ? 6 : BN == 192 ? 5 : 4;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 1024 + 4 * 32 * STG_ROW;      // + barriers, bias tile, output staging
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -98,19 +99,24 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
       }
     }
   } else {
+    // ===== epilogue warps 2..5: TMEM lane quarter q = warp % 4; thread = accumulator row =====
     const int q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    float* sBias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + 1024 + (warp - 2) * (32 * STG_ROW);
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int et = tid - 64;                        // 0..127 among the epilogue threads
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int tn = tile % tiles_n, tm = tile / tiles_n;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int m = tm * BM + q * 32 + lane;
+      const int m_warp = tm * BM + q * 32;
+      const int m = m_warp + lane;
       const bool live = m < g.M;
-      size_t orow = (size_t)m;
-      if (g.up_w) {
-        const int x = m % g.up_w, y = (m / g.up_w) % g.up_h, img = m / (g.up_w * g.up_h);
-        orow = ((size_t)img * 2 * g.up_h + 2 * y + g.py) * 2 * g.up_w + 2 * x + g.px;
-      }
+      // bias of this tile's columns -> shared memory (read back as broadcasts)
+      asm volatile("bar.sync 1, 128;" ::: "memory");             // previous tile's readers are done
+      for (int i = et; i < BN; i += 128) sBias[i] = g.bias ? __ldg(g.bias + tn * BN + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(bar_tfull + 8 * acc, aph);
       fence_after();
 #pragma unroll 1
@@ -128,20 +134,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
           }
         }
         tmem_wait_ld();
-        if (live) {
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]) + (g.bias ? __ldg(g.bias + n + j) : 0.f);
+          f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
           if (g.act == VIT_ACT_GELU) f[j] = gelu_erf(f[j]);
           if (g.act == VIT_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
         }
-        if (g.R) {
+        if (g.R && live) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += r[j];
         }
+        // stage the warp's 32 x 32 block in shared memory, then write it out with row-contiguous (full sector) stores
+        const uint32_t my = stg_u32 + lane * STG_ROW;
         if (g.c_bf16) {
-          uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)g.C + orow * g.N + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t o[4];
@@ -150,14 +156,33 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
               __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
               o[e] = *reinterpret_cast<uint32_t*>(&b2);
             }
-            op[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
           }
         } else {
-          float4* op = reinterpret_cast<float4*>((float*)g.C + orow * g.N + n);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
         }
+        __syncwarp();
+        const int lpr = g.c_bf16 ? 4 : 8;            // lanes per row (16 bytes each)
+        const int rpi = 32 / lpr;                    // rows per store instruction
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const int rr = r0 + lane / lpr, u = lane % lpr;
+          const int mr = m_warp + rr;
+          if (mr < g.M) {
+            size_t orow = (size_t)mr;
+            if (g.up_w) {
+              const int x = mr % g.up_w, y = (mr / g.up_w) % g.up_h, img = mr / (g.up_w * g.up_h);
+              orow = ((size_t)img * 2 * g.up_h + 2 * y + g.py) * 2 * g.up_w + 2 * x + g.px;
+            }
+            uint4 val;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(stg_u32 + rr * STG_ROW + u * 16));
+            uint8_t* dst = (uint8_t*)g.C + (orow * g.N + n) * (g.c_bf16 ? 2 : 4) + u * 16;
+            *reinterpret_cast<uint4*>(dst) = val;
+          }
         }
+        __syncwarp();
       }
       fence_before();
       __syncwarp();

@@ -4,13 +4,15 @@
 //
 // One CTA = one (image, head, 128-query tile); it walks the key tiles (128 keys) once:
 //   S   = Q K_j^T           tcgen05.mma 128 x 128 x 32, Q / K_j tiles staged by TMA (64-byte swizzle), S in TMEM (128 columns)
-//   P_j = exp2(S*c - m)     thread r owns query row r: two passes over its TMEM row (row maximum, then exponentials), running
-//                           maximum / sum in registers, P_j written as a bf16 K-major A operand (128-byte swizzle) in shared memory
+//   P_j = exp2(S*c - m)     thread r owns query row r: the 128 scores of its TMEM row are pulled into registers at once (S is then
+//                           free, so the next Q K^T overlaps the exponentials), running maximum / sum in registers, P_j written as
+//                           a bf16 K-major A operand (128-byte swizzle) in shared memory
 //   O_j = P_j V_j           tcgen05.mma 128 x 32 x 128; V is staged TRANSPOSED ([dim][key], from a small transpose kernel) so that it
 //                           is an ordinary K-major B operand; O_j lands in TMEM (32 columns) and is folded into the thread's
 //                           float32 accumulator with the usual exp2(m_old - m_new) correction.
-// Warps 0-3 are the softmax / correction warps (TMEM lane quarter = warp), warp 4 issues TMA and MMA.  The kernel needs 160 TMEM
-// columns (256 allocated) and ~90 KB of shared memory, so two CTAs share an SM and one CTA's exponentials overlap the other's MMAs.
+// Warps 0-7 are the softmax / correction warps (TMEM lane quarter = warp % 4, two threads per query row: 64 keys and 16 output
+// dimensions each), warp 8 issues TMA and MMA.  The kernel needs 160 TMEM columns (256 allocated) and ~93 KB of shared memory, so
+// two CTAs share an SM and one CTA's exponentials overlap the other's MMAs.
 // The exponentials (128 x 128 per tile on the 16/clk MUFU) bound the kernel, not the tensor pipe (head dimension 32).
 #include "umma_prims.h"
 #include "vit.h"
@@ -19,14 +21,21 @@ namespace {
 
 using namespace umma;
 
-constexpr int HD = 32, BQ = 128, BKEY = 128, NST = 3, THREADS = 160;
+constexpr int HD = 32, BQ = 128, BKEY = 128, NST = 3, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
 constexpr int Q_BYTES = BQ * HD * 2;                 // 8 KB, 64-byte rows
 constexpr int K_BYTES = BKEY * HD * 2;               // 8 KB
 constexpr int V_BYTES = 2 * HD * 128;                // two 64-key chunks of [32 dims][128 B]
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
 constexpr int P_BYTES = 2 * BQ * 128;                // two 64-key chunks of [128 rows][128 B]
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * KV_BYTES + P_BYTES + 256;
+constexpr int X_BYTES = 6 * BQ * 4;                  // row maxima (2 parities x 2 halves) and row sums (2 halves) exchanged between partner warps
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * KV_BYTES + P_BYTES + X_BYTES + 256;
 constexpr int TMEM_COLS = 256;
+
+__device__ __forceinline__ float ex2(float x) {       // bare MUFU.EX2 (exp2f adds denormal range handling around it)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnMaps {
   CUtensorMap qkv;     // [images][tokens][3*dim], box {32, 128, 1}, SWIZZLE_64B
@@ -57,7 +66,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;
   uint8_t* sP = sKV + NST * KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint8_t* sX = sP + P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + X_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
   const uint32_t bar_kv_full = smem_u32(bars), bar_kv_empty = bar_kv_full + 8 * NST, bar_q = bar_kv_empty + 8 * NST, bar_s_full = bar_q + 8,
                  bar_s_empty = bar_s_full + 8, bar_p_full = bar_s_empty + 8, bar_o_full = bar_p_full + 8;
@@ -72,8 +82,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
     }
     mbar_init(bar_q, 1);
     mbar_init(bar_s_full, 1);
-    mbar_init(bar_s_empty, 4);
-    mbar_init(bar_p_full, 4);
+    mbar_init(bar_s_empty, 8);
+    mbar_init(bar_p_full, 8);
     mbar_init(bar_o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -84,7 +94,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + BKEY;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       auto load_kv = [&](int j) {
         const uint32_t s = j % NST;
@@ -132,67 +142,78 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       }
     }
   } else {
-    const int row = warp * 32 + lane;               // query row of this thread = TMEM lane
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // softmax warps 0..7: warp w and w+4 share TMEM lanes 32 (w % 4) .., i.e. the same 32 query rows; `half` picks the 64 key
+    // columns (= one swizzled P chunk) and the 16 output dimensions a thread owns.  Two threads per row double the warps that
+    // can hide each other's TMEM / MUFU latencies.
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;                  // query row of this thread = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;      // 32^-0.5 * log2(e)
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, o[HD];
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, o[HD / 2];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    const uint32_t p_row = smem_u32(sP) + row * 128;
+    for (int d = 0; d < HD / 2; ++d) o[d] = 0.f;
+    const uint32_t p_row = smem_u32(sP) + half * (BQ * 128) + row * 128;
+    float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima, then [2][128] row sums
+    constexpr int HK = BKEY / 2;
     for (int j = 0; j < nk; ++j) {
-      const int valid = min(BKEY, tokens - j * BKEY);                    // keys of this tile that exist
+      const int valid = min(BKEY, tokens - j * BKEY) - half * HK;        // keys of this thread's half that exist (may be <= 0)
       mbar_wait(bar_s_full, j & 1);
       fence_after();
-      // the whole score row into registers, then S is free for the next Q K^T (which overlaps the exponentials below)
-      uint32_t sv[BKEY];
+      // the thread's 64 scores into registers, then S is free for the next Q K^T (which overlaps the exponentials below)
+      uint32_t sv[HK];
 #pragma unroll
-      for (int c = 0; c < BKEY; c += 32) tmem_ld32(tS + lane_base + c, sv + c);
+      for (int c = 0; c < HK; c += 32) tmem_ld32(tS + lane_base + half * HK + c, sv + c);
       tmem_wait_ld();
       fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_s_empty);
-      if (valid < BKEY) {                                                // last key tile only (warp-uniform)
+      if (valid < HK) {                                                  // last key tile only (warp-uniform)
 #pragma unroll
-        for (int i = 0; i < BKEY; ++i)
+        for (int i = 0; i < HK; ++i)
           if (i >= valid) sv[i] = 0xff800000u;                           // -inf
       }
-      float mx = __uint_as_float(sv[0]);
+      float mx4[4] = {__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]), __uint_as_float(sv[3])};
 #pragma unroll
-      for (int i = 1; i < BKEY; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+      for (int i = 4; i < HK; i += 4) {               // four independent chains
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mx4[k] = fmaxf(mx4[k], __uint_as_float(sv[i + k]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      // row maximum over both halves: exchange through shared memory with the partner warp (named barrier per lane quarter)
+      xch[((j & 1) * 2 + half) * BQ + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BQ + row]);
       const float m_new = fmaxf(m_run, mx * sl2);
-      const float alpha = exp2f(m_run - m_new);                          // 0 on the first tile
-      // O_{j-1} is complete before P_{j-1} may be overwritten
+      const float alpha = ex2(m_run - m_new);                            // 0 on the first tile
+      // exponentials and row sum first (P_j packed in registers): they need neither O_{j-1} nor the P buffer, so they overlap
+      // the P_{j-1} V_{j-1} MMA that is still running
+      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[HK / 2];
+#pragma unroll
+      for (int i = 0; i < HK / 2; ++i) {
+        const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, -m_new));
+        const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -m_new));
+        ls4[i & 3] += p0 + p1;
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        pk[i] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      // O_{j-1} is complete: fold it in, and P_{j-1} may be overwritten
       if (j > 0) {
         mbar_wait(bar_o_full, (j - 1) & 1);
         fence_after();
-        uint32_t v[32];
-        tmem_ld32(tO + lane_base, v);
+        uint32_t v[16];
+        tmem_ld16(tO + lane_base + half * 16, v);
         tmem_wait_ld();
 #pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+        for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
       }
-      // exponentials, row sum, P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
-      float lsum = 0.f;
+      // P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
 #pragma unroll
-      for (int c = 0; c < BKEY; c += 32) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(__uint_as_float(sv[c + 2 * i]), sl2, -m_new));
-          const float p1 = exp2f(fmaf(__uint_as_float(sv[c + 2 * i + 1]), sl2, -m_new));
-          lsum += p0 + p1;
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        const uint32_t chunk = p_row + (c >> 6) * (BQ * 128);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t unit = ((c & 63) >> 3) + u;
-          const uint32_t ad = chunk + ((unit ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
-        }
+      for (int u = 0; u < HK / 8; ++u) {
+        const uint32_t ad = p_row + (((uint32_t)u ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
       }
-      l_run = l_run * alpha + lsum;
+      l_run = l_run * alpha + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
       m_run = m_new;
       alpha_prev = alpha;
       fence_async_smem();                            // P_j visible to the tensor core (async proxy)
@@ -202,23 +223,28 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
     mbar_wait(bar_o_full, (nk - 1) & 1);
     fence_after();
     {
-      uint32_t v[32];
-      tmem_ld32(tO + lane_base, v);
+      uint32_t v[16];
+      tmem_ld16(tO + lane_base + half * 16, v);
       tmem_wait_ld();
 #pragma unroll
-      for (int d = 0; d < HD; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+      for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
     }
+    // row sum over both halves
+    float* lx = xch + 4 * BQ;
+    lx[half * BQ + row] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    l_run += lx[(half ^ 1) * BQ + row];
     if (q0 + row < tokens) {
       const float inv = 1.f / l_run;
-      uint32_t pk[16];
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
         pk[i] = *reinterpret_cast<uint32_t*>(&b2);
       }
-      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)img * tokens + q0 + row) * dim + head * HD);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) op[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)img * tokens + q0 + row) * dim + head * HD + half * 16);
+      op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
   }
   fence_before();

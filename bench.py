@@ -33,6 +33,10 @@ SRC = (1080, 1920)
 WASB_GFLOP_PER_STACK = 344.07        # SURVEY.md section 8d (2*MAC, convs only)
 UPLIFT_GFLOP_PER_TRAJ = 0.753
 UPLIFT_BATCH = 4096
+VIT_RES = (1152, 640)      # ViTPose input resolution (balldetection/config.py:82-83)
+VIT_GFLOP_PER_STACK = 313.5
+VIT_BATCH = 16
+CALIB_CLIPS = 64
 WORKLOAD = 'configs[1]: WASB ball-detect (1280x704 input, 344 GFLOP/stack) + heatmap decode on synthetic 1920x1080 3-frame stacks, batch %d per GPU' % BATCH
 
 
@@ -103,6 +107,12 @@ def make_checkpoints(hub_dir):
         d = os.path.join(w, sub)
         os.makedirs(d, exist_ok=True)
         torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(d, 'model.pt'))
+    from upliftingtabletennis_b200 import vitpose
+    vit_sd = synthetic.vit_state_dict(vitpose.state_dict_layout(9, 2880, 1), seed=5)
+    d = os.path.join(w, 'inference_balldetection', 'vitpose')
+    os.makedirs(d, exist_ok=True)
+    torch.save({'model_state_dict': vit_sd, 'identifier': 'synthetic',
+                'additional_info': {'model_name': 'vitpose', 'image_resolution': VIT_RES, 'in_frames': 3, 'lr': 0.0}}, os.path.join(d, 'model.pt'))
     return wasb_sd, up_sd
 
 
@@ -272,6 +282,34 @@ def main():
         vm = um_d.bool()
         bf16_rel = float(((p16 - p32)[vm].norm() / p32[vm].norm()).item())
 
+    # ---- second detector family (ViTPose-small, SURVEY.md section 8 row a4') and camera calibration, same run ----
+    vit = hubconf.ball_detection('vitpose')
+    vit.model._sync()
+    vit_x = torch.empty((VIT_BATCH, 9, VIT_RES[1], VIT_RES[0]), dtype=torch.float32, device=dev)
+    vit_heat = torch.empty((VIT_BATCH, 1, 4 * vit.model.engine.hp, 4 * vit.model.engine.wp), dtype=torch.float32, device=dev)
+    vit_res = {}
+    for key, dt in (('bf16', torch.bfloat16), ('f32', torch.float32)):
+        def vit_step():
+            ops.preprocess_stacks(frames_dev, 3, 1, VIT_BATCH, VIT_RES[0], VIT_RES[1], layout='nchw', out=vit_x)
+            vit.model.engine.forward(vit_x, dt, out=vit_heat)
+            return ops.decode_heatmaps(vit_heat, SRC[1], SRC[0], 'table')
+        vsteps = args.steps if key == 'bf16' else 1
+        vms = timed(vit_step, vsteps, args.warmup if key == 'bf16' else 1)
+        vit_res[key] = (world * VIT_BATCH * vsteps / (vms * 1e-3), vms / vsteps, vit.model.engine.last_launches() + 3)
+    vit.model.compute_dtype = torch.bfloat16
+    vit_triples = triples[:VIT_BATCH]
+    vit_e2e_ms = timed(lambda: vit.predict(vit_triples, return_heatmaps=False), args.steps, args.warmup)
+    with torch.no_grad():
+        ops.preprocess_stacks(frames_dev, 3, 1, VIT_BATCH, VIT_RES[0], VIT_RES[1], layout='nchw', out=vit_x)
+        h32 = vit.model.engine.forward(vit_x, torch.float32).clone()
+        h16 = vit.model.engine.forward(vit_x, torch.bfloat16)
+        vit_rel = float(((h16 - h32).norm() / h32.norm()).item())
+    kps = synthetic.table_keypoints(CALIB_CLIPS, seed=11 + rank)
+    kps_d = torch.from_numpy(kps).to(dev)
+    smp_d = torch.from_numpy(ops.ransac_sample_table(kps)).to(dev)
+    calib_ms = timed(lambda: ops.calibrate_camera(kps_d, smp_d), args.steps, args.warmup)
+    calib_info = ops.calibrate_camera(kps_d, smp_d)[2].cpu().numpy()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,6 +416,20 @@ def main():
                    'gpu_launches': up_res['bf16'][3], 'bf16_vs_f32_rel_l2': bf16_rel,
                    'f32': {'value': up_res['f32'][0], 'e2e': up_res['f32'][1], 'ms_per_step': up_res['f32'][2], 'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['f32'][0] / 1e3}},
     }
+    line['vitpose'] = {'value': vit_res['bf16'][0], 'unit': 'frames/s', 'dtype': 'bf16', 'batch_per_gpu': VIT_BATCH, 'ms_per_step': vit_res['bf16'][1],
+                       'workload': 'ViTPose-small ball-detect (1152x640 input, 313.5 GFLOP/stack) + decode on the same 1080p stacks',
+                       'e2e': {'value': world * VIT_BATCH * args.steps / (vit_e2e_ms * 1e-3), 'unit': 'frames/s',
+                               'h2d_bytes_per_step': int(frames_pinned[:VIT_BATCH + 2].numel()), 'd2h_bytes_per_step': VIT_BATCH * 3 * 8,
+                               'api': "hubconf.ball_detection('vitpose').predict(triples, return_heatmaps=False)"},
+                       'tflops': VIT_GFLOP_PER_STACK * vit_res['bf16'][0] / 1e3,
+                       'tensor_frac': VIT_GFLOP_PER_STACK * vit_res['bf16'][0] / 1e3 / world / pk['bf16_tflops_sustained'],
+                       'gpu_launches': vit_res['bf16'][2], 'bf16_vs_f32_rel_l2': vit_rel,
+                       'f32': {'value': vit_res['f32'][0], 'ms_per_step': vit_res['f32'][1]}}
+    line['calibration'] = {'value': world * CALIB_CLIPS * args.steps / (calib_ms * 1e-3), 'unit': 'clips/s', 'clips_per_gpu': CALIB_CLIPS,
+                           'ms_per_step': calib_ms / args.steps, 'gpu_launches': 3,
+                           'workload': 'calibrate_camera: DLT + 100 RANSAC hypotheses of SciPy-BFGS fits + refit per clip (13 keypoints, 1 outlier, 1 hidden)',
+                           'median_inliers': float(np.median(calib_info[:, 0])),
+                           'cpu_reference_note': 'the reference needs ~24 s per clip on the host (SURVEY.md section 6; 100 sequential scipy.optimize.minimize calls)'}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -15,12 +15,12 @@ IMAGES_ZIP_FILENAME = "example_images.zip"
 
 
 def ball_detection(model_name='segformerpp_b2', **kwargs):
-    """Loads the Ball Detection Model.  B200 kernels exist for 'wasb' (see DESIGN.md for the segformer++ status)."""
+    """Loads the Ball Detection Model.  B200 kernels exist for 'wasb' and 'vitpose' (see DESIGN.md for the segformer++ status)."""
     return BallDetector(model_name=model_name)
 
 
 def table_detection(model_name='segformerpp_b2', **kwargs):
-    """Loads the Table Detection Model.  B200 kernels exist for 'hrnet'."""
+    """Loads the Table Detection Model.  B200 kernels exist for 'hrnet' and 'vitpose'."""
     return TableDetector(model_name=model_name)
 
 

@@ -355,6 +355,37 @@ def gen_interface(w):
                         spin=spin.numpy(), pos3d=pos3d)
 
 
+def write_vitpose_checkpoints(w, res=(160, 96)):
+    """Reference-format ViTPose checkpoints (ball: 9 -> 1 channels, table: 3 -> 13) with oracle weights."""
+    from oracle import vitpose as ov
+    hp, wp = ov.tokens_hw(res[1], res[0])
+    for sub, sd, info in (
+            ('inference_balldetection/vitpose', ov.random_state_dict(51, 9, hp * wp, 1),
+             {'model_name': 'vitpose', 'image_resolution': res, 'in_frames': 3, 'lr': 1e-4}),
+            ('inference_tabledetection/vitpose', ov.random_state_dict(52, 3, hp * wp, 13),
+             {'model_name': 'vitpose', 'image_resolution': res})):
+        d = os.path.join(w, sub)
+        os.makedirs(d, exist_ok=True)
+        torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(d, 'model.pt'))
+
+
+def gen_interface_vitpose(w):
+    """BallDetector('vitpose') / TableDetector('vitpose').predict (interface.py:83-186) on small frames."""
+    os.makedirs(os.path.join(w, 'initialization', 'vitpose'), exist_ok=True)
+    torch.save({'model': {}}, os.path.join(w, 'initialization', 'vitpose', 'mae_pretrain_vit_small.pth'))
+    write_vitpose_checkpoints(w)
+    import interface
+    rng = np.random.default_rng(650)
+    frames = synthetic_frames(rng, 5, 135, 240)
+    bd = interface.BallDetector('vitpose')
+    triples = [(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 4)]
+    bpos, bhm = bd.predict(triples)
+    td = interface.TableDetector('vitpose')
+    tpos, thm = td.predict(frames[:2])
+    np.savez_compressed(os.path.join(GOLDEN, 'interface_vitpose.npz'), frames=np.stack(frames), ball_pos=bpos, ball_hm=bhm,
+                        table_pos=tpos, table_hm=np.stack([np.asarray(t) for t in thm]))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     w = setup_reference()
@@ -369,6 +400,9 @@ def main():
     if not only or 'gen_vitpose' in only:
         gen_vitpose(w)
         print('wrote gen_vitpose')
+    if not only or 'gen_interface_vitpose' in only:
+        gen_interface_vitpose(w)
+        print('wrote gen_interface_vitpose')
     if not only or 'gen_interface' in only:
         gen_interface(w)
         print('wrote gen_interface')

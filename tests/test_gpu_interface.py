@@ -54,8 +54,27 @@ def test_table_detector_predict(weights, golden):
     np.testing.assert_allclose(hm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
     err = np.abs(pos[..., :2] - g['table_pos'][..., :2]).max(axis=-1)
     assert np.mean(err < 1e-3) >= 0.95, err
-    with pytest.raises(NotImplementedError):
-        td.calibrate_camera(pos[0])
+    assert td.KEYPOINT_VISIBLE == 1          # calibrate_camera / filter_trajectory: tests/test_gpu_parity.py (calibration, filters)
+
+
+def test_vitpose_detectors_predict(weights, golden):
+    """ball_detection('vitpose') / table_detection('vitpose') through the hub entry points against the reference's interface.py."""
+    from oracle.gen_golden import write_vitpose_checkpoints
+    import hubconf
+    write_vitpose_checkpoints(weights)
+    g = golden('interface_vitpose')
+    frames = list(g['frames'])
+    bd = hubconf.ball_detection('vitpose')
+    pos, hm = bd.predict([(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 4)])
+    assert hm.shape == g['ball_hm'].shape and hm.dtype == np.float32 and pos.shape == (3, 3)
+    np.testing.assert_allclose(hm, g['ball_hm'], rtol=0, atol=1e-4 * np.abs(g['ball_hm']).max() + 1e-5)
+    np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=1e-3)
+    td = hubconf.table_detection('vitpose')
+    tpos, thm = td.predict(frames[:2])
+    assert thm.shape == g['table_hm'].shape
+    np.testing.assert_allclose(thm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
+    err = np.abs(tpos[..., :2] - g['table_pos'][..., :2]).max(axis=-1)
+    assert np.mean(err < 1e-3) >= 0.9, err
 
 
 def test_uplifting_model_predict(weights, golden):

@@ -79,3 +79,48 @@ def trajectories(n, seed, T=50):
     table = np.concatenate([rng.uniform(0.2, 0.8, (n, 13, 1)), rng.uniform(0.4, 0.9, (n, 13, 1)),
                             (rng.uniform(0, 1, (n, 13, 1)) > 0.15).astype(np.float64)], axis=-1).astype(np.float32)
     return ball, table, mask, times
+
+
+def vit_state_dict(layout, seed):
+    """layout: [(key, shape)] from vitpose.state_dict_layout(): activations of order one through all 12 blocks."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for key, shape in layout:
+        if key.endswith('num_batches_tracked'):
+            sd[key] = torch.tensor(0, dtype=torch.long)
+            continue
+        if key.endswith('running_var'):
+            a = rng.uniform(0.5, 1.5, shape)
+        elif key.endswith('running_mean'):
+            a = rng.normal(0, 0.1, shape)
+        elif len(shape) == 1 and key.endswith('weight'):
+            a = rng.uniform(0.8, 1.2, shape)
+        elif key.endswith('bias'):
+            a = rng.normal(0, 0.05, shape)
+        elif key.endswith('pos_embed'):
+            a = rng.normal(0, 0.2, shape)
+        else:
+            fan_in = int(np.prod(shape[1:])) if 'deconv' not in key else shape[0] * 4
+            a = rng.normal(0, 1.0 / math.sqrt(fan_in), shape)
+        sd[key] = torch.from_numpy(np.asarray(a, dtype=np.float32))
+    return sd
+
+
+def table_keypoints(n, seed, noise=0.7):
+    """n sets of 13 table keypoints (x, y, v) seen by plausible broadcast cameras, with pixel noise, an outlier and a hidden point."""
+    from .ops import TABLE_POINTS
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 13, 3))
+    for i in range(n):
+        a, b, c = rng.uniform(1.9, 2.2), rng.uniform(-0.1, 0.1), rng.uniform(-0.3, 0.3)
+        rx = np.array([[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]])
+        ry = np.array([[math.cos(b), 0, math.sin(b)], [0, 1, 0], [-math.sin(b), 0, math.cos(b)]])
+        rz = np.array([[math.cos(c), -math.sin(c), 0], [math.sin(c), math.cos(c), 0], [0, 0, 1]])
+        cam = TABLE_POINTS @ (rz @ ry @ rx).T + np.array([rng.uniform(-0.3, 0.3), rng.uniform(0.3, 0.8), rng.uniform(6.0, 9.0)])
+        out[i, :, 0] = 2100.0 * cam[:, 0] / cam[:, 2] + 960 + rng.normal(0, noise, 13)
+        out[i, :, 1] = 2150.0 * cam[:, 1] / cam[:, 2] + 540 + rng.normal(0, noise, 13)
+        out[i, :, 2] = 1.0
+        k = rng.choice([j for j in range(13) if j not in (9, 10)], 2, replace=False)
+        out[i, k[0], :2] += rng.uniform(15, 40, 2)
+        out[i, k[1]] = [-1, -1, 0]
+    return out

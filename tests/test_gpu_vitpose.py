@@ -105,6 +105,8 @@ def _gemm(dev, M, N, K, act, res, c_bf16, up=None, seed=0):
     (5760, 1152, 384, 0, False, True),       # qkv
     (5760, 1536, 384, 1, False, True),       # fc1 + GELU
     (5760, 384, 1536, 0, True, False),       # fc2 + residual, float32 stream
+    (5760, 384, 384, 0, True, False),        # proj + residual (weights resident in shared memory, like qkv / fc1 at this M)
+    (2100, 1152, 384, 0, False, True),       # resident variant with a partial last M tile and idle CTAs
     (300, 384, 384, 0, True, False),         # partial M tile
     (24, 1152, 384, 0, False, True),         # fewer rows than one tile
     (130, 128, 64, 2, False, True),          # BN = 128 path, single K block

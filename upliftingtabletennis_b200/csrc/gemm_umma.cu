@@ -3,8 +3,8 @@
 //   A [M][K] bf16 (activations, K contiguous), W [N][K] bf16 (torch Linear weight as stored) -- both K-major UMMA operands.
 // Persistent CTAs, static tile round-robin (n fastest, so the CTAs working on one 128-row slab of A run together and A is read
 // from HBM once).  Roles: warp 0 = TMA producer (128 x 64 A box + BN x 64 W box per stage, 128-byte swizzle), warp 1 = MMA issuer
-// (one elected thread: 4 x tcgen05.mma 128 x BN x 16 per stage), warps 2-5 = epilogue (tcgen05.ld -> bias / GELU / ReLU /
-// residual -> bf16 or float32 stores; thread = output row).  smem ring of STAGES stages, two TMEM accumulators of BN columns
+// (one elected thread: 4 x tcgen05.mma 128 x BN x 16 per stage), warps 2-9 = epilogue (tcgen05.ld -> bias / GELU / ReLU /
+// residual -> staged, row-contiguous bf16 or float32 stores; thread = output row, two warps per TMEM lane quarter).  smem ring of STAGES stages, two TMEM accumulators of BN columns
 // so the epilogue of tile i overlaps the MMAs of tile i+1.
 // BN is 192 where N allows (384, 1152, 1536): one MMA then computes for 96 clk against 80 clk of operand reads
 // (10 KB at 128 B/clk), i.e. the tensor pipe, not shared memory, is the limiter; N = 256 uses BN = 256, anything else 128.
@@ -15,34 +15,79 @@ namespace {
 
 using namespace umma;
 
-constexpr int BM = 128, BK = 64, THREADS = 192;
-constexpr int STG_ROW = 144;        // bytes per staged output row (128 + 16 padding: conflict-free 16-byte accesses)
+constexpr int BM = 128, BK = 64, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+constexpr int STG_ROW = 80;         // bytes per staged output row piece (64 + 16 padding: conflict-free 16-byte accesses)
 
 struct GemmMaps {
   CUtensorMap a, w;
 };
 
-template <int BN>
+// WRES: the whole BN x K weight tile (K = 384 = 6 k-blocks) stays in shared memory and the CTA walks M tiles of one N tile, so only
+// A streams through the ring.  L2 -> SM operand traffic, not the tensor pipe, bounds the streaming variant (~42 B/clk per SM
+// against 40 KB per 384 clk of MMA); with the weights resident it drops from 40 KB to 16 KB per k-block.
+constexpr int KB_RES = 6;
+template <int BN, bool WRES>
 struct GCfg {
   static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int STAGES = BN == 128 ? 6 : BN == 192 ? 5 : 4;
+  static constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + W_BYTES;
+  static constexpr int STAGES = WRES ? (BN == 192 ? 3 : 6) : (BN == 128 ? 6 : BN == 192 ? 5 : 4);
+  static constexpr int WRES_BYTES = WRES ? KB_RES * W_BYTES : 0;
+  static constexpr int RING_BYTES = WRES_BYTES + STAGES * STAGE_BYTES;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + 256 + 1024 + 4 * 32 * STG_ROW;      // + barriers, bias tile, output staging
+  static constexpr int SMEM_BYTES = 1024 + RING_BYTES + 256 + 1024 + 8 * 32 * STG_ROW;      // + barriers, bias tile, output staging
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// tile walk of one CTA: streaming variant = global round-robin over (m, n) tiles, n fastest; resident variant = M tiles of a fixed n
+template <bool WRES>
+struct Walk {
+  int tn_fixed, first, step, limit, tiles_n;
+  __device__ Walk(int tiles_m, int tiles_n_) : tiles_n(tiles_n_) {
+    if (WRES) {
+      tn_fixed = blockIdx.x % tiles_n;
+      first = blockIdx.x / tiles_n;
+      step = (gridDim.x - tn_fixed + tiles_n - 1) / tiles_n;
+      limit = tiles_m;
+    } else {
+      tn_fixed = 0;
+      first = blockIdx.x;
+      step = gridDim.x;
+      limit = tiles_m * tiles_n;
+    }
+  }
+  __device__ int tn(int t) const { return WRES ? tn_fixed : t % tiles_n; }
+  __device__ int tm(int t) const { return WRES ? t : t / tiles_n; }
+};
 
-template <int BN>
+// exact (erf) GELU with one MUFU: erf(z) = 1 - exp2(-z Q(z)) for 0 <= z <= 4 (Q: degree-5 least-squares fit, |erf error| <= 3.3e-7,
+// |GELU error| <= 4e-7, far below the bf16 resolution of the output); erf(z > 4) = 1 to 1.5e-8.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float q = -1.588800078e-04f;
+  q = fmaf(q, z, 3.746585688e-03f);
+  q = fmaf(q, z, -3.103881516e-02f);
+  q = fmaf(q, z, 1.498060673e-01f);
+  q = fmaf(q, z, 9.181324244e-01f);
+  q = fmaf(q, z, 1.627928257e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * q));
+  const float erf_abs = 1.f - e;
+  return 0.5f * x * (1.f + copysignf(erf_abs, x));
+}
+
+template <int BN, bool WRES, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs g, int tiles_m, int tiles_n) {
-  using C = GCfg<BN>;
+  using C = GCfg<BN, WRES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
-  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::STAGES, bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 16;
+  uint8_t* ring = smem + C::WRES_BYTES;             // [resident W k-blocks][A (+ W) stages]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 5);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * C::STAGES, bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 16,
+                 bar_w = bar_tempty + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int total = tiles_m * tiles_n, kblocks = g.K / BK;
+  const int kblocks = g.K / BK;
+  const Walk<WRES> walk(tiles_m, tiles_n);
 
   if (tid == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -51,8 +96,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_tempty + 8 * i, 8);
     }
+    mbar_init(bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
@@ -64,15 +110,19 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
   if (warp == 0) {
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int tn = tile % tiles_n, tm = tile / tiles_n;
+      if (WRES && walk.first < walk.limit) {          // the weight tile of this CTA's N tile, once
+        mbar_expect_tx(bar_w, C::WRES_BYTES);
+        for (int kb = 0; kb < KB_RES; ++kb) tma_load_2d(smem_u32(smem + kb * C::W_BYTES), &maps.w, bar_w, kb * BK, walk.tn_fixed * BN);
+      }
+      for (int tile = walk.first; tile < walk.limit; tile += walk.step) {
+        const int tn = walk.tn(tile), tm = walk.tm(tile);
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1;
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_expect_tx(bar_full + 8 * s, C::STAGE_BYTES);
-          const uint32_t dst = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t dst = smem_u32(ring + s * C::STAGE_BYTES);
           tma_load_2d(dst, &maps.a, bar_full + 8 * s, kb * BK, tm * BM);
-          tma_load_2d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN);
+          if (!WRES) tma_load_2d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN);
         }
       }
     }
@@ -80,7 +130,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BM, BN);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
+      if (WRES && walk.first < walk.limit) mbar_wait(bar_w, 0);
+      for (int tile = walk.first; tile < walk.limit; tile += walk.step, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);        // accumulator drained by the epilogue (passes at once the first two times)
         fence_after();
@@ -89,7 +140,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
           const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           fence_after();
-          const uint32_t a0 = smem_u32(smem + s * C::STAGE_BYTES), b0 = a0 + C::A_BYTES;
+          const uint32_t a0 = smem_u32(ring + s * C::STAGE_BYTES), b0 = WRES ? smem_u32(smem + kb * C::W_BYTES) : a0 + C::A_BYTES;
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16)
             mma(d, make_desc(a0 + k16 * 32, 1024, 2), make_desc(b0 + k16 * 32, 1024, 2), idesc, (kb | k16) ? 1u : 0u);
@@ -99,34 +150,65 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
       }
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lane quarter q = warp % 4; thread = accumulator row =====
-    const int q = warp & 3;
+    // ===== epilogue warps 2..9: TMEM lane quarter q = warp % 4 (thread = accumulator row), column chunks interleaved between the two
+    // warps of a quarter =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-    float* sBias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
-    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + 1024 + (warp - 2) * (32 * STG_ROW);
-    const uint32_t stg_u32 = smem_u32(stg);
-    const int et = tid - 64;                        // 0..127 among the epilogue threads
+    float* sBias = reinterpret_cast<float*>(smem + C::RING_BYTES + 256);
+    const uint32_t stg_u32 = smem_u32(smem + C::RING_BYTES + 256 + 1024 + (warp - 2) * (32 * STG_ROW));
+    const int et = tid - 64;                        // 0..255 among the epilogue threads
+    // kernel parameters in registers (the asm memory clobbers below would otherwise re-read them from the constant bank)
+    const uint32_t sbias_u32 = smem_u32(sBias);
+    const int gM = g.M, gN = g.N, dbg = g.act >> 8, up_w = g.up_w, up_h = g.up_h, upy = g.py, upx = g.px;
+    const bool c_bf16 = g.c_bf16 != 0;
+    const float* __restrict__ gR = g.R;
+    const float* __restrict__ gBias = g.bias;
+    uint8_t* const gC = (uint8_t*)g.C;
+    const int esz = c_bf16 ? 2 : 4;
+    const int rsel = lane >> 2, usel = lane & 3;    // copy-out: 4 lanes per 64-byte row piece, 8 rows per store instruction
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-      const int tn = tile % tiles_n, tm = tile / tiles_n;
+    for (int tile = walk.first; tile < walk.limit; tile += walk.step, ++tcount) {
+      const int tn = walk.tn(tile), tm = walk.tm(tile);
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       const int m_warp = tm * BM + q * 32;
       const int m = m_warp + lane;
-      const bool live = m < g.M;
+      const bool live = m < gM;
+      // output byte offsets of the four rows this lane copies out (row r0 + lane / 4), -1 = row does not exist
+      long long obase[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mr = m_warp + 8 * i + rsel;
+        size_t orow = (size_t)mr;
+        if (up_w) {
+          const int x = mr % up_w, y = (mr / up_w) % up_h, img = mr / (up_w * up_h);
+          orow = ((size_t)img * 2 * up_h + 2 * y + upy) * 2 * up_w + 2 * x + upx;
+        }
+        obase[i] = mr < gM ? (long long)(orow * gN) * esz + usel * 16 : -1;
+      }
       // bias of this tile's columns -> shared memory (read back as broadcasts)
-      asm volatile("bar.sync 1, 128;" ::: "memory");             // previous tile's readers are done
-      for (int i = et; i < BN; i += 128) sBias[i] = g.bias ? __ldg(g.bias + tn * BN + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");             // previous tile's readers are done
+      for (int i = et; i < BN; i += 256) sBias[i] = gBias ? __ldg(gBias + tn * BN + i) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(bar_tfull + 8 * acc, aph);
       fence_after();
+      if (dbg & 1) {                                  // measurement aid: mainloop only
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        continue;
+      }
+      uint32_t v[32];
+      tmem_ld32(lane_base + acc * BN + half * 32, v);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_base + acc * BN + c0, v);
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
         const int n = tn * BN + c0;
+        float bz[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bz[4 * j]), "=f"(bz[4 * j + 1]), "=f"(bz[4 * j + 2]), "=f"(bz[4 * j + 3]) : "r"(sbias_u32 + c0 * 4 + 16 * j));
         float r[32];
-        if (g.R && live) {
-          const float4* rp = reinterpret_cast<const float4*>(g.R + (size_t)m * g.N + n);
+        if (gR && live) {
+          const float4* rp = reinterpret_cast<const float4*>(gR + (size_t)m * gN + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = rp[j];
@@ -136,53 +218,56 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
         tmem_wait_ld();
         float f[32];
 #pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (c0 + 64 < BN) tmem_ld32(lane_base + acc * BN + c0 + 64, v);      // next chunk's accumulators while this one is processed
+#pragma unroll
         for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[j]) + sBias[c0 + j];
-          if (g.act == VIT_ACT_GELU) f[j] = gelu_erf(f[j]);
-          if (g.act == VIT_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
+          f[j] += bz[j];
+          if (ACT == VIT_ACT_GELU) f[j] = gelu_erf(f[j]);
+          if (ACT == VIT_ACT_RELU) f[j] = fmaxf(f[j], 0.f);
         }
-        if (g.R && live) {
+        if (gR && live) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += r[j];
         }
-        // stage the warp's 32 x 32 block in shared memory, then write it out with row-contiguous (full sector) stores
+        // stage 64-byte row pieces of the warp's 32 x 32 block in shared memory, then write them out row-contiguous (4 lanes per row,
+        // full 32-byte sectors): bf16 = one piece of 32 columns, float32 = two pieces of 16 columns
         const uint32_t my = stg_u32 + lane * STG_ROW;
-        if (g.c_bf16) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-              o[e] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "f"(f[4 * j]), "f"(f[4 * j + 1]), "f"(f[4 * j + 2]), "f"(f[4 * j + 3]) : "memory");
-        }
-        __syncwarp();
-        const int lpr = g.c_bf16 ? 4 : 8;            // lanes per row (16 bytes each)
-        const int rpi = 32 / lpr;                    // rows per store instruction
+        const int pieces = c_bf16 ? 1 : 2;
 #pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += rpi) {
-          const int rr = r0 + lane / lpr, u = lane % lpr;
-          const int mr = m_warp + rr;
-          if (mr < g.M) {
-            size_t orow = (size_t)mr;
-            if (g.up_w) {
-              const int x = mr % g.up_w, y = (mr / g.up_w) % g.up_h, img = mr / (g.up_w * g.up_h);
-              orow = ((size_t)img * 2 * g.up_h + 2 * y + g.py) * 2 * g.up_w + 2 * x + g.px;
+        for (int pc = 0; pc < pieces; ++pc) {
+          if (c_bf16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                o[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
             }
-            uint4 val;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(stg_u32 + rr * STG_ROW + u * 16));
-            uint8_t* dst = (uint8_t*)g.C + (orow * g.N + n) * (g.c_bf16 ? 2 : 4) + u * 16;
-            *reinterpret_cast<uint4*>(dst) = val;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              // f[16 * pc + 4 * j ..]: select without dynamic register indexing
+              const float a0 = pc ? f[16 + 4 * j] : f[4 * j], a1 = pc ? f[17 + 4 * j] : f[4 * j + 1], a2 = pc ? f[18 + 4 * j] : f[4 * j + 2],
+                          a3 = pc ? f[19 + 4 * j] : f[4 * j + 3];
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
+            }
           }
+          __syncwarp();
+          uint4 val[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val[i].x), "=r"(val[i].y), "=r"(val[i].z), "=r"(val[i].w)
+                         : "r"(stg_u32 + (8 * i + rsel) * STG_ROW + usel * 16));
+          const long long coff = (long long)(n + pc * 16) * esz;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (obase[i] >= 0 && !(dbg & 2)) *reinterpret_cast<uint4*>(gC + obase[i] + coff) = val[i];
+          __syncwarp();
         }
-        __syncwarp();
       }
       fence_before();
       __syncwarp();
@@ -194,12 +279,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
   if (warp == 2) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
-template <int BN>
-int launch(const GemmArgs& g, cudaStream_t st) {
-  using C = GCfg<BN>;
+template <int BN, bool WRES, int ACT>
+int launch_act(const GemmArgs& g, cudaStream_t st) {
+  using C = GCfg<BN, WRES>;
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, WRES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
   GemmMaps maps;
@@ -210,9 +295,18 @@ int launch(const GemmArgs& g, cudaStream_t st) {
   }
   const int tiles_m = ttk_cdiv(g.M, BM), tiles_n = g.N / BN;
   const int grid = std::max(1, std::min(tiles_m * tiles_n, ttk_num_sms()));
-  gemm_umma_kernel<BN><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, g, tiles_m, tiles_n);
+  gemm_umma_kernel<BN, WRES, ACT><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, g, tiles_m, tiles_n);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
+}
+
+template <int BN, bool WRES>
+int launch(const GemmArgs& g, cudaStream_t st) {      // the activation is a compile-time parameter of the epilogue
+  switch (g.act & 0xff) {
+    case VIT_ACT_GELU: return launch_act<BN, WRES, VIT_ACT_GELU>(g, st);
+    case VIT_ACT_RELU: return launch_act<BN, WRES, VIT_ACT_RELU>(g, st);
+    default: return launch_act<BN, WRES, VIT_ACT_NONE>(g, st);
+  }
 }
 
 }  // namespace
@@ -222,7 +316,9 @@ int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st) {
     ttk_set_error("ttk_gemm_umma: unsupported shape M %d N %d K %d", g.M, g.N, g.K);
     return TTK_ERR_UNSUPPORTED;
   }
-  if (g.N % 192 == 0) return launch<192>(g, st);
-  if (g.N % 256 == 0) return launch<256>(g, st);
-  return launch<128>(g, st);
+  // K = 384 (qkv, proj, fc1) with enough M tiles per CTA to amortise the weight load: weights resident in shared memory
+  if (g.K == KB_RES * BK && g.M >= 16 * BM) return g.N >= 1152 && g.N % 192 == 0 ? launch<192, true>(g, st) : launch<128, true>(g, st);
+  if (g.N % 192 == 0) return launch<192, false>(g, st);
+  if (g.N % 256 == 0) return launch<256, false>(g, st);
+  return launch<128, false>(g, st);
 }

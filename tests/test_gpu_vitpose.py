@@ -127,7 +127,7 @@ def test_attention_umma(dev, images, tokens):
     g = torch.Generator(device='cpu').manual_seed(tokens)
     qkv = (torch.randn(images * tokens, 1152, generator=g) * 1.5).to(torch.bfloat16).to(dev)
     out = torch.full((images * tokens, 384), float('nan'), dtype=torch.bfloat16, device=dev)
-    scratch = torch.empty((images * 384 * (tokens + 8) * 2,), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((images * 12 * 48 * (tokens + 8) * 2,), dtype=torch.uint8, device=dev)       # V^T + ones row per head
     check(lib.ttk_vit_debug_attention(ptr(qkv), ptr(out), ptr(scratch), scratch.numel(), images, tokens, _lib.BF16, stream_ptr()))
     torch.cuda.synchronize()
     q, k, v = qkv.float().view(images, tokens, 3, 12, 32).permute(2, 0, 3, 1, 4)

@@ -24,10 +24,12 @@ using namespace umma;
 constexpr int HD = 32, BQ = 128, BKEY = 128, NST = 3, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
 constexpr int Q_BYTES = BQ * HD * 2;                 // 8 KB, 64-byte rows
 constexpr int K_BYTES = BKEY * HD * 2;               // 8 KB
-constexpr int V_BYTES = 2 * HD * 128;                // two 64-key chunks of [32 dims][128 B]
+constexpr int VR = 48;                               // rows of the staged V^T tile: 32 dims, a row of ones (row sums of P come out of the
+                                                     // same MMA, in float32 and from the bf16-rounded P), 15 rows of zeros (N % 16 == 0)
+constexpr int V_BYTES = 2 * VR * 128;                // two 64-key chunks of [48 rows][128 B]
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
 constexpr int P_BYTES = 2 * BQ * 128;                // two 64-key chunks of [128 rows][128 B]
-constexpr int X_BYTES = 6 * BQ * 4;                  // row maxima (2 parities x 2 halves) and row sums (2 halves) exchanged between partner warps
+constexpr int X_BYTES = 4 * BQ * 4;                  // row maxima (2 parities x 2 halves) exchanged between partner warps
 constexpr int SMEM_BYTES = 1024 + Q_BYTES + NST * KV_BYTES + P_BYTES + X_BYTES + 256;
 constexpr int TMEM_COLS = 256;
 
@@ -39,10 +41,10 @@ __device__ __forceinline__ float ex2(float x) {       // bare MUFU.EX2 (exp2f ad
 
 struct AttnMaps {
   CUtensorMap qkv;     // [images][tokens][3*dim], box {32, 128, 1}, SWIZZLE_64B
-  CUtensorMap vt;      // [images][heads*32][tokens], box {64, 32, 1}, SWIZZLE_128B
+  CUtensorMap vt;      // [images][heads*48][tokens], box {64, 48, 1}, SWIZZLE_128B
 };
 
-// V^T: vt[img][head*32 + d][token] = qkv[img][token][2*dim + head*32 + d]
+// V^T with the extra rows: vt[img][head*48 + d][token] = qkv[img][token][2*dim + head*32 + d] for d < 32, 1 for d == 32, 0 above
 __global__ void __launch_bounds__(256) v_transpose_kernel(const __nv_bfloat16* __restrict__ qkv, int tokens, int tok_pad, int dim,
                                                           __nv_bfloat16* __restrict__ vt) {
   __shared__ __nv_bfloat16 tile[64][HD + 2];
@@ -53,9 +55,10 @@ __global__ void __launch_bounds__(256) v_transpose_kernel(const __nv_bfloat16* _
     tile[t][d] = t0 + t < tokens ? qkv[((size_t)img * tokens + t0 + t) * 3 * dim + 2 * dim + head * HD + d] : __float2bfloat16(0.f);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * HD; i += 256) {
+  __nv_bfloat16* base = vt + ((size_t)img * heads + head) * VR * tok_pad;
+  for (int i = threadIdx.x; i < 64 * VR; i += 256) {
     const int d = i / 64, t = i % 64;
-    if (t0 + t < tok_pad) vt[((size_t)img * heads * HD + head * HD + d) * tok_pad + t0 + t] = tile[t][d];
+    if (t0 + t < tok_pad) base[(size_t)d * tok_pad + t0 + t] = d < HD ? tile[t][d] : __float2bfloat16(d == HD && t0 + t < tokens ? 1.f : 0.f);
   }
 }
 
@@ -101,8 +104,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
         mbar_expect_tx(bar_kv_full + 8 * s, KV_BYTES);
         const uint32_t dst = smem_u32(sKV + s * KV_BYTES);
         tma_load_3d(dst, &maps.qkv, bar_kv_full + 8 * s, dim + head * HD, j * BKEY, img);
-        tma_load_3d(dst + K_BYTES, &maps.vt, bar_kv_full + 8 * s, j * BKEY, head * HD, img);
-        tma_load_3d(dst + K_BYTES + HD * 128, &maps.vt, bar_kv_full + 8 * s, j * BKEY + 64, head * HD, img);
+        tma_load_3d(dst + K_BYTES, &maps.vt, bar_kv_full + 8 * s, j * BKEY, head * VR, img);
+        tma_load_3d(dst + K_BYTES + VR * 128, &maps.vt, bar_kv_full + 8 * s, j * BKEY + 64, head * VR, img);
       };
       auto issue_s = [&](int j) {
         const uint32_t s = j % NST;
@@ -131,8 +134,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
         const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES);
 #pragma unroll
         for (int k16 = 0; k16 < BKEY / 16; ++k16)
-          mma(tO, make_desc(p0 + (k16 >> 2) * (BQ * 128) + (k16 & 3) * 32, 1024, 2), make_desc(v0 + (k16 >> 2) * (HD * 128) + (k16 & 3) * 32, 1024, 2),
-              make_idesc(BQ, HD), k16 ? 1u : 0u);
+          mma(tO, make_desc(p0 + (k16 >> 2) * (BQ * 128) + (k16 & 3) * 32, 1024, 2), make_desc(v0 + (k16 >> 2) * (VR * 128) + (k16 & 3) * 32, 1024, 2),
+              make_idesc(BQ, VR), k16 ? 1u : 0u);
         commit(bar_kv_empty + 8 * s);
         commit(bar_o_full);
         if (j + NST < nk) {                          // refill this stage once P_j V_j has read it
@@ -152,9 +155,12 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, o[HD / 2];
 #pragma unroll
     for (int d = 0; d < HD / 2; ++d) o[d] = 0.f;
-    const uint32_t p_row = smem_u32(sP) + half * (BQ * 128) + row * 128;
-    float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima, then [2][128] row sums
     constexpr int HK = BKEY / 2;
+    const uint32_t p_row = smem_u32(sP) + half * (BQ * 128) + row * 128;
+    uint32_t p_addr[HK / 8];                        // the thread's eight 16-byte units of its P row, swizzled
+#pragma unroll
+    for (int u = 0; u < HK / 8; ++u) p_addr[u] = p_row + (((uint32_t)u ^ (row & 7)) << 4);
+    float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima
     for (int j = 0; j < nk; ++j) {
       const int valid = min(BKEY, tokens - j * BKEY) - half * HK;        // keys of this thread's half that exist (may be <= 0)
       mbar_wait(bar_s_full, j & 1);
@@ -187,13 +193,11 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       const float alpha = ex2(m_run - m_new);                            // 0 on the first tile
       // exponentials and row sum first (P_j packed in registers): they need neither O_{j-1} nor the P buffer, so they overlap
       // the P_{j-1} V_{j-1} MMA that is still running
-      float ls4[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[HK / 2];
 #pragma unroll
       for (int i = 0; i < HK / 2; ++i) {
         const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, -m_new));
         const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -m_new));
-        ls4[i & 3] += p0 + p1;
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&b2);
       }
@@ -201,19 +205,19 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       if (j > 0) {
         mbar_wait(bar_o_full, (j - 1) & 1);
         fence_after();
-        uint32_t v[16];
+        uint32_t v[16], w[16];
         tmem_ld16(tO + lane_base + half * 16, v);
+        tmem_ld16(tO + lane_base + HD, w);           // column 32: sum_k P_{j-1}[row][k]
         tmem_wait_ld();
 #pragma unroll
         for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+        l_run = l_run * alpha_prev + __uint_as_float(w[0]);
       }
       // P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
 #pragma unroll
       for (int u = 0; u < HK / 8; ++u) {
-        const uint32_t ad = p_row + (((uint32_t)u ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(p_addr[u]), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
       }
-      l_run = l_run * alpha + ((ls4[0] + ls4[1]) + (ls4[2] + ls4[3]));
       m_run = m_new;
       alpha_prev = alpha;
       fence_async_smem();                            // P_j visible to the tensor core (async proxy)
@@ -223,17 +227,14 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
     mbar_wait(bar_o_full, (nk - 1) & 1);
     fence_after();
     {
-      uint32_t v[16];
+      uint32_t v[16], w[16];
       tmem_ld16(tO + lane_base + half * 16, v);
+      tmem_ld16(tO + lane_base + HD, w);
       tmem_wait_ld();
 #pragma unroll
       for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
+      l_run = l_run * alpha_prev + __uint_as_float(w[0]);           // both threads of a row read the same (complete) row sum
     }
-    // row sum over both halves
-    float* lx = xch + 4 * BQ;
-    lx[half * BQ + row] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    l_run += lx[(half ^ 1) * BQ + row];
     if (q0 + row < tokens) {
       const float inv = 1.f / l_run;
       uint32_t pk[8];
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
 
 size_t ttk_attention_umma_scratch_bytes(int images, int tokens, int heads, int head_dim) {
   const size_t tok_pad = (size_t)(tokens + 7) / 8 * 8;
-  return (size_t)images * heads * head_dim * tok_pad * 2;
+  (void)head_dim;
+  return (size_t)images * heads * VR * tok_pad * 2;
 }
 
 int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_scratch, int images, int tokens, int heads, int head_dim,
@@ -292,9 +294,9 @@ int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_sc
     }
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)dim, (cuuint64_t)images};
-    cuuint64_t strides[2] = {(cuuint64_t)tok_pad * 2, (cuuint64_t)dim * tok_pad * 2};
-    cuuint32_t box[3] = {64, HD, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)tokens, (cuuint64_t)heads * VR, (cuuint64_t)images};
+    cuuint64_t strides[2] = {(cuuint64_t)tok_pad * 2, (cuuint64_t)heads * VR * tok_pad * 2};
+    cuuint32_t box[3] = {64, VR, 1};
     if (enc(&maps.vt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
       ttk_set_error("ttk_attention_umma: tensor map (v^T) failed");

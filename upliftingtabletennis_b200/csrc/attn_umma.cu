@@ -7,9 +7,10 @@
 //   P_j = exp2(S*c - m)     thread r owns query row r: the 128 scores of its TMEM row are pulled into registers at once (S is then
 //                           free, so the next Q K^T overlaps the exponentials), running maximum / sum in registers, P_j written as
 //                           a bf16 K-major A operand (128-byte swizzle) in shared memory
-//   O_j = P_j V_j           tcgen05.mma 128 x 32 x 128; V is staged TRANSPOSED ([dim][key], from a small transpose kernel) so that it
-//                           is an ordinary K-major B operand; O_j lands in TMEM (32 columns) and is folded into the thread's
-//                           float32 accumulator with the usual exp2(m_old - m_new) correction.
+//   O  += P_j V_j           tcgen05.mma 128 x 48 x 128; V is staged TRANSPOSED ([dim][key], from a small transpose kernel) so that it
+//                           is an ordinary K-major B operand, with a row of ones appended so that the row sums of P come out of the
+//                           same MMA; O and the row sums accumulate in TMEM (48 columns) over all key tiles and are rescaled in
+//                           place only when a row maximum grew by more than 2^8 (lazy rescaling).
 // Warps 0-7 are the softmax / correction warps (TMEM lane quarter = warp % 4, two threads per query row: 64 keys and 16 output
 // dimensions each), warp 8 issues TMA and MMA.  The kernel needs 160 TMEM columns (256 allocated) and ~93 KB of shared memory, so
 // two CTAs share an SM and one CTA's exponentials overlap the other's MMAs.
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
 #pragma unroll
         for (int k16 = 0; k16 < BKEY / 16; ++k16)
           mma(tO, make_desc(p0 + (k16 >> 2) * (BQ * 128) + (k16 & 3) * 32, 1024, 2), make_desc(v0 + (k16 >> 2) * (VR * 128) + (k16 & 3) * 32, 1024, 2),
-              make_idesc(BQ, VR), k16 ? 1u : 0u);
+              make_idesc(BQ, VR), (j | k16) ? 1u : 0u);       // O (and the row sums) accumulate in TMEM over all key tiles
         commit(bar_kv_empty + 8 * s);
         commit(bar_o_full);
         if (j + NST < nk) {                          // refill this stage once P_j V_j has read it
@@ -152,9 +153,7 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
     const int row = q * 32 + lane;                  // query row of this thread = TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float sl2 = 0.17677669529663687f * 1.4426950408889634f;      // 32^-0.5 * log2(e)
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, o[HD / 2];
-#pragma unroll
-    for (int d = 0; d < HD / 2; ++d) o[d] = 0.f;
+    float m_run = -INFINITY;                        // the maximum the exponentials are scaled with (may lag the true one, see below)
     constexpr int HK = BKEY / 2;
     const uint32_t p_row = smem_u32(sP) + half * (BQ * 128) + row * 128;
     uint32_t p_addr[HK / 8];                        // the thread's eight 16-byte units of its P row, swizzled
@@ -189,58 +188,68 @@ __global__ void __launch_bounds__(THREADS, 2) attention_umma_kernel(const __grid
       xch[((j & 1) * 2 + half) * BQ + row] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BQ + row]);
-      const float m_new = fmaxf(m_run, mx * sl2);
-      const float alpha = ex2(m_run - m_new);                            // 0 on the first tile
-      // exponentials and row sum first (P_j packed in registers): they need neither O_{j-1} nor the P buffer, so they overlap
-      // the P_{j-1} V_{j-1} MMA that is still running
+      const float m_true = fmaxf(m_run, mx * sl2);
+      // Lazy rescaling: O and the row sums stay in TMEM and are multiplied by 2^(m_run - m_true) only when the maximum grew by more
+      // than 8 (log2 units); otherwise P is scaled with the lagging maximum (entries up to 2^8, exact in float32 / bf16 terms since
+      // numerator and denominator carry the same factor).  The decision is per row; the TMEM round trip is warp-collective, so a
+      // warp takes it when any of its rows needs it (both partner warps see the same rows and decide alike).
+      const bool grow = j > 0 && m_true - m_run > 8.0f;
+      if (j == 0) m_run = m_true;
+      if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(bar_o_full, (j - 1) & 1);          // P_{j-1} V_{j-1} has landed
+        fence_after();
+        const float alpha = grow ? ex2(m_run - m_true) : 1.f;
+        uint32_t v[16];
+        tmem_ld16(tO + lane_base + half * 16, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+        tmem_st16(tO + lane_base + half * 16, v);
+        if (half == 0) {                             // the row-sum column block (32..47) belongs to the first partner
+          tmem_ld16(tO + lane_base + HD, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) v[d] = __float_as_uint(__uint_as_float(v[d]) * alpha);
+          tmem_st16(tO + lane_base + HD, v);
+        }
+        tmem_wait_st();
+        if (grow) m_run = m_true;
+      }
+      // exponentials (P_j packed in registers): they need neither O nor the P buffer, so they overlap the P_{j-1} V_{j-1} MMA
       uint32_t pk[HK / 2];
 #pragma unroll
       for (int i = 0; i < HK / 2; ++i) {
-        const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, -m_new));
-        const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -m_new));
+        const float p0 = ex2(fmaf(__uint_as_float(sv[2 * i]), sl2, -m_run));
+        const float p1 = ex2(fmaf(__uint_as_float(sv[2 * i + 1]), sl2, -m_run));
         __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
         pk[i] = *reinterpret_cast<uint32_t*>(&b2);
       }
-      // O_{j-1} is complete: fold it in, and P_{j-1} may be overwritten
+      // P_{j-1} has been consumed by its MMA: P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
       if (j > 0) {
         mbar_wait(bar_o_full, (j - 1) & 1);
         fence_after();
-        uint32_t v[16], w[16];
-        tmem_ld16(tO + lane_base + half * 16, v);
-        tmem_ld16(tO + lane_base + HD, w);           // column 32: sum_k P_{j-1}[row][k]
-        tmem_wait_ld();
-#pragma unroll
-        for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
-        l_run = l_run * alpha_prev + __uint_as_float(w[0]);
       }
-      // P_j -> shared memory (bf16, 128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
 #pragma unroll
       for (int u = 0; u < HK / 8; ++u) {
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(p_addr[u]), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
       }
-      m_run = m_new;
-      alpha_prev = alpha;
+      fence_before();                                // TMEM writes of a rescale are ordered before the MMA that follows the arrive
       fence_async_smem();                            // P_j visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
     }
     mbar_wait(bar_o_full, (nk - 1) & 1);
     fence_after();
-    {
-      uint32_t v[16], w[16];
-      tmem_ld16(tO + lane_base + half * 16, v);
-      tmem_ld16(tO + lane_base + HD, w);
-      tmem_wait_ld();
-#pragma unroll
-      for (int d = 0; d < HD / 2; ++d) o[d] = o[d] * alpha_prev + __uint_as_float(v[d]);
-      l_run = l_run * alpha_prev + __uint_as_float(w[0]);           // both threads of a row read the same (complete) row sum
-    }
+    uint32_t v[16], w[16];
+    tmem_ld16(tO + lane_base + half * 16, v);
+    tmem_ld16(tO + lane_base + HD, w);               // column 32: sum_k P[row][k] (both threads of a row read it)
+    tmem_wait_ld();
     if (q0 + row < tokens) {
-      const float inv = 1.f / l_run;
+      const float inv = 1.f / __uint_as_float(w[0]);
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(o[2 * i] * inv, o[2 * i + 1] * inv);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv);
         pk[i] = *reinterpret_cast<uint32_t*>(&b2);
       }
       uint4* op = reinterpret_cast<uint4*>(out + ((size_t)img * tokens + q0 + row) * dim + head * HD + half * 16);

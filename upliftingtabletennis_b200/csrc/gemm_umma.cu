@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     const int et = tid - 64;                        // 0..255 among the epilogue threads
     // kernel parameters in registers (the asm memory clobbers below would otherwise re-read them from the constant bank)
     const uint32_t sbias_u32 = smem_u32(sBias);
-    const int gM = g.M, gN = g.N, dbg = g.act >> 8, up_w = g.up_w, up_h = g.up_h, upy = g.py, upx = g.px;
+    const int gM = g.M, gN = g.N, dbg = g.act >> 8, r_mod = g.r_mod, up_w = g.up_w, up_h = g.up_h, upy = g.py, upx = g.px;
     const bool c_bf16 = g.c_bf16 != 0;
     const float* __restrict__ gR = g.R;
     const float* __restrict__ gBias = g.bias;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
           asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bz[4 * j]), "=f"(bz[4 * j + 1]), "=f"(bz[4 * j + 2]), "=f"(bz[4 * j + 3]) : "r"(sbias_u32 + c0 * 4 + 16 * j));
         float r[32];
         if (gR && live) {
-          const float4* rp = reinterpret_cast<const float4*>(gR + (size_t)m * gN + n);
+          const float4* rp = reinterpret_cast<const float4*>(gR + (size_t)(r_mod ? m % r_mod : m) * gN + n);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 t = rp[j];

@@ -22,20 +22,32 @@ constexpr int DIM = 384, DEPTH = 12, HEADS = 12, HD = 32, MLP = 1536, PATCH = 16
 // ---- im2col of the patch embedding: A[t][c*256 + ky*16 + kx] = x[b][c][ty*16 - 2 + ky][tx*16 - 2 + kx] ----------------
 template <typename T>
 __global__ void patch_im2col_kernel(const float* __restrict__ x, int images, int C, int H, int W, int hp, int wp, T* __restrict__ A) {
-  const long long total = (long long)images * hp * wp * C * PATCH;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ky = (int)(i % PATCH);
-    const int c = (int)((i / PATCH) % C);
-    const long long t = i / ((long long)PATCH * C);
+  // one warp per (token, channel): lane = (ky, half row) reads 8 consecutive pixels and writes 8 consecutive elements, so a warp
+  // reads 16 segments of 64 bytes and writes one contiguous run of 256 elements
+  const int lane = threadIdx.x & 31, ky = lane >> 1, hx = (lane & 1) * 8;
+  const long long total = (long long)images * hp * wp * C;
+  for (long long i = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); i < total; i += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
     const int tx = (int)(t % wp), ty = (int)((t / wp) % hp), b = (int)(t / ((long long)wp * hp));
-    const int y = ty * PATCH - PAD + ky;
-    T* o = A + (size_t)t * (C * PATCH * PATCH) + (size_t)c * PATCH * PATCH + ky * PATCH;
-    const float* row = x + (((size_t)b * C + c) * H + (y < 0 || y >= H ? 0 : y)) * W;
+    const int y = ty * PATCH - PAD + ky, x0 = tx * PATCH - PAD + hx;
+    float v[8];
+    const bool row_ok = y >= 0 && y < H;
+    const float* row = x + (((size_t)b * C + c) * H + (row_ok ? y : 0)) * W;
 #pragma unroll
-    for (int kx = 0; kx < PATCH; ++kx) {
-      const int xx = tx * PATCH - PAD + kx;
-      const float v = (y >= 0 && y < H && xx >= 0 && xx < W) ? row[xx] : 0.f;
-      o[kx] = (T)v;
+    for (int k = 0; k < 8; ++k) v[k] = (row_ok && x0 + k >= 0 && x0 + k < W) ? __ldg(row + x0 + k) : 0.f;
+    T* o = A + (size_t)t * (C * PATCH * PATCH) + (size_t)c * PATCH * PATCH + ky * PATCH + hx;
+    if constexpr (sizeof(T) == 4) {
+      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint32_t pk[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        pk[k] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmArgs g) {
       if (g.act == VIT_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
     }
     if (g.R) {
-      const float4 r = *reinterpret_cast<const float4*>(g.R + (size_t)m * g.N + n);
+      const float4 r = *reinterpret_cast<const float4*>(g.R + (size_t)(g.r_mod ? m % g.r_mod : m) * g.N + n);
       v[0] += r.x, v[1] += r.y, v[2] += r.z, v[3] += r.w;
     }
     *reinterpret_cast<float4*>((float*)g.C + out_row(g, m) * g.N + n) = make_float4(v[0], v[1], v[2], v[3]);
@@ -549,17 +561,18 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
         layernorm_kernel<float><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(wo), fptr(bo), T, (float*)w.A);
     };
     int rc;
-    // patch embedding (+ bias + position): the position table repeats per image, so it enters as the residual of one GEMM per image
+    // patch embedding (+ bias + position): the position table repeats per image and enters as a residual read modulo the token count
     ++h->launches;
     if (bf)
       patch_im2col_kernel<__nv_bfloat16><<<ttk_num_sms() * 8, 256, 0, st>>>(x, n, h->in_ch, h->height, h->width, h->hp, h->wp, (__nv_bfloat16*)w.A);
     else
       patch_im2col_kernel<float><<<ttk_num_sms() * 8, 256, 0, st>>>(x, n, h->in_ch, h->height, h->width, h->hp, h->wp, (float*)w.A);
     TTK_LAUNCH_CHECK();
-    for (int i = 0; i < n; ++i) {
-      rc = gemm(w.A + (size_t)i * h->tokens * h->patch.k * es, h->patch, fptr(h->pos_off), w.X + (size_t)i * h->tokens * DIM, h->tokens,
-                VIT_ACT_NONE, 0);
-      if (rc != TTK_OK) return rc;
+    {
+      GemmArgs g;
+      g.A = w.A, g.W = wptr(h->patch.w_off), g.bias = fptr(h->patch.b_off), g.R = fptr(h->pos_off), g.r_mod = h->tokens, g.C = w.X;
+      g.M = T, g.N = h->patch.n, g.K = h->patch.k, g.act = VIT_ACT_NONE, g.c_bf16 = 0, g.up_h = g.up_w = g.py = g.px = 0;
+      if ((rc = launch_gemm(h, g, dtype, st)) != TTK_OK) return rc;
     }
     for (int i = 0; i < DEPTH; ++i) {
       const ttk_vit::Block& B = h->blocks[i];

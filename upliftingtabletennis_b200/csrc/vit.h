@@ -15,6 +15,7 @@ struct GemmArgs {
   const void* W;          // [N][K]
   const float* bias;      // [N] or null
   const float* R;         // [M][N] float32 residual or null (may alias C when C is float32)
+  int r_mod = 0;          // > 0: the residual has r_mod rows and row m reads row m % r_mod (position table repeated per image)
   void* C;                // [M][N] f32 or bf16
   int M, N, K;
   int act;
@@ -35,7 +36,7 @@ struct ttk_vit {
   std::vector<VitParam> params;
   bool ready = false;
   int launches = 0;
-  int subbatch = 8;
+  int subbatch = 16;
   // prepared device weights (float32 and bf16 copies of every GEMM operand)
   float* f32_pool = nullptr;
   __nv_bfloat16* bf16_pool = nullptr;

@@ -37,6 +37,8 @@ VIT_RES = (1152, 640)      # ViTPose input resolution (balldetection/config.py:8
 VIT_GFLOP_PER_STACK = 313.5
 VIT_BATCH = 16
 CALIB_CLIPS = 64
+CLIP_FRAMES = 300          # BASELINE.json configs[2]: full hub pipeline on a synthetic 300-frame clip
+RALLY_FRAMES = 50          # ... processed as rallies of 50 frames (see the pipeline leg)
 WORKLOAD = 'configs[1]: WASB ball-detect (1280x704 input, 344 GFLOP/stack) + heatmap decode on synthetic 1920x1080 3-frame stacks, batch %d per GPU' % BATCH
 
 
@@ -107,6 +109,11 @@ def make_checkpoints(hub_dir):
         d = os.path.join(w, sub)
         os.makedirs(d, exist_ok=True)
         torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(d, 'model.pt'))
+    table_sd = synthetic.hrnet_state_dict(HRNetEngine(3, 13, 0, 13).state_dict_layout(), seed=2)
+    d = os.path.join(w, 'inference_tabledetection', 'hrnet')
+    os.makedirs(d, exist_ok=True)
+    torch.save({'model_state_dict': table_sd, 'identifier': 'synthetic', 'additional_info': {'model_name': 'hrnet', 'image_resolution': RES}},
+               os.path.join(d, 'model.pt'))
     from upliftingtabletennis_b200 import vitpose
     vit_sd = synthetic.vit_state_dict(vitpose.state_dict_layout(9, 2880, 1), seed=5)
     d = os.path.join(w, 'inference_balldetection', 'vitpose')
@@ -304,6 +311,27 @@ def main():
         h32 = vit.model.engine.forward(vit_x, torch.float32).clone()
         h16 = vit.model.engine.forward(vit_x, torch.bfloat16)
         vit_rel = float(((h16 - h32).norm() / h32.norm()).item())
+    # ---- the full hub pipeline on a 300-frame 1080p clip (configs[2]): main + auxiliary WASB and HRNet passes, both agreement
+    # filters, uplift.  The reference's uplifting model (and this drop-in) raise ValueError on 50 or more detections
+    # (uplifting/model.py:541-546, SURVEY.md finding 6), and random-init detectors agree on every frame, so the clip is processed as
+    # six rallies of 50 frames (48 detections each): six calls of the public API, end to end from pinned host frames ----
+    from upliftingtabletennis_b200.interface import BallDetector, TableDetector
+    pipe = hubconf.full_pipeline()
+    pipe.ball_detector_aux, pipe.table_detector_aux = BallDetector('wasb'), TableDetector('hrnet')
+    for m in (pipe.ball_detector, pipe.ball_detector_aux, pipe.table_detector, pipe.table_detector_aux):
+        m.model.compute_dtype = cdt
+    pipe.uplifting_model.model.compute_dtype = cdt
+    clip = torch.from_numpy(synthetic.frames_1080p(CLIP_FRAMES, seed=200 + rank)).pin_memory()
+    rallies = [[clip[i] for i in range(r0, r0 + RALLY_FRAMES)] for r0 in range(0, CLIP_FRAMES, RALLY_FRAMES)]
+
+    def pipe_step():
+        return [pipe.predict(r, 50.0) for r in rallies]
+    pipe_steps = 2
+    pipe_ms = timed(pipe_step, pipe_steps, 1)
+    res = pipe_step()
+    pipe_ok = all(bool(torch.isfinite(sp).all().item()) and bool(np.isfinite(p3).all()) for sp, p3 in res)
+    pipe_detections = [int(p3.shape[0]) for _, p3 in res]
+    del rallies, clip
     kps = synthetic.table_keypoints(CALIB_CLIPS, seed=11 + rank)
     kps_d = torch.from_numpy(kps).to(dev)
     smp_d = torch.from_numpy(ops.ransac_sample_table(kps)).to(dev)
@@ -425,6 +453,12 @@ def main():
                        'tensor_frac': VIT_GFLOP_PER_STACK * vit_res['bf16'][0] / 1e3 / world / pk['bf16_tflops_sustained'],
                        'gpu_launches': vit_res['bf16'][2], 'bf16_vs_f32_rel_l2': vit_rel,
                        'f32': {'value': vit_res['f32'][0], 'ms_per_step': vit_res['f32'][1]}}
+    line['pipeline'] = {'value': world * CLIP_FRAMES * pipe_steps / (pipe_ms * 1e-3), 'unit': 'frames/s', 'clips_per_sec': world * pipe_steps / (pipe_ms * 1e-3),
+                        'ms_per_clip': pipe_ms / pipe_steps, 'frames_per_clip': CLIP_FRAMES, 'dtype': args.dtype, 'finite_outputs': pipe_ok, 'trajectory_lengths': pipe_detections,
+                        'workload': 'configs[2]: hubconf.full_pipeline().predict(...) on a 300-frame pinned host 1080p clip, as 6 rallies of 50 frames '
+                                    '(the uplifting model takes < 50 detections): WASB main + aux on 288 stacks, HRNet main + aux on 300 frames, '
+                                    '8376 heatmap decodes, both agreement filters, uplift; end to end',
+                        'h2d_bytes_per_clip': CLIP_FRAMES * SRC[0] * SRC[1] * 3}
     line['calibration'] = {'value': world * CALIB_CLIPS * args.steps / (calib_ms * 1e-3), 'unit': 'clips/s', 'clips_per_gpu': CALIB_CLIPS,
                            'ms_per_step': calib_ms / args.steps, 'gpu_launches': 3,
                            'workload': 'calibrate_camera: DLT + 100 RANSAC hypotheses of SciPy-BFGS fits + refit per clip (13 keypoints, 1 outlier, 1 hidden)',

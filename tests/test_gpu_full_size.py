@@ -101,3 +101,49 @@ def test_uplift_50k_trajectories_properties(dev):
     # the local-axis rotation is norm preserving in the x-y plane
     loc = ops.rotation_local(r32, p32)
     np.testing.assert_allclose(loc.norm(dim=1).cpu().numpy(), r32.norm(dim=1).cpu().numpy(), rtol=1e-4)
+
+
+def test_full_pipeline_1080p_rally(dev, tmp_path):
+    """BASELINE.json configs[2] at full frame size, one 50-frame rally (48 detections: the reference's uplifting model and this drop-in
+    raise ValueError on 50 or more, SURVEY.md finding 6): the hub pipeline with separate main and auxiliary detector objects runs end to
+    end on the device and agrees with the same stages called one by one through the public API."""
+    import os
+    from upliftingtabletennis_b200 import synthetic
+    from upliftingtabletennis_b200.detector import HRNetEngine
+    from upliftingtabletennis_b200.interface import BallDetector, TableDetector, TableTennisPipeline, _uplifting_transform
+    from upliftingtabletennis_b200.uplift import get_model
+    hub = str(tmp_path)
+    torch.hub.set_dir(hub)
+    w = os.path.join(hub, 'checkpoints', 'tt_uplifting_extracted', 'weights')
+    up = get_model('connectstage', 'large', 'dynamic', 'new')
+    for sub, sd, info in (
+            ('inference_balldetection/wasb', synthetic.hrnet_state_dict(HRNetEngine(9, 3, 1, 1).state_dict_layout(), seed=1),
+             {'model_name': 'wasb', 'image_resolution': (1280, 704), 'in_frames': 3, 'lr': 0.0}),
+            ('inference_tabledetection/hrnet', synthetic.hrnet_state_dict(HRNetEngine(3, 13, 0, 13).state_dict_layout(), seed=2),
+             {'model_name': 'hrnet', 'image_resolution': (1280, 704)}),
+            ('inference_uplifting/ours', synthetic.uplift_state_dict(up, seed=3),
+             {'name': 'connectstage', 'size': 'large', 'tabletoken_mode': 'dynamic', 'time_rotation': 'new', 'transform_mode': 'global',
+              'randdet_prob': 0.0, 'randmiss_prob': 0.0, 'tablemiss_prob': 0.0})):
+        os.makedirs(os.path.join(w, sub), exist_ok=True)
+        torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(w, sub, 'model.pt'))
+    pipe = TableTennisPipeline()
+    pipe.ball_detector_aux, pipe.table_detector_aux = BallDetector('wasb'), TableDetector('hrnet')
+    frames = list(synthetic.frames_1080p(50, seed=9))
+    spin, pos3d = pipe.predict(frames, 50.0)
+    assert spin.shape == (3,) and pos3d.shape == (48, 3)
+    assert torch.isfinite(spin).all() and np.isfinite(pos3d).all()
+    # stage by stage through the public API (host round trips between the stages, like the reference's interface.py:263-289)
+    triples = [(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, len(frames) - 1)]
+    bpos, _ = pipe.ball_detector.predict(triples, return_heatmaps=False)
+    bpos_aux, _ = pipe.ball_detector_aux.predict(triples, return_heatmaps=False)
+    assert np.array_equal(bpos, bpos_aux)
+    fpos, fidx, ftimes = pipe.ball_detector.filter_trajectory(bpos, bpos_aux, 50.0)
+    tpos, _ = pipe.table_detector.predict(frames, return_heatmaps=False)
+    ftab = pipe.table_detector_aux.filter_trajectory(tpos, tpos)
+    b, t, ti, m = _uplifting_transform(fpos, ftab, ftimes)
+    spin2, pos2 = pipe.uplifting_model.predict_without_normalization(b, t, m, ti)
+    np.testing.assert_allclose(pos3d, pos2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(spin.cpu().numpy(), spin2.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # 52 frames = 50 agreeing detections: the all-ones mask is rejected like in the reference
+    with pytest.raises(ValueError):
+        pipe.predict(list(synthetic.frames_1080p(52, seed=9)), 50.0)

@@ -379,18 +379,25 @@ class TableTennisPipeline:
     def predict(self, images, fps):
         """interface.py:263-289.  Detections, both filters, the normalise/pad step and the transformer stay on the
         device: the only host visit is the final result (and T' for slicing it, as in the reference)."""
-        image_triples = [(images[i - 1], images[i], images[i + 1]) for i in range(1, len(images) - 1)]
-        ball_positions, _ = self.ball_detector.predict_device(image_triples)
-        if self.ball_detector_aux is self.ball_detector:
-            ball_positions_aux = ball_positions
-        else:
-            ball_positions_aux, _ = self.ball_detector_aux.predict_device(image_triples)
-        ball_xy, _, times_ball, offsets = ops.filter_ball(ball_positions, ball_positions_aux, float(fps))
-        table_keypoints, _ = self.table_detector.predict_device(images)
-        if self.table_detector_aux is self.table_detector:
-            table_keypoints_aux = table_keypoints
-        else:
-            table_keypoints_aux, _ = self.table_detector_aux.predict_device(images)
+        n = len(images)
+        # every frame crosses PCIe once: the four detector passes (ball / table, main / auxiliary) share the uploaded clip, and the
+        # first pass starts while later frames are still arriving
+        frames, order, ready = self.ball_detector._upload(list(images), self.device)
+        if order != list(range(n)):
+            torch.cuda.current_stream().wait_event(ready[-1][1])
+            frames, ready = frames[torch.tensor(order, device=self.device)], None
+        with torch.no_grad():
+            ball_positions = self.ball_detector._run(frames, 1, n - 2, False, ready)[0][:, 0]       # sliding (prev, cur, next) window
+            if self.ball_detector_aux is self.ball_detector:
+                ball_positions_aux = ball_positions
+            else:
+                ball_positions_aux = self.ball_detector_aux._run(frames, 1, n - 2, False, None)[0][:, 0]
+            ball_xy, _, times_ball, offsets = ops.filter_ball(ball_positions, ball_positions_aux, float(fps))
+            table_keypoints = self.table_detector._run(frames, 1, n, False, None)[0]
+            if self.table_detector_aux is self.table_detector:
+                table_keypoints_aux = table_keypoints
+            else:
+                table_keypoints_aux = self.table_detector_aux._run(frames, 1, n, False, None)[0]
         filtered_table_keypoints = ops.filter_table(table_keypoints, table_keypoints_aux)
         ball_coords, table_coords, times, mask = ops.trajectory_pack(ball_xy, times_ball, offsets, filtered_table_keypoints[None],
                                                                     SEQ_LEN, WIDTH, HEIGHT)

@@ -96,6 +96,10 @@ TTK_API int ttk_hrnet_set_force_simt(ttk_hrnet* h, int enable);   /* bf16 path t
  * path 0: fp32 SIMT (float32 tensors), 1: bf16 SIMT, 2: bf16 tcgen05 (TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel). */
 TTK_API int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, const void* res_dev,
                          int relu, int path, void* out_dev, void* stream);
+/* Test hook: one BasicBlock (convs conv_index and conv_index + 1, 16 or 32 padded channels) through the fused tcgen05 kernel:
+ * out = relu(conv2(relu(conv1(in))) + in), NHWC bf16.  ttk_hrnet_set_block_fusion(0) runs the blocks conv by conv (A/B, cross-check). */
+TTK_API int ttk_hrnet_debug_block(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, void* out_dev, void* stream);
+TTK_API int ttk_hrnet_set_block_fusion(ttk_hrnet* h, int enable);
 TTK_API int ttk_hrnet_set_profile(ttk_hrnet* h, int enable);
 TTK_API int ttk_hrnet_profile_count(const ttk_hrnet* h);
 TTK_API int ttk_hrnet_profile_read(ttk_hrnet* h, int i, int* op_type, int* conv_index, float* ms, double* flops, double* bytes);

@@ -92,3 +92,59 @@ def test_network_umma_vs_simt(net):
     r_simt = np.linalg.norm(y_simt.cpu().numpy() - ref) / np.linalg.norm(ref)
     assert r_tc < 3e-2 and r_simt < 3e-2, (r_tc, r_simt)
     assert np.linalg.norm((y_tc - y_simt).cpu().numpy()) / np.linalg.norm(ref) < 3e-2
+
+
+@pytest.mark.parametrize('shape', [(2, 24, 200), (1, 10, 130), (1, 7, 126), (1, 40, 72), (3, 16, 520), (1, 5, 127)])
+def test_fused_basic_block_vs_separate_convs_and_cpu(net, shape):
+    """block_umma.cu: relu(conv2(relu(conv1(x))) + x) in one kernel against the two tcgen05 convolutions run one after the other
+    (same bf16 operands; the only difference is where the intermediate is rounded: identically, to bf16) and a CPU fp32 reference."""
+    from upliftingtabletennis_b200._lib import lib, ptr, stream_ptr
+    m, sd = net
+    eng = m.engine
+    n, H, W = shape
+    rng = np.random.default_rng(H * W + n)
+    blocks = [i for i, s in enumerate(eng.specs[:-1]) if s[0].endswith('.conv1') and 'branches' in s[0] and s[2] in (16, 32)]
+    assert len(blocks) == 12
+    for idx in blocks:
+        name, _, cin, cout, k, stride = eng.specs[idx]
+        assert eng.specs[idx + 1][0] == name.replace('conv1', 'conv2')
+        x = torch.from_numpy(rng.standard_normal((n, H, W, cin)).astype(np.float32)).to(torch.bfloat16).cuda()
+        y = torch.full((n, H, W, cin), float('nan'), dtype=torch.bfloat16, device='cuda')
+        rc = lib.ttk_hrnet_debug_block(eng.h, idx, ptr(x), n, H, W, ptr(y), stream_ptr())
+        torch.cuda.synchronize()
+        assert rc == 0, name
+        rc1, t = _run(eng, idx, x, None, True, 2, (n, H, W, cin), torch.bfloat16)
+        rc2, y_sep = _run(eng, idx + 1, t, x, True, 2, (n, H, W, cin), torch.bfloat16)
+        assert rc1 == 0 and rc2 == 0
+        yf, ys = y.float().cpu(), y_sep.float().cpu()
+        assert torch.isfinite(yf).all(), name
+        scale = float(ys.abs().max()) + 1e-6
+        assert float((yf - ys).abs().max()) <= 8e-3 * scale, (name, shape, float((yf - ys).abs().max()), scale)
+        specs = ohr.conv_specs(9, 3)
+        (w1, b1), (w2, b2) = ohr.fold_bn(sd, specs[idx]), ohr.fold_bn(sd, specs[idx + 1])
+        q = lambda w: torch.from_numpy(w.astype(np.float32)).to(torch.bfloat16).float()
+        xin = x.float().cpu().permute(0, 3, 1, 2)
+        tt = torch.relu(F.conv2d(xin, q(w1), torch.from_numpy(b1.astype(np.float32)), padding=1)).to(torch.bfloat16).float()
+        ref = torch.relu(F.conv2d(tt, q(w2), torch.from_numpy(b2.astype(np.float32)), padding=1) + xin).permute(0, 2, 3, 1)
+        assert float((ref - yf).abs().max()) <= 1.6e-2 * (float(ref.abs().max()) + 1e-6), (name, shape)
+
+
+def test_network_block_fusion_on_off(net):
+    from upliftingtabletennis_b200._lib import lib
+    m, sd = net
+    x = torch.from_numpy(np.random.default_rng(2).standard_normal((2, 9, 64, 160)).astype(np.float32)).cuda()
+    m.compute_dtype = torch.bfloat16
+    try:
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)
+        y_on, _ = m(x)
+        n_on = m.engine.last_launches()
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 0)
+        y_off, _ = m(x)
+        n_off = m.engine.last_launches()
+    finally:
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)
+        m.compute_dtype = torch.float32
+    assert n_off - n_on == 12           # twelve BasicBlocks of the 16- and 32-channel branches run as one launch each
+    ref = ohr.wasb_forward(sd, x.cpu()).numpy()
+    assert np.linalg.norm(y_on.cpu().numpy() - ref) / np.linalg.norm(ref) < 3e-2
+    assert np.linalg.norm((y_on - y_off).cpu().numpy()) / np.linalg.norm(ref) < 2e-2

@@ -40,6 +40,8 @@ def _load():
         'ttk_hrnet_set_profile': (i32, [vp, i32]),
         'ttk_hrnet_set_force_simt': (i32, [vp, i32]),
         'ttk_hrnet_debug_conv': (i32, [vp, i32, vp, i32, i32, i32, vp, i32, i32, vp, vp]),
+        'ttk_hrnet_debug_block': (i32, [vp, i32, vp, i32, i32, i32, vp, vp]),
+        'ttk_hrnet_set_block_fusion': (i32, [vp, i32]),
         'ttk_hrnet_profile_count': (i32, [vp]),
         'ttk_hrnet_profile_read': (i32, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         'ttk_vit_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),

@@ -1,0 +1,310 @@
+// Fused BasicBlock of the HRNet branches on tcgen05 (bf16, 16- and 32-channel branches):
+//   y = relu(conv2(relu(conv1(x) + b1)) + b2 + x)              balldetection/models/wasb.py:35-64 (BasicBlock.forward, BN folded)
+// The two 3x3 convolutions of a block run in ONE kernel: the intermediate tensor never leaves the SM and the residual is taken
+// from the staged input tile, so a block reads x once and writes y once (conv by conv it is read x, write t, read t, read x,
+// write y: 5 tensor passes instead of 2 -- the branch layers are HBM bound).
+//
+// Tile = R output rows x 126 output pixels.  One TMA box brings the (R+4) x 130 pixel input halo (zero fill outside the image).
+//   M1: conv1 on tensor cores for the (R+2) x 128 intermediate pixels the tile needs (vertical tap fusion as in conv_umma.cu:
+//       one MMA per input row and horizontal tap against [W(ky=0) | W(ky=1) | W(ky=2)], accumulators in reverse row order)
+//   E1: accumulators -> + b1, ReLU, zero outside the image (conv2 pads the intermediate TENSOR with zeros) -> bf16 -> shared
+//       memory in the same swizzled pixel-row layout TMA produces, so conv2 addresses it with the same descriptors
+//   M2: conv2 from that tile,  E2: + b2 + x (from the staged input tile) -> ReLU -> global.
+// Roles (persistent CTA): warp 0 TMA producer (2-slot input ring), warp 1 MMA issuer, warps 2-5 epilogues.  The MMA warp issues
+// M1 of the next tile right behind M2, so it overlaps E2; the accumulators are zeroed by the epilogue that drains them.
+#include <algorithm>
+
+#include "hrnet.h"
+#include "umma_prims.h"
+
+namespace {
+
+using namespace umma;
+
+constexpr int BW = 128, WO = 126, TW = 130, THREADS = 192;
+constexpr int al1024(int b) { return (b + 1023) & ~1023; }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+
+template <int C, int R>
+struct BCfg {
+  static constexpr int ROWB = 2 * C;                   // bytes per pixel row of a tile (32 or 64)
+  static constexpr int R1 = R + 2, RX = R + 4;         // intermediate rows, input rows
+  static constexpr int X_BYTES = RX * TW * ROWB, X_AL = al1024(X_BYTES);
+  static constexpr int T_BYTES = R1 * TW * ROWB, T_AL = al1024(T_BYTES);
+  static constexpr int W_BYTES = 9 * C * ROWB, W_AL = al1024(W_BYTES);
+  static constexpr int ACC1 = R1 * C, ACC2 = R * C;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + 2 * W_AL + 2 * X_AL + T_AL + 2 * C * 4 + 256;
+  static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : 4u;     // SWIZZLE_32B / 64B
+  static constexpr uint32_t SWZ = ROWB == 32 ? 1u : 3u;
+  static_assert(C == 16 || C == 32, "channel counts of the fused block");
+  static_assert(ACC1 + ACC2 <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+struct BlockArgs {
+  const __nv_bfloat16 *w1, *w2;      // packed like ttk_conv_umma_pack (fused 3x3: [kx][ky][cout][cin])
+  const float *b1, *b2;
+  __nv_bfloat16* out;
+  int n, h, w;
+  int tiles_x, tiles_y, total;
+};
+
+// RR output rows from RR + 2 staged rows at `abase`, weights at `wbase`, accumulators at `d_acc` (row yo in column block RR-1-yo)
+template <int C, int RR, uint32_t LAYOUT>
+__device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint32_t d_acc) {
+  constexpr int ROWB = 2 * C;
+#pragma unroll 1
+  for (int hr = 0; hr < RR + 2; ++hr) {
+    const int yi = hr - 1;
+    const int k0 = yi + 2 - RR > 0 ? yi + 2 - RR : 0;
+    const int k1 = yi + 1 < 2 ? yi + 1 : 2;
+    const uint32_t idesc = make_idesc(128, (k1 - k0 + 1) * C);
+    const uint32_t d = d_acc + (RR - 2 - yi + k0) * C;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const uint32_t arow = abase + (hr * TW + kx) * ROWB;
+      const uint32_t brow = wbase + ((kx * 3 + k0) * C) * ROWB;
+#pragma unroll
+      for (int k16 = 0; k16 < C / 16; ++k16)
+        mma(d, make_desc(arow + k16 * 32, 8 * ROWB, LAYOUT), make_desc(brow + k16 * 32, 8 * ROWB, LAYOUT), idesc, 1u);
+    }
+  }
+}
+
+template <int C, int R>
+__global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_constant__ CUtensorMap xmap, const BlockArgs a) {
+  using K = BCfg<C, R>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = sW1 + K::W_AL;
+  uint8_t* sX = sW2 + K::W_AL;                         // two input tiles
+  uint8_t* sT = sX + 2 * K::X_AL;                      // intermediate tile
+  float* sB1 = reinterpret_cast<float*>(sT + K::T_AL);
+  float* sB2 = sB1 + C;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + C);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_xfull = smem_u32(bars), bar_xempty = bar_xfull + 16, bar_m1 = bar_xempty + 16, bar_st = bar_m1 + 8, bar_m2 = bar_st + 8,
+                 bar_init = bar_m2 + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), biases, zeroed intermediate tile ----
+  {
+    constexpr int CPR = K::ROWB / 16;
+    for (int which = 0; which < 2; ++which) {
+      const uint4* src = reinterpret_cast<const uint4*>(which ? a.w2 : a.w1);
+      uint8_t* dstb = which ? sW2 : sW1;
+      const uint32_t wb = smem_u32(dstb);
+      for (int i = tid; i < K::W_BYTES / 16; i += THREADS) {
+        uint32_t addr = wb + (i / CPR) * K::ROWB + (i % CPR) * 16;
+        addr ^= ((addr >> 7) & K::SWZ) << 4;
+        *reinterpret_cast<uint4*>(dstb + (addr - wb)) = __ldg(src + i);
+      }
+    }
+    for (int i = tid; i < C; i += THREADS) sB1[i] = a.b1[i], sB2[i] = a.b2[i];
+    for (int i = tid; i < K::T_AL / 16; i += THREADS) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_xfull + 8 * s, 1);
+      mbar_init(bar_xempty + 8 * s, 4);
+    }
+    mbar_init(bar_m1, 1);
+    mbar_init(bar_st, 4);
+    mbar_init(bar_m2, 1);
+    mbar_init(bar_init, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();                                  // weights / zeros: generic-proxy writes -> async proxy (tensor core)
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), K::TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t acc1 = tmem, acc2 = tmem + K::ACC1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
+        const uint32_t s = tcount & 1, ph = (tcount >> 1) & 1;
+        mbar_wait(bar_xempty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_xfull + 8 * s, K::X_BYTES);
+        tma_load_4d(smem_u32(sX + s * K::X_AL), &xmap, bar_xfull + 8 * s, 0, tx * WO - 2, ty * R - 2, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(bar_init, 0);                          // accumulators zeroed
+      fence_after();
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+        const uint32_t s = tcount & 1, ph = (tcount >> 1) & 1, tp = tcount & 1;
+        mbar_wait(bar_xfull + 8 * s, ph);
+        fence_after();
+        issue_conv<C, K::R1, K::LAYOUT>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1);
+        commit(bar_m1);
+        mbar_wait(bar_st, tp);                         // intermediate tile written (and acc1 zeroed again)
+        fence_after();
+        issue_conv<C, R, K::LAYOUT>(smem_u32(sT), smem_u32(sW2), acc2);
+        commit(bar_m2);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // pixel within the tile row = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int c = 0; c < K::ACC1 + K::ACC2; c += 16) tmem_zero16(tmem + lane_base + c);
+    tmem_wait_st();
+    fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_init);
+    const uint32_t st_base = smem_u32(sT);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+      const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
+      const uint32_t s = tcount & 1, tp = tcount & 1;
+      const int x0 = tx * WO, y0 = ty * R;
+      // ---- E1: intermediate pixel (y0 - 1 + ri, x0 - 1 + m) ----
+      mbar_wait(bar_m1, tp);
+      fence_after();
+      const int ix = x0 - 1 + m;
+      const bool col_in = ix >= 0 && ix < a.w;
+#pragma unroll 1
+      for (int ri = 0; ri < K::R1; ++ri) {
+        const int iy = y0 - 1 + ri;
+        const bool inside = col_in && iy >= 0 && iy < a.h;
+        const uint32_t taddr = acc1 + lane_base + (K::R1 - 1 - ri) * C;
+        uint32_t v[C];
+#pragma unroll
+        for (int c = 0; c < C; c += 16) tmem_ld16(taddr + c, v + c);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < C; c += 16) tmem_zero16(taddr + c);
+        uint32_t pk[C / 2];
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) {
+          const float f0 = inside ? fmaxf(__uint_as_float(v[2 * j]) + sB1[2 * j], 0.f) : 0.f;
+          const float f1 = inside ? fmaxf(__uint_as_float(v[2 * j + 1]) + sB1[2 * j + 1], 0.f) : 0.f;
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        const uint32_t row_ad = st_base + (ri * TW + m) * K::ROWB;
+#pragma unroll
+        for (int u = 0; u < K::ROWB / 16; ++u) {
+          uint32_t ad = row_ad + u * 16;
+          ad ^= ((ad >> 7) & K::SWZ) << 4;
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+        }
+      }
+      tmem_wait_st();
+      fence_before();
+      fence_async_smem();                              // intermediate tile visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_st);
+      // ---- E2: output pixel (y0 + r, x0 + m), residual from the staged input tile at (r + 2, m + 2) ----
+      mbar_wait(bar_m2, tp);
+      fence_after();
+      const int ox = x0 + m;
+      const bool col_ok = m < WO && ox < a.w;
+      const uint32_t sx_base = smem_u32(sX + s * K::X_AL);
+#pragma unroll 1
+      for (int r = 0; r < R; ++r) {
+        const int oy = y0 + r;
+        const uint32_t taddr = acc2 + lane_base + (R - 1 - r) * C;
+        uint32_t v[C];
+#pragma unroll
+        for (int c = 0; c < C; c += 16) tmem_ld16(taddr + c, v + c);
+        uint32_t rv[C / 2];
+        const uint32_t row_ad = sx_base + ((r + 2) * TW + (m + 2)) * K::ROWB;
+#pragma unroll
+        for (int u = 0; u < K::ROWB / 16; ++u) {
+          uint32_t ad = row_ad + u * 16;
+          ad ^= ((ad >> 7) & K::SWZ) << 4;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[4 * u]), "=r"(rv[4 * u + 1]), "=r"(rv[4 * u + 2]), "=r"(rv[4 * u + 3]) : "r"(ad));
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < C; c += 16) tmem_zero16(taddr + c);
+        if (col_ok && oy < a.h) {
+          uint32_t o[C / 2];
+#pragma unroll
+          for (int j = 0; j < C / 2; ++j) {
+            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + sB2[2 * j] + __uint_as_float(rv[j] << 16), 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + sB2[2 * j + 1] + __uint_as_float(rv[j] & 0xffff0000u), 0.f);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+            o[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w + ox) * C);
+#pragma unroll
+          for (int u = 0; u < K::ROWB / 16; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        }
+      }
+      tmem_wait_st();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_xempty + 8 * s);  // the input tile (residual source) is free
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, K::TMEM_COLS);
+}
+
+template <int C, int R>
+int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
+  using K = BCfg<C, R>;
+  EncodeFn encode = get_encode();
+  if (!encode) {
+    ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return TTK_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap map;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TW, (cuuint32_t)K::RX, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             K::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    ttk_set_error("cuTensorMapEncodeTiled failed for the fused block %s", c1.name.c_str());
+    return TTK_ERR_CUDA;
+  }
+  BlockArgs a;
+  a.w1 = c1.w_umma, a.w2 = c2.w_umma, a.b1 = c1.bias, a.b2 = c2.bias, a.out = (__nv_bfloat16*)y;
+  a.n = n, a.h = h, a.w = w;
+  a.tiles_x = ttk_cdiv(w, WO), a.tiles_y = ttk_cdiv(h, R);
+  a.total = a.tiles_x * a.tiles_y * n;
+  const int grid = std::max(1, std::min(a.total, ttk_num_sms()));
+  block_umma_kernel<C, R><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}
+
+}  // namespace
+
+// y = relu(conv2(relu(conv1(x))) + x) for two 3x3 stride-1 convolutions with cin = cout = 16 or 32 (padded), NHWC bf16.
+int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
+  if (c1.k != 3 || c2.k != 3 || c1.stride != 1 || c2.stride != 1 || c1.cin_p != c1.cout_p || c2.cin_p != c1.cin_p || c2.cout_p != c1.cin_p)
+    return TTK_ERR_UNSUPPORTED;
+  if (c1.cin_p == 16) return launch<16, 8>(c1, c2, x, y, n, h, w, st);
+  if (c1.cin_p == 32) return launch<32, 4>(c1, c2, x, y, n, h, w, st);
+  return TTK_ERR_UNSUPPORTED;
+}

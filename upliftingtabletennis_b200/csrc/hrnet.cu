@@ -581,11 +581,47 @@ int prepare_dual(ttk_hrnet* h) {
   return TTK_OK;
 }
 
+// op oi is conv1 of a BasicBlock whose conv2 (op oi + 1) adds the block input: candidates for block_umma.cu
+bool is_basic_block(const ttk_hrnet* h, size_t oi) {
+  if (oi + 1 >= h->ops.size()) return false;
+  const TtkOp &a = h->ops[oi], &b = h->ops[oi + 1];
+  if (a.type != OP_CONV || b.type != OP_CONV || a.nres != 0 || !a.relu || !b.relu || b.in != a.out || b.nres != 1 || b.res[0] != a.in) return false;
+  const TtkConv &c1 = h->convs[a.conv], &c2 = h->convs[b.conv];
+  if (c1.k != 3 || c2.k != 3 || c1.stride != 1 || c2.stride != 1) return false;
+  if (c1.cin_p != c1.cout_p || c2.cin_p != c1.cin_p || c2.cout_p != c1.cin_p) return false;
+  if (c1.cin_p != 16 && c1.cin_p != 32) return false;
+  if (h->tensors[a.out].last != (int)oi + 1) return false;          // the intermediate tensor has no other reader
+  return true;
+}
+
 template <typename T>
 int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, char* ws, bool umma, cudaStream_t st) {
   bool dual_skipped = false;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const TtkOp& op = h->ops[oi];
+    if (umma && sizeof(T) == 2 && h->use_block_fusion && is_basic_block(h, oi)) {
+      const TtkOp& op2 = h->ops[oi + 1];
+      const TtkTensor& ti = h->tensors[op.in];
+      auto p2 = [&](int t) -> void* { return t == h->input_tensor ? const_cast<void*>(x) : (void*)(ws + h->tensors[t].offset); };
+      if (h->profile) {
+        int rc = profile_mark(h, (int)oi, bs, H, W, sizeof(T), st);
+        if (rc) return rc;
+        // one launch does both convolutions: x in, y out, the intermediate tensor and the residual read never touch HBM
+        ttk_hrnet::Rec& r = h->recs.back();
+        const TtkConv& c2 = h->convs[op2.conv];
+        const double opix = (double)bs * (H >> ti.shift) * (W >> ti.shift);
+        r.flops += 2.0 * opix * c2.cin * c2.cout * 9;
+        r.bytes = 2.0 * opix * ti.c * sizeof(T) + 2.0 * 9 * ti.c * ti.c * sizeof(T);
+      }
+      const int rc = ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st);
+      if (rc == TTK_OK) {
+        h->launches++;
+        ++oi;                                      // conv2 is done as well
+        continue;
+      }
+      if (rc != TTK_ERR_UNSUPPORTED) return rc;
+      if (h->profile) h->recs.pop_back();
+    }
     // bottleneck fusion (tensor-core path): the projection shortcut is folded into conv3's GEMM
     if (umma && h->dual_ready && h->use_dual && (int)oi == h->dual_ds_op) {
       dual_skipped = true;
@@ -896,6 +932,21 @@ extern "C" int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in
   if (path == 0) return launch_conv_simt<float>(cv, a, false, st);
   if (path == 1) return launch_conv_simt<__nv_bfloat16>(cv, a, true, st);
   return ttk_conv_umma_launch(cv, a, st);
+}
+
+// Test hook: one BasicBlock (conv_index = its conv1, conv_index + 1 = its conv2) through the fused tcgen05 kernel on caller buffers:
+// out = relu(conv2(relu(conv1(in))) + in), NHWC bf16.
+extern "C" int ttk_hrnet_debug_block(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, void* out_dev, void* stream) {
+  TTK_CHECK_ARG(h && conv_index >= 0 && conv_index + 1 < (int)h->convs.size() - 1, "ttk_hrnet_debug_block: bad conv index %d", conv_index);
+  const TtkConv &c1 = h->convs[conv_index], &c2 = h->convs[conv_index + 1];
+  TTK_CHECK_ARG(c1.set && c2.set, "ttk_hrnet_debug_block: weights not set");
+  return ttk_block_umma_launch(c1, c2, in_dev, out_dev, n, hin, win, (cudaStream_t)stream);
+}
+
+extern "C" int ttk_hrnet_set_block_fusion(ttk_hrnet* h, int enable) {
+  TTK_CHECK_ARG(h, "ttk_hrnet_set_block_fusion: null handle");
+  h->use_block_fusion = enable ? 1 : 0;
+  return TTK_OK;
 }
 
 extern "C" int ttk_hrnet_last_launches(const ttk_hrnet* h) { return h ? h->launches : 0; }

@@ -66,6 +66,7 @@ struct ttk_hrnet {
   float* bias_dual = nullptr;
   bool dual_ready = false;
   int use_dual = 1;
+  int use_block_fusion = 1;     // BasicBlocks of the 16- and 32-channel branches as one kernel (block_umma.cu)
   // optional per-launch timing (ttk_hrnet_set_profile): events bracket every launch on the caller's stream
   int profile = 0;
   std::vector<cudaEvent_t> events;     // pool, events[i] precedes launch i
@@ -79,3 +80,6 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host);
 // out = relu(W3 a + Wd x + bias): a.in = a (32 ch), a.in2 = x (64 ch); returns TTK_ERR_UNSUPPORTED if the driver rejects the maps
 int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st);
+
+// block_umma.cu: y = relu(conv2(relu(conv1(x))) + x) for the 3x3 stride-1 pairs of a BasicBlock with 16 or 32 (padded) channels.
+int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st);

@@ -142,7 +142,7 @@ def test_network_block_fusion_on_off(net):
         y_off, _ = m(x)
         n_off = m.engine.last_launches()
     finally:
-        lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 0)          # the default (see hrnet.h)
         m.compute_dtype = torch.float32
     assert n_off - n_on == 12           # twelve BasicBlocks of the 16- and 32-channel branches run as one launch each
     ref = ohr.wasb_forward(sd, x.cpu()).numpy()

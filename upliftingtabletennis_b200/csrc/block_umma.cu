@@ -10,8 +10,10 @@
 //   E1: accumulators -> + b1, ReLU, zero outside the image (conv2 pads the intermediate TENSOR with zeros) -> bf16 -> shared
 //       memory in the same swizzled pixel-row layout TMA produces, so conv2 addresses it with the same descriptors
 //   M2: conv2 from that tile,  E2: + b2 + x (from the staged input tile) -> ReLU -> global.
-// Roles (persistent CTA): warp 0 TMA producer (2-slot input ring), warp 1 MMA issuer, warps 2-5 epilogues.  The MMA warp issues
-// M1 of the next tile right behind M2, so it overlaps E2; the accumulators are zeroed by the epilogue that drains them.
+// Roles (persistent CTA): warp 0 TMA producer (input ring), warp 1 MMA issuer, warps 2-5 / 6-9 the epilogue groups of slot 0 / 1.
+// With 16 channels two tiles are in flight per CTA (slot = accumulators + intermediate tile): the MMA issuer polls the slots'
+// barriers and issues whichever convolution is ready, so the tensor pipe works on one tile while the other is in an epilogue.
+// The accumulators are zeroed by the epilogue that drains them (every MMA accumulates).
 #include <algorithm>
 
 #include "hrnet.h"
@@ -21,7 +23,7 @@ namespace {
 
 using namespace umma;
 
-constexpr int BW = 128, WO = 126, TW = 130, THREADS = 192;
+constexpr int BW = 128, WO = 126, TW = 130, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -35,20 +37,21 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
 }
 
-template <int C, int R>
+template <int C, int R, int SLOTS>
 struct BCfg {
   static constexpr int ROWB = 2 * C;                   // bytes per pixel row of a tile (32 or 64)
   static constexpr int R1 = R + 2, RX = R + 4;         // intermediate rows, input rows
+  static constexpr int NX = SLOTS + 1;                 // input tile ring: one tile per slot in flight plus one being loaded
   static constexpr int X_BYTES = RX * TW * ROWB, X_AL = al1024(X_BYTES);
   static constexpr int T_BYTES = R1 * TW * ROWB, T_AL = al1024(T_BYTES);
   static constexpr int W_BYTES = 9 * C * ROWB, W_AL = al1024(W_BYTES);
-  static constexpr int ACC1 = R1 * C, ACC2 = R * C;
+  static constexpr int ACC1 = R1 * C, ACC2 = R * C, ACC = ACC1 + ACC2;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + 2 * W_AL + 2 * X_AL + T_AL + 2 * C * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 + 2 * W_AL + NX * X_AL + SLOTS * T_AL + 2 * C * 4 + 256;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : 4u;     // SWIZZLE_32B / 64B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : 3u;
   static_assert(C == 16 || C == 32, "channel counts of the fused block");
-  static_assert(ACC1 + ACC2 <= 512, "accumulators exceed TMEM");
+  static_assert(SLOTS * ACC <= 512, "accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -82,24 +85,40 @@ __device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint3
   }
 }
 
-template <int C, int R>
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Tiles of a CTA are numbered t = 0, 1, 2, ... in the order it takes them; tile t lives in input buffer t % NX and in slot t % SLOTS
+// (slot = its own accumulators and intermediate tile, served by its own group of four epilogue warps), so with two slots the MMAs of
+// one tile run under the epilogues of the other.
+template <int C, int R, int SLOTS>
 __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_constant__ CUtensorMap xmap, const BlockArgs a) {
-  using K = BCfg<C, R>;
+  using K = BCfg<C, R, SLOTS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW1 = smem;
   uint8_t* sW2 = sW1 + K::W_AL;
-  uint8_t* sX = sW2 + K::W_AL;                         // two input tiles
-  uint8_t* sT = sX + 2 * K::X_AL;                      // intermediate tile
-  float* sB1 = reinterpret_cast<float*>(sT + K::T_AL);
+  uint8_t* sX = sW2 + K::W_AL;                         // NX input tiles
+  uint8_t* sT = sX + K::NX * K::X_AL;                  // one intermediate tile per slot
+  float* sB1 = reinterpret_cast<float*>(sT + SLOTS * K::T_AL);
   float* sB2 = sB1 + C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + C);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const uint32_t bar_xfull = smem_u32(bars), bar_xempty = bar_xfull + 16, bar_m1 = bar_xempty + 16, bar_st = bar_m1 + 8, bar_m2 = bar_st + 8,
-                 bar_init = bar_m2 + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_xfull = smem_u32(bars), bar_xempty = bar_xfull + 8 * 3, bar_m1 = bar_xempty + 8 * 3, bar_st = bar_m1 + 8 * 2, bar_m2 = bar_st + 8 * 2,
+                 bar_init = bar_m2 + 8 * 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int my_tiles = a.total > (int)blockIdx.x ? (a.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), biases, zeroed intermediate tile ----
+  // ---- one-time setup: weights (software swizzle on absolute address bits, as TMA does), biases, zeroed intermediate tiles ----
   {
     constexpr int CPR = K::ROWB / 16;
     for (int which = 0; which < 2; ++which) {
@@ -113,17 +132,19 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       }
     }
     for (int i = tid; i < C; i += THREADS) sB1[i] = a.b1[i], sB2[i] = a.b2[i];
-    for (int i = tid; i < K::T_AL / 16; i += THREADS) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < SLOTS * K::T_AL / 16; i += THREADS) reinterpret_cast<uint4*>(sT)[i] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < K::NX; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
       mbar_init(bar_xempty + 8 * s, 4);
     }
-    mbar_init(bar_m1, 1);
-    mbar_init(bar_st, 4);
-    mbar_init(bar_m2, 1);
-    mbar_init(bar_init, 4);
+    for (int k = 0; k < SLOTS; ++k) {
+      mbar_init(bar_m1 + 8 * k, 1);
+      mbar_init(bar_st + 8 * k, 4);
+      mbar_init(bar_m2 + 8 * k, 1);
+    }
+    mbar_init(bar_init, 4 * SLOTS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();                                  // weights / zeros: generic-proxy writes -> async proxy (tensor core)
@@ -132,14 +153,13 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   __syncthreads();
   fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t acc1 = tmem, acc2 = tmem + K::ACC1;
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t tcount = 0;
-      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = blockIdx.x + t * gridDim.x;
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
-        const uint32_t s = tcount & 1, ph = (tcount >> 1) & 1;
+        const uint32_t s = t % K::NX, ph = (t / K::NX) & 1;
         mbar_wait(bar_xempty + 8 * s, ph ^ 1);
         mbar_expect_tx(bar_xfull + 8 * s, K::X_BYTES);
         tma_load_4d(smem_u32(sX + s * K::X_AL), &xmap, bar_xfull + 8 * s, 0, tx * WO - 2, ty * R - 2, img);
@@ -149,107 +169,149 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
     if (lane == 0) {
       mbar_wait(bar_init, 0);                          // accumulators zeroed
       fence_after();
-      uint32_t tcount = 0;
-      for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
-        const uint32_t s = tcount & 1, ph = (tcount >> 1) & 1, tp = tcount & 1;
-        mbar_wait(bar_xfull + 8 * s, ph);
-        fence_after();
-        issue_conv<C, K::R1, K::LAYOUT>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1);
-        commit(bar_m1);
-        mbar_wait(bar_st, tp);                         // intermediate tile written (and acc1 zeroed again)
-        fence_after();
-        issue_conv<C, R, K::LAYOUT>(smem_u32(sT), smem_u32(sW2), acc2);
-        commit(bar_m2);
+      // per slot: next tile number and whether its conv1 has been issued; a slot advances whenever its barrier has flipped
+      int nxt[SLOTS], stage[SLOTS], live = 0;
+      for (int k = 0; k < SLOTS; ++k) nxt[k] = k, stage[k] = 0, live += k < my_tiles ? 1 : 0;
+      while (live > 0) {
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) {
+          const int t = nxt[k];
+          if (t >= my_tiles) continue;
+          const uint32_t acc1 = tmem + k * K::ACC, acc2 = acc1 + K::ACC1;
+          if (stage[k] == 0) {
+            const uint32_t s = t % K::NX;
+            if (!mbar_test(bar_xfull + 8 * s, (t / K::NX) & 1)) continue;
+            fence_after();
+            issue_conv<C, K::R1, K::LAYOUT>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1);
+            commit(bar_m1 + 8 * k);
+            stage[k] = 1;
+          } else {
+            if (!mbar_test(bar_st + 8 * k, (t / SLOTS) & 1)) continue;       // intermediate tile written (and acc1 zeroed again)
+            fence_after();
+            issue_conv<C, R, K::LAYOUT>(smem_u32(sT + k * K::T_AL), smem_u32(sW2), acc2);
+            commit(bar_m2 + 8 * k);
+            stage[k] = 0;
+            nxt[k] = t + SLOTS;
+            if (nxt[k] >= my_tiles) --live;
+          }
+        }
       }
     }
-  } else {
-    const int q = warp & 3;
+  } else if (warp - 2 < 4 * SLOTS) {
+    // epilogue group k = (warp - 2) / 4 serves slot k; TMEM lane quarter q = warp % 4, thread = pixel of a tile row.
+    // Rows are drained G at a time (64 accumulator columns per TMEM wait) so that the load latency is paid once per group.
+    const int q = warp & 3, k = (warp - 2) >> 2;
     const int m = q * 32 + lane;                       // pixel within the tile row = TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    for (int c = 0; c < K::ACC1 + K::ACC2; c += 16) tmem_zero16(tmem + lane_base + c);
+    const uint32_t acc1 = tmem + k * K::ACC, acc2 = acc1 + K::ACC1;
+    constexpr int G = 64 / C;                          // rows per group
+    for (int c = 0; c < K::ACC; c += 16) tmem_zero16(acc1 + lane_base + c);
     tmem_wait_st();
     fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_init);
-    const uint32_t st_base = smem_u32(sT);
-    uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
+    const uint32_t st_base = smem_u32(sT + k * K::T_AL);
+    for (int t = k; t < my_tiles; t += SLOTS) {
+      const int tile = blockIdx.x + t * gridDim.x;
       const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
-      const uint32_t s = tcount & 1, tp = tcount & 1;
+      const uint32_t s = t % K::NX, tp = (t / SLOTS) & 1;
       const int x0 = tx * WO, y0 = ty * R;
       // ---- E1: intermediate pixel (y0 - 1 + ri, x0 - 1 + m) ----
-      mbar_wait(bar_m1, tp);
+      mbar_wait(bar_m1 + 8 * k, tp);
       fence_after();
       const int ix = x0 - 1 + m;
       const bool col_in = ix >= 0 && ix < a.w;
 #pragma unroll 1
-      for (int ri = 0; ri < K::R1; ++ri) {
-        const int iy = y0 - 1 + ri;
-        const bool inside = col_in && iy >= 0 && iy < a.h;
-        const uint32_t taddr = acc1 + lane_base + (K::R1 - 1 - ri) * C;
-        uint32_t v[C];
+      for (int r0 = 0; r0 < K::R1; r0 += G) {
+        uint32_t v[G][C];
 #pragma unroll
-        for (int c = 0; c < C; c += 16) tmem_ld16(taddr + c, v + c);
+        for (int g = 0; g < G; ++g)
+          if (r0 + g < K::R1) {
+#pragma unroll
+            for (int c = 0; c < C; c += 16) tmem_ld16(acc1 + lane_base + (K::R1 - 1 - (r0 + g)) * C + c, v[g] + c);
+          }
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < C; c += 16) tmem_zero16(taddr + c);
-        uint32_t pk[C / 2];
+        for (int g = 0; g < G; ++g)
+          if (r0 + g < K::R1) {
 #pragma unroll
-        for (int j = 0; j < C / 2; ++j) {
-          const float f0 = inside ? fmaxf(__uint_as_float(v[2 * j]) + sB1[2 * j], 0.f) : 0.f;
-          const float f1 = inside ? fmaxf(__uint_as_float(v[2 * j + 1]) + sB1[2 * j + 1], 0.f) : 0.f;
-          __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
-          pk[j] = *reinterpret_cast<uint32_t*>(&b2);
-        }
-        const uint32_t row_ad = st_base + (ri * TW + m) * K::ROWB;
+            for (int c = 0; c < C; c += 16) tmem_zero16(acc1 + lane_base + (K::R1 - 1 - (r0 + g)) * C + c);
+          }
 #pragma unroll
-        for (int u = 0; u < K::ROWB / 16; ++u) {
-          uint32_t ad = row_ad + u * 16;
-          ad ^= ((ad >> 7) & K::SWZ) << 4;
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+        for (int g = 0; g < G; ++g) {
+          const int ri = r0 + g;
+          if (ri < K::R1) {
+            const int iy = y0 - 1 + ri;
+            const bool inside = col_in && iy >= 0 && iy < a.h;
+            uint32_t pk[C / 2];
+#pragma unroll
+            for (int j = 0; j < C / 2; ++j) {
+              const float f0 = inside ? fmaxf(__uint_as_float(v[g][2 * j]) + sB1[2 * j], 0.f) : 0.f;
+              const float f1 = inside ? fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB1[2 * j + 1], 0.f) : 0.f;
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            const uint32_t row_ad = st_base + (ri * TW + m) * K::ROWB;
+#pragma unroll
+            for (int u = 0; u < K::ROWB / 16; ++u) {
+              uint32_t ad = row_ad + u * 16;
+              ad ^= ((ad >> 7) & K::SWZ) << 4;
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ad), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]), "r"(pk[4 * u + 3]) : "memory");
+            }
+          }
         }
       }
       tmem_wait_st();
       fence_before();
       fence_async_smem();                              // intermediate tile visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_st);
+      if (lane == 0) mbar_arrive(bar_st + 8 * k);
       // ---- E2: output pixel (y0 + r, x0 + m), residual from the staged input tile at (r + 2, m + 2) ----
-      mbar_wait(bar_m2, tp);
+      mbar_wait(bar_m2 + 8 * k, tp);
       fence_after();
       const int ox = x0 + m;
       const bool col_ok = m < WO && ox < a.w;
       const uint32_t sx_base = smem_u32(sX + s * K::X_AL);
 #pragma unroll 1
-      for (int r = 0; r < R; ++r) {
-        const int oy = y0 + r;
-        const uint32_t taddr = acc2 + lane_base + (R - 1 - r) * C;
-        uint32_t v[C];
+      for (int r0 = 0; r0 < R; r0 += G) {
+        uint32_t v[G][C], rv[G][C / 2];
 #pragma unroll
-        for (int c = 0; c < C; c += 16) tmem_ld16(taddr + c, v + c);
-        uint32_t rv[C / 2];
-        const uint32_t row_ad = sx_base + ((r + 2) * TW + (m + 2)) * K::ROWB;
+        for (int g = 0; g < G; ++g)
+          if (r0 + g < R) {
 #pragma unroll
-        for (int u = 0; u < K::ROWB / 16; ++u) {
-          uint32_t ad = row_ad + u * 16;
-          ad ^= ((ad >> 7) & K::SWZ) << 4;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[4 * u]), "=r"(rv[4 * u + 1]), "=r"(rv[4 * u + 2]), "=r"(rv[4 * u + 3]) : "r"(ad));
-        }
+            for (int c = 0; c < C; c += 16) tmem_ld16(acc2 + lane_base + (R - 1 - (r0 + g)) * C + c, v[g] + c);
+            const uint32_t row_ad = sx_base + ((r0 + g + 2) * TW + (m + 2)) * K::ROWB;
+#pragma unroll
+            for (int u = 0; u < K::ROWB / 16; ++u) {
+              uint32_t ad = row_ad + u * 16;
+              ad ^= ((ad >> 7) & K::SWZ) << 4;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[g][4 * u]), "=r"(rv[g][4 * u + 1]), "=r"(rv[g][4 * u + 2]), "=r"(rv[g][4 * u + 3]) : "r"(ad));
+            }
+          }
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < C; c += 16) tmem_zero16(taddr + c);
-        if (col_ok && oy < a.h) {
-          uint32_t o[C / 2];
+        for (int g = 0; g < G; ++g)
+          if (r0 + g < R) {
 #pragma unroll
-          for (int j = 0; j < C / 2; ++j) {
-            const float f0 = fmaxf(__uint_as_float(v[2 * j]) + sB2[2 * j] + __uint_as_float(rv[j] << 16), 0.f);
-            const float f1 = fmaxf(__uint_as_float(v[2 * j + 1]) + sB2[2 * j + 1] + __uint_as_float(rv[j] & 0xffff0000u), 0.f);
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
-            o[j] = *reinterpret_cast<uint32_t*>(&b2);
+            for (int c = 0; c < C; c += 16) tmem_zero16(acc2 + lane_base + (R - 1 - (r0 + g)) * C + c);
           }
-          uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w + ox) * C);
 #pragma unroll
-          for (int u = 0; u < K::ROWB / 16; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+        for (int g = 0; g < G; ++g) {
+          const int r = r0 + g;
+          const int oy = y0 + r;
+          if (r < R && col_ok && oy < a.h) {
+            uint32_t o[C / 2];
+#pragma unroll
+            for (int j = 0; j < C / 2; ++j) {
+              const float f0 = fmaxf(__uint_as_float(v[g][2 * j]) + sB2[2 * j] + __uint_as_float(rv[g][j] << 16), 0.f);
+              const float f1 = fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB2[2 * j + 1] + __uint_as_float(rv[g][j] & 0xffff0000u), 0.f);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+              o[j] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w + ox) * C);
+#pragma unroll
+            for (int u = 0; u < K::ROWB / 16; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
+          }
         }
       }
       tmem_wait_st();
@@ -263,9 +325,9 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
-template <int C, int R>
+template <int C, int R, int SLOTS>
 int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
-  using K = BCfg<C, R>;
+  using K = BCfg<C, R, SLOTS>;
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -273,7 +335,7 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
     attr = true;
   }
   CUtensorMap map;
@@ -293,7 +355,7 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
   a.tiles_x = ttk_cdiv(w, WO), a.tiles_y = ttk_cdiv(h, R);
   a.total = a.tiles_x * a.tiles_y * n;
   const int grid = std::max(1, std::min(a.total, ttk_num_sms()));
-  block_umma_kernel<C, R><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
+  block_umma_kernel<C, R, SLOTS><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
@@ -304,7 +366,7 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
 int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
   if (c1.k != 3 || c2.k != 3 || c1.stride != 1 || c2.stride != 1 || c1.cin_p != c1.cout_p || c2.cin_p != c1.cin_p || c2.cout_p != c1.cin_p)
     return TTK_ERR_UNSUPPORTED;
-  if (c1.cin_p == 16) return launch<16, 8>(c1, c2, x, y, n, h, w, st);
-  if (c1.cin_p == 32) return launch<32, 4>(c1, c2, x, y, n, h, w, st);
+  if (c1.cin_p == 16) return launch<16, 6, 2>(c1, c2, x, y, n, h, w, st);      // two tiles in flight (2 x 224 TMEM columns)
+  if (c1.cin_p == 32) return launch<32, 4, 1>(c1, c2, x, y, n, h, w, st);      // 320 TMEM columns per tile: one slot
   return TTK_ERR_UNSUPPORTED;
 }

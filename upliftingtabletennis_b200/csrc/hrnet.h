@@ -66,7 +66,10 @@ struct ttk_hrnet {
   float* bias_dual = nullptr;
   bool dual_ready = false;
   int use_dual = 1;
-  int use_block_fusion = 1;     // BasicBlocks of the 16- and 32-channel branches as one kernel (block_umma.cu)
+  int use_block_fusion = 0;     // BasicBlocks of the 16- and 32-channel branches as one kernel (block_umma.cu).  Off: measured
+                                // break-even (31.8 vs 31.2-32.0 ms per 32 stacks); the thin-channel MMAs cost ~79 clk each on the
+                                // tensor pipe whatever N <= 48 is, and the fused tile needs 9 of them per output row (halo rows of
+                                // the intermediate) against 7.5 for the two separate kernels, see DESIGN.md section 4.2
   // optional per-launch timing (ttk_hrnet_set_profile): events bracket every launch on the caller's stream
   int profile = 0;
   std::vector<cudaEvent_t> events;     // pool, events[i] precedes launch i

@@ -18,6 +18,16 @@ using namespace umma;
 constexpr int BM = 128, BK = 64, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STG_ROW = 80;         // bytes per staged output row piece (64 + 16 padding: conflict-free 16-byte accesses)
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// implicit transposed-convolution mode: an M tile is a 16 x 8 pixel patch of the input grid (pixel-major rows of the A operand)
+constexpr int PW = 16, PH = 8;
+
 struct GemmMaps {
   CUtensorMap a, w;
 };
@@ -121,7 +131,17 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
           mbar_wait(bar_empty + 8 * s, ph ^ 1);
           mbar_expect_tx(bar_full + 8 * s, C::STAGE_BYTES);
           const uint32_t dst = smem_u32(ring + s * C::STAGE_BYTES);
-          tma_load_2d(dst, &maps.a, bar_full + 8 * s, kb * BK, tm * BM);
+          if (g.implicit_c) {
+            // tap t = (ty, tx): ty = 0 reads the pixel itself, ty = 1 the row below (py = 1) or above (py = 0); same along x.
+            // Out-of-image pixels are TMA zero fill.
+            const int kpt = g.implicit_c / BK, tap = kb / kpt, kc = kb % kpt;
+            const int ptx = (g.up_w + PW - 1) / PW, pty = (g.up_h + PH - 1) / PH;
+            const int px0 = (tm % ptx) * PW, py0 = ((tm / ptx) % pty) * PH, img = tm / (ptx * pty);
+            const int dy = (tap >> 1) == 0 ? 0 : (g.py ? 1 : -1), dx = (tap & 1) == 0 ? 0 : (g.px ? 1 : -1);
+            tma_load_4d(dst, &maps.a, bar_full + 8 * s, kc * BK, px0 + dx, py0 + dy, img);
+          } else {
+            tma_load_2d(dst, &maps.a, bar_full + 8 * s, kb * BK, tm * BM);
+          }
           if (!WRES) tma_load_2d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN);
         }
       }
@@ -159,6 +179,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     const int et = tid - 64;                        // 0..255 among the epilogue threads
     // kernel parameters in registers (the asm memory clobbers below would otherwise re-read them from the constant bank)
     const uint32_t sbias_u32 = smem_u32(sBias);
+    const bool implicit = g.implicit_c > 0;
     const int gM = g.M, gN = g.N, dbg = g.act >> 8, r_mod = g.r_mod, up_w = g.up_w, up_h = g.up_h, upy = g.py, upx = g.px;
     const bool c_bf16 = g.c_bf16 != 0;
     const float* __restrict__ gR = g.R;
@@ -172,18 +193,26 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       const int m_warp = tm * BM + q * 32;
       const int m = m_warp + lane;
-      const bool live = m < gM;
+      const bool live = m < gM;                    // (residual rows; not used in the implicit mode)
+      const int ptx = implicit ? (up_w + PW - 1) / PW : 1, pty = implicit ? (up_h + PH - 1) / PH : 1;
+      const int ipx0 = (tm % ptx) * PW, ipy0 = ((tm / ptx) % pty) * PH, iimg = tm / (ptx * pty);
       // output byte offsets of the four rows this lane copies out (row r0 + lane / 4), -1 = row does not exist
       long long obase[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int mr = m_warp + 8 * i + rsel;
         size_t orow = (size_t)mr;
-        if (up_w) {
+        bool ok = mr < gM;
+        if (implicit) {
+          const int rt = q * 32 + 8 * i + rsel;          // row within the 16 x 8 pixel patch
+          const int x = ipx0 + rt % PW, y = ipy0 + rt / PW;
+          ok = x < up_w && y < up_h;
+          orow = ((size_t)iimg * 2 * up_h + 2 * y + upy) * 2 * up_w + 2 * x + upx;
+        } else if (up_w) {
           const int x = mr % up_w, y = (mr / up_w) % up_h, img = mr / (up_w * up_h);
           orow = ((size_t)img * 2 * up_h + 2 * y + upy) * 2 * up_w + 2 * x + upx;
         }
-        obase[i] = mr < gM ? (long long)(orow * gN) * esz + usel * 16 : -1;
+        obase[i] = ok ? (long long)(orow * gN) * esz + usel * 16 : -1;
       }
       // bias of this tile's columns -> shared memory (read back as broadcasts)
       asm volatile("bar.sync 1, 256;" ::: "memory");             // previous tile's readers are done
@@ -288,12 +317,25 @@ int launch_act(const GemmArgs& g, cudaStream_t st) {
     attr = true;
   }
   GemmMaps maps;
-  if (!encode_2d(&maps.a, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.K, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B) ||
-      !encode_2d(&maps.w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) {
+  bool ok_a;
+  int tiles_m = ttk_cdiv(g.M, BM);
+  if (g.implicit_c) {
+    EncodeFn enc = get_encode();
+    const int c = g.implicit_c, n_img = g.M / (g.up_h * g.up_w);
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)g.up_w, (cuuint64_t)g.up_h, (cuuint64_t)n_img};
+    cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)g.up_w * c * 2, (cuuint64_t)g.up_h * g.up_w * c * 2};
+    cuuint32_t box[4] = {BK, PW, PH, 1}, es[4] = {1, 1, 1, 1};
+    ok_a = enc && enc(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g.A), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    tiles_m = n_img * ttk_cdiv(g.up_w, PW) * ttk_cdiv(g.up_h, PH);
+  } else {
+    ok_a = encode_2d(&maps.a, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.K, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (!ok_a || !encode_2d(&maps.w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) {
     ttk_set_error("ttk_gemm_umma: cuTensorMapEncodeTiled failed (M %d N %d K %d)", g.M, g.N, g.K);
     return TTK_ERR_CUDA;
   }
-  const int tiles_m = ttk_cdiv(g.M, BM), tiles_n = g.N / BN;
+  const int tiles_n = g.N / BN;
   const int grid = std::max(1, std::min(tiles_m * tiles_n, ttk_num_sms()));
   gemm_umma_kernel<BN, WRES, ACT><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, g, tiles_m, tiles_n);
   TTK_LAUNCH_CHECK();
@@ -312,7 +354,8 @@ int launch(const GemmArgs& g, cudaStream_t st) {      // the activation is a com
 }  // namespace
 
 int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st) {
-  if (g.M <= 0 || g.K % BK != 0 || g.N % 128 != 0 || (g.R && g.c_bf16)) {
+  if (g.M <= 0 || g.K % BK != 0 || g.N % 128 != 0 || (g.R && g.c_bf16) ||
+      (g.implicit_c && (g.implicit_c % BK != 0 || g.K != 4 * g.implicit_c || g.up_w <= 0 || g.R))) {
     ttk_set_error("ttk_gemm_umma: unsupported shape M %d N %d K %d", g.M, g.N, g.K);
     return TTK_ERR_UNSUPPORTED;
   }

@@ -602,11 +602,17 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
       const int M = n * fh * fw;
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
+          if (bf) {
+            // tensor-core path: TMA gathers the 2x2 taps straight from the feature map (implicit GEMM, no materialised gather)
+            GemmArgs g;
+            const ttk_vit::Lin& l = h->deconv[layer][py * 2 + px];
+            g.A = feat, g.W = wptr(l.w_off), g.bias = fptr(l.b_off), g.R = nullptr, g.C = outs[layer], g.M = M, g.N = l.n, g.K = l.k;
+            g.act = VIT_ACT_RELU, g.c_bf16 = 1, g.up_h = fh, g.up_w = fw, g.py = py, g.px = px, g.implicit_c = cin;
+            if ((rc = launch_gemm(h, g, dtype, st)) != TTK_OK) return rc;
+            continue;
+          }
           ++h->launches;
-          if (bf)
-            deconv_gather_kernel<__nv_bfloat16><<<ttk_num_sms() * 8, 256, 0, st>>>((const __nv_bfloat16*)feat, n, fh, fw, cin, py, px, (__nv_bfloat16*)w.A);
-          else
-            deconv_gather_kernel<float><<<ttk_num_sms() * 8, 256, 0, st>>>((const float*)feat, n, fh, fw, cin, py, px, (float*)w.A);
+          deconv_gather_kernel<float><<<ttk_num_sms() * 8, 256, 0, st>>>((const float*)feat, n, fh, fw, cin, py, px, (float*)w.A);
           if ((rc = gemm(w.A, h->deconv[layer][py * 2 + px], nullptr, outs[layer], M, VIT_ACT_RELU, bf, fh, fw, py, px)) != TTK_OK) return rc;
         }
       feat = outs[layer];

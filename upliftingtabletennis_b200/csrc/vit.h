@@ -21,6 +21,8 @@ struct GemmArgs {
   int act;
   int c_bf16;             // output type
   int up_h, up_w, py, px; // up_w == 0: no scatter
+  int implicit_c = 0;     // > 0 (tcgen05 path only): A is the NHWC feature map [img][up_h][up_w][implicit_c] itself and the 2x2 taps of the
+                          // transposed convolution's output parity (py, px) are gathered by TMA (K = 4 taps x implicit_c), no materialised gather
 };
 
 struct VitParam {

@@ -31,6 +31,15 @@ constexpr int LAYER_ROWS = 768;                    // qkv 384 | proj 128 | fc1 1
 
 enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
 
+// 32 consecutive floats of a small parameter vector (bias, LayerNorm weight): eight 128-bit uniform loads instead of 32 scalar ones
+__device__ __forceinline__ void ldg32(const float* __restrict__ p, float* out) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
+    out[4 * j] = t.x, out[4 * j + 1] = t.y, out[4 * j + 2] = t.z, out[4 * j + 3] = t.w;
+  }
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -262,8 +271,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       if (add) {
         float a[32];
         tmem_ld32(lane_base + col_delta + chalf + c, a);
+        if (bias) {
+          float bz[32];
+          ldg32(bias + chalf + c, bz);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[c + j] += a[j] + (bias ? __ldg(bias + chalf + c + j) : 0.f);
+          for (int j = 0; j < 32; ++j) v[c + j] += a[j] + bz[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[c + j] += a[j];
+        }
         tmem_st32(lane_base + COL_X + chalf + c, v + c);
       }
 #pragma unroll
@@ -294,11 +310,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
 #pragma unroll
     for (int c = 0; c < 64; c += 8) {
       uint32_t w[4];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(lnw + chalf + c)), g1 = __ldg(reinterpret_cast<const float4*>(lnw + chalf + c + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(lnb + chalf + c)), h1 = __ldg(reinterpret_cast<const float4*>(lnb + chalf + c + 4));
+      const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, gb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = c + 2 * j;
-        const float y0 = (v[i] - mean) * rstd * __ldg(lnw + chalf + i) + __ldg(lnb + chalf + i);
-        const float y1 = (v[i + 1] - mean) * rstd * __ldg(lnw + chalf + i + 1) + __ldg(lnb + chalf + i + 1);
+        const float y0 = (v[i] - mean) * rstd * gw[2 * j] + gb[2 * j];
+        const float y1 = (v[i + 1] - mean) * rstd * gw[2 * j + 1] + gb[2 * j + 1];
         w[j] = pack_bf16(y0, y1);
       }
       *reinterpret_cast<uint4*>(sA + a_off(row, chalf + c)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -375,8 +394,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       for (int c0 = cbase; c0 < cbase + 192; c0 += 32) {        // one head of q, k or v per step
         float a[32];
         tmem_ld32(lane_base + c0, a);
+        {
+          float bz[32];
+          ldg32(lw.qkvb + c0, bz);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] += __ldg(lw.qkvb + c0 + j);
+          for (int j = 0; j < 32; ++j) a[j] += bz[j];
+        }
         const int hh = (c0 >> 5) & 3;
         if (c0 < 256) {
 #pragma unroll
@@ -500,8 +523,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
         float a[32];
         tmem_ld32(lane_base + COL_FC1 + c0, a);
+        {
+          float bz[32];
+          ldg32(lw.fc1b + c0, bz);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j] + __ldg(lw.fc1b + c0 + j), 0.f);
+          for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j] + bz[j], 0.f);
+        }
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           *reinterpret_cast<uint4*>(sQh + a_off(row, c0 + 8 * q4)) =

@@ -189,8 +189,15 @@ class _Detector:
         pos, hms = [], []
         main = torch.cuda.current_stream()
         waited = 0
-        for s0 in range(0, n_stacks, self.chunk):
-            ns = min(self.chunk, n_stacks - s0)
+        # while frames are still arriving the first passes are short (4, then 12 stacks), so that the network starts after 6 frames
+        # instead of 18; afterwards full chunks
+        bounds, s0 = [], 0
+        ramp = [4, 12] if ready is not None and n_stacks > self.chunk else []
+        while s0 < n_stacks:
+            ns = min(ramp.pop(0) if ramp else self.chunk, n_stacks - s0)
+            bounds.append((s0, ns))
+            s0 += ns
+        for s0, ns in bounds:
             f0 = s0 * stack_stride
             f_hi = f0 + (ns - 1) * stack_stride + self.frames_per_stack - 1
             while ready is not None and waited < len(ready) and (waited == 0 or ready[waited - 1][0] < f_hi):

@@ -2,8 +2,8 @@
 // layers, second stage) with every Linear layer on tcgen05.mma.
 // Reference: uplifting/model.py:278-300 (SimpleStaticLayer), :186-229 (rotary attention), :335-390, :529-571.
 //
-// A CTA owns 128 token rows (9 table-token sequences of 14, or 2 temporal sequences of <= 64) for ALL layers of a
-// stage:
+// A CTA owns 128 token rows (8 table-token sequences of 14 in 16-row slots, or 2 temporal sequences of <= 64) for
+// ALL layers of a stage:
 //   * the fp32 residual stream lives in TMEM (128 lanes x 128 columns) for the whole stage; thread r owns row r,
 //     so LayerNorm is a per-thread reduction over tcgen05.ld'ed registers and the residual adds are TMEM
 //     read-modify-writes by the same thread;
@@ -14,7 +14,11 @@
 //     sequence block is the valid part) land in TMEM, the row-owning thread applies masks + safe softmax and writes
 //     un-normalised probabilities as a bf16 A operand, O_h = P V_h accumulates into TMEM and is scaled by 1/sum in
 //     the epilogue (V is stored transposed, keys contiguous, so it is a K-major B operand);
-//   * bias + RoPE + bf16 packing of q/k/v run on CUDA cores straight out of TMEM.
+//   * bias + RoPE + bf16 packing of q/k/v run on CUDA cores straight out of TMEM;
+//   * every CUDA-core phase is split between the two warp groups (warps w and w+4 share TMEM lane quarter w): the
+//     softmax by key columns (partial maxima / sums exchanged through shared memory and a 64-thread named barrier),
+//     the attention-output epilogue by heads, everything else by column halves; the scores of head h+1 are issued
+//     together with P V of head h, so a head costs one MMA round trip.
 #include <cuda.h>
 
 #include "uplift.h"
@@ -109,6 +113,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 64-thread named barrier of the two warps that share a TMEM lane quarter (ids 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
   asm volatile(
@@ -155,19 +168,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   uint8_t* sKh = sQh + 32768;                   // 4 heads x [128 rows][64 B] SW64 (k)
   uint8_t* sVt = sKh + 32768;                   // 4 heads x [32 dims][128 keys] as 2 SW128 halves (v transposed)
   uint8_t* sW = sVt + 32768;
-  __shared__ float sMask[ROWS];
-  __shared__ float sTime[ROWS];
-  __shared__ float2 sRed[ROWS];                 // per-row (sum, sum of squares) exchange between the two column halves
+  // 227 KB - 224 KB of operand tiles leave 3 KB of static shared memory: the exchange buffers overlay dead storage
+  __shared__ float sSum[HEADS][ROWS];           // softmax: the OTHER warp group's partial row sums of the heads a group normalises
+  __shared__ __nv_bfloat16 sMax[2][ROWS];       // softmax: partial row maxima of the two key-column halves (rounded, see below)
+  float* sMask = &sSum[0][0];                   // set-up only: additive key masks and times of the rows
+  float* sTime = &sSum[1][0];
+  float2(*sRed)[ROWS] = reinterpret_cast<float2(*)[ROWS]>(sKh);   // LayerNorm partial sums: k is dead whenever LayerNorm runs
   __shared__ uint64_t bars[4];                  // full[3], mma
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(bars), bar_mma = bar_full + 24;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;       // TMEM lane of this thread (warps w and w+4 share a lane quarter)
-  const bool row_thread = tid < ROWS;
   const int T = p.T;
   const int S = MODE == MODE_POS ? NTAB + 1 : (MODE == MODE_TEMPORAL ? T : T + 1);
-  const int SSTRIDE = MODE == MODE_POS ? NTAB + 1 : 64;
-  const int G = MODE == MODE_POS ? 9 : 2;
+  constexpr int SSTRIDE = MODE == MODE_POS ? 16 : 64;      // rows per sequence slot: a warp's 32 rows hold whole slots
+  constexpr int G = ROWS / SSTRIDE;
   const long long n_seq = MODE == MODE_POS ? (long long)p.batch * T : p.batch;
   const long long seq0 = (long long)blockIdx.x * G;
   const float NEG_INF = -INFINITY;
@@ -261,7 +276,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   };
   // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  ALL threads: warps w and w+4 own the two 64-column halves
   // of row `row` and exchange their partial (sum, sum of squares) through shared memory.
-  const int chalf = (warp >> 2) * 64;
+  const int grp = warp >> 2, quarter = warp & 3;
+  const int chalf = grp * 64;
   auto residual_ln = [&](bool add, uint32_t col_delta, const float* bias, const float* lnw, const float* lnb, bool do_ln, float* out_global) {
     float v[64];
     float s1 = 0.f, s2 = 0.f;
@@ -294,18 +310,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(out_global + chalf + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
     }
     if (!do_ln) return;
-    if (warp >= 4) sRed[row] = make_float2(s1, s2);
-    __syncthreads();
-    if (warp < 4) {
-      const float2 o = sRed[row];
-      s1 += o.x;
-      s2 += o.y;
-      sRed[row] = make_float2(s1, s2);
-    }
-    __syncthreads();
-    const float2 t = sRed[row];
-    const float mean = t.x * (1.f / D);
-    const float var = fmaxf(t.y * (1.f / D) - mean * mean, 0.f);
+    sRed[grp][row] = make_float2(s1, s2);
+    pair_barrier(quarter);
+    const float2 t0 = sRed[0][row], t1 = sRed[1][row];      // both halves add in the same order
+    const float mean = (t0.x + t1.x) * (1.f / D);
+    const float var = fmaxf((t0.y + t1.y) * (1.f / D) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
 #pragma unroll
     for (int c = 0; c < 64; c += 8) {
@@ -323,13 +332,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       *reinterpret_cast<uint4*>(sA + a_off(row, chalf + c)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   };
-  // valid keys of this row inside its warp's 64-column score window (fixed for the whole stage)
-  const int r0 = (warp & 3) * 32;
-  const int c_start = MODE == MODE_POS ? min(((r0 / SSTRIDE) * SSTRIDE) & ~7, 64) : (r0 >> 6) * 64;
-  unsigned long long key_bits = 0ull;
-  for (int j = 0; j < 64; ++j) {
-    const int key = c_start + j;
-    if (q_live && key >= k_lo && key < k_hi && sMask[key] == 0.f) key_bits |= 1ull << j;
+  // Softmax work split.  The keys of a row are its own slot's (k_lo .. k_hi); the two warp groups take half of the
+  // slot's columns each: NC = 8 of 16 (table-token stage) or 32 of 64 (temporal stages) score columns per thread,
+  // starting at key `col0`.  The valid ones are a per-thread bit mask that is fixed for the whole stage.
+  constexpr int NC = SSTRIDE / 2;
+  const int col0 = k_lo + grp * NC;
+  uint32_t key_bits = 0u;
+  for (int j = 0; j < NC; ++j) {
+    const int key = col0 + j;
+    if (q_live && key < k_hi && sMask[key] == 0.f) key_bits |= 1u << j;
   }
 
   if (tid == 0) {
@@ -425,44 +436,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       }
     }
     // ---- attention per head on the tensor cores ---------------------------------------------------
-    float inv_sum[HEADS];
+    auto issue_scores = [&](int hh) {             // thread 0 only: S = Q_h K_h^T (K = 32 = two K16 steps)
+      const uint32_t qa = smem_u32(sQh + hh * 8192), ka = smem_u32(sKh + hh * 8192);
+      umma(tmem + COL_S, make_desc_sw64(qa), make_desc_sw64(ka), 0u);
+      umma(tmem + COL_S, make_desc_sw64(qa + 32), make_desc_sw64(ka + 32), 1u);
+    };
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_scores(0);
+      umma_commit(bar_mma);
+    }
+    float own_sum[2] = {0.f, 0.f};
 #pragma unroll 1
     for (int hh = 0; hh < HEADS; ++hh) {
-      proxy_fence();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQh + hh * 8192), ka = smem_u32(sKh + hh * 8192);
-        umma(tmem + COL_S, make_desc_sw64(qa), make_desc_sw64(ka), 0u);
-        umma(tmem + COL_S, make_desc_sw64(qa + 32), make_desc_sw64(ka + 32), 1u);
-        umma_commit(bar_mma);
-      }
-      mma_sync();
-      if (row_thread) {
-        // masks + safe softmax of this row over its warp's 64-column window; un-normalised bf16 probabilities -> sA
-        float e[64];
-        tmem_ld32(lane_base + COL_S + c_start, e);
-        tmem_ld32(lane_base + COL_S + c_start + 32, e + 32);
+      mma_sync();       // S_hh is complete; for hh > 0 so is O_{hh-1}, and P (sA) is free again
+      {
+        // masks + safe softmax of this row; each warp group takes NC of the row's key columns, the partial maxima meet
+        // in shared memory; un-normalised bf16 probabilities -> sA, partial sums -> sSum (used by the O epilogue)
+        float e[NC];
+        if constexpr (MODE == MODE_POS) {
+          float a0[8], a1[8];                      // the warp's rows sit in two 16-row slots: load both, keep the own one
+          const uint32_t c = lane_base + COL_S + quarter * 32 + grp * 8;
+          tmem_ld8_nowait(c, a0);
+          tmem_ld8_nowait(c + 16, a1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) e[j] = (lane & 16) ? a1[j] : a0[j];
+        } else {
+          tmem_ld32(lane_base + COL_S + (quarter >> 1) * 64 + grp * 32, e);
+        }
         float mx = NEG_INF;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
+        for (int j = 0; j < NC; ++j) {
           e[j] *= scale;
-          if ((key_bits >> j) & 1ull) mx = fmaxf(mx, e[j]);
+          if ((key_bits >> j) & 1u) mx = fmaxf(mx, e[j]);
         }
+        // any common offset is a valid softmax shift: both groups use the maximum of the two bf16-rounded partial maxima
+        const __nv_bfloat16 mxr = __float2bfloat16_rn(mx);
+        sMax[grp][row] = mxr;
+        pair_barrier(quarter);
+        mx = fmaxf(__bfloat162float(mxr), __bfloat162float(sMax[grp ^ 1][row]));
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          e[j] = ((key_bits >> j) & 1ull) ? __expf(e[j] - mx) : 0.f;
+        for (int j = 0; j < NC; ++j) {
+          e[j] = ((key_bits >> j) & 1u) ? __expf(e[j] - mx) : 0.f;
           sum += e[j];
         }
-        inv_sum[hh] = sum > 0.f ? 1.f / sum : 0.f;      // fully masked row -> zero output (safe softmax)
+        if ((hh >> 1) == grp) own_sum[hh & 1] = sum; else sSum[hh][row] = sum;   // group g normalises heads 2g, 2g+1
 #pragma unroll
-        for (int jj = 0; jj < 64; jj += 8)
-          *reinterpret_cast<uint4*>(sA + a_off(row, c_start + jj)) =
+        for (int jj = 0; jj < NC; jj += 8)
+          *reinterpret_cast<uint4*>(sA + a_off(row, col0 + jj)) =
               make_uint4(pack_bf16(e[jj], e[jj + 1]), pack_bf16(e[jj + 2], e[jj + 3]), pack_bf16(e[jj + 4], e[jj + 5]), pack_bf16(e[jj + 6], e[jj + 7]));
-        for (int c = 0; c < c_start; c += 8) *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(0, 0, 0, 0);
-        for (int c = c_start + 64; c < ROWS; c += 8) *reinterpret_cast<uint4*>(sA + a_off(row, c)) = make_uint4(0, 0, 0, 0);
+        if (hh == 0) {
+          // columns outside the row's slot are zero for every head: written once per layer (sA held the LayerNorm output)
+          if constexpr (MODE == MODE_POS) {
+            const int own = (k_lo >> 3) + grp;     // the 8-column chunk this thread just wrote
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int ch = 2 * i + grp;
+              if (ch != own) *reinterpret_cast<uint4*>(sA + a_off(row, ch * 8)) = make_uint4(0, 0, 0, 0);
+            }
+          } else {
+            const int zb = ((quarter >> 1) ? 0 : 64) + grp * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(sA + a_off(row, zb + i * 8)) = make_uint4(0, 0, 0, 0);
+          }
+        }
       }
       proxy_fence();
       tc_fence_before();
@@ -474,23 +516,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
         for (int k16 = 0; k16 < 8; ++k16)
           umma(tmem + COL_O + hh * HD, make_desc_sw128(pa + (k16 >> 2) * 16384 + (k16 & 3) * 32),
                make_desc_sw128(va + (k16 >> 2) * 4096 + (k16 & 3) * 32), k16 != 0 ? 1u : 0u, IDESC_128x32);
+        if (hh + 1 < HEADS) issue_scores(hh + 1);  // every thread has drained S_hh; one round trip per head
         umma_commit(bar_mma);
       }
-      mma_sync();       // P (sA) is free again, O_h is complete
     }
-    // ---- attention output: O_h / sum -> bf16 A operand of the projection --------------------------------
-    if (row_thread) {
+    mma_sync();         // O of the last head is complete
+    // ---- attention output: O_h / sum -> bf16 A operand of the projection; two heads per warp group -------------
 #pragma unroll
-      for (int hh = 0; hh < HEADS; ++hh) {
-        float a[32];
-        tmem_ld32(lane_base + COL_O + hh * HD, a);
-        const float is = inv_sum[hh];
+    for (int i = 0; i < 2; ++i) {
+      const int hh = grp * 2 + i;
+      float a[32];
+      tmem_ld32(lane_base + COL_O + hh * HD, a);
+      const float sum = own_sum[i] + sSum[hh][row];
+      const float is = sum > 0.f ? 1.f / sum : 0.f;      // a fully masked row sums to zero -> zero output (safe softmax)
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(sA + a_off(row, hh * HD + 8 * q4)) =
-              make_uint4(pack_bf16(a[8 * q4] * is, a[8 * q4 + 1] * is), pack_bf16(a[8 * q4 + 2] * is, a[8 * q4 + 3] * is),
-                         pack_bf16(a[8 * q4 + 4] * is, a[8 * q4 + 5] * is), pack_bf16(a[8 * q4 + 6] * is, a[8 * q4 + 7] * is));
-      }
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<uint4*>(sA + a_off(row, hh * HD + 8 * q4)) =
+            make_uint4(pack_bf16(a[8 * q4] * is, a[8 * q4 + 1] * is), pack_bf16(a[8 * q4 + 2] * is, a[8 * q4 + 3] * is),
+                       pack_bf16(a[8 * q4 + 4] * is, a[8 * q4 + 5] * is), pack_bf16(a[8 * q4 + 6] * is, a[8 * q4 + 7] * is));
     }
     // ---- projection GEMM (no bias, model.py:268) -------------------------------------------
     proxy_fence();
@@ -673,7 +716,7 @@ int ttk_uplift_tc_stage(ttk_uplift* h, int mode, const UpliftIO& io, cudaStream_
     p.n_layers = 4;
     p.layer_first = 0;
     p.out_rows = io.X;
-    uplift_tc_kernel<MODE_POS><<<ttk_cdiv(ntok, 9), TC_THREADS, TC_SMEM, st>>>(wmap, p);
+    uplift_tc_kernel<MODE_POS><<<ttk_cdiv(ntok, 8), TC_THREADS, TC_SMEM, st>>>(wmap, p);
   } else if (mode == MODE_TEMPORAL) {
     p.layers = h->layers_dev + 4;
     p.n_layers = h->depth - 4;

@@ -138,32 +138,33 @@ __global__ void __launch_bounds__(256) preprocess_tile_kernel(const uint8_t* __r
   const uint32_t wx = (uint32_t)tx.a0 | ((uint32_t)tx.a1 << 16);
   const float* my_lut = s_lut + (threadIdx.x & (LUT_COPIES - 1));
   // staging slots of this thread: vector v of source row r (0: upper, 1: lower) of frame f
-  int st_src[PRE_STAGE], st_dst[PRE_STAGE];                    // source byte offset without the row term; < 0: none
+  int st_dst[PRE_STAGE], st_col[PRE_STAGE];                    // shared offset (< 0: none), byte offset within the source row
+  size_t st_src[PRE_STAGE];                                    // byte offset from the stack's first frame, without the row term
   bool st_low[PRE_STAGE], st_ragged[PRE_STAGE];
 #pragma unroll
   for (int j = 0; j < PRE_STAGE; ++j) {
     const int i = threadIdx.x + 256 * j;
     const int v = i % nvec, r = (i / nvec) & 1, f = i / (2 * nvec);
     st_dst[j] = i < F * 2 * nvec ? (f * 2 + r) * PRE_ROW_BYTES + 16 * v : -1;
-    st_src[j] = byte_lo + 16 * v;
+    st_col[j] = byte_lo + 16 * v;
+    st_src[j] = (size_t)f * frame_bytes + st_col[j];
     st_low[j] = r != 0;
-    st_ragged[j] = byte_lo + 16 * v + 16 > (int)row_bytes;
+    st_ragged[j] = st_col[j] + 16 > (int)row_bytes;
   }
   uint4 q[PRE_STAGE];
-  auto fetch = [&](int t) {                                    // global -> registers
-    const int s = t / dst_h, y = t - s * dst_h;
-    const AxisTap ty = axis_tap(y, src_h, scale_y);
+  auto fetch = [&](int s, const AxisTap& ty) {                 // global -> registers
+    const uint8_t* base = frames + (size_t)s * stack_stride * frame_bytes;
+    const uint8_t* up = base + (size_t)ty.s0 * row_bytes;
+    const uint8_t* low = base + (size_t)ty.s1 * row_bytes;
 #pragma unroll
     for (int j = 0; j < PRE_STAGE; ++j) {
       if (st_dst[j] < 0) continue;
-      const int i = threadIdx.x + 256 * j;
-      const int f = i / (2 * nvec);
-      const uint8_t* src = frames + (size_t)(s * stack_stride + f) * frame_bytes + (size_t)(st_low[j] ? ty.s1 : ty.s0) * row_bytes + st_src[j];
+      const uint8_t* src = (st_low[j] ? low : up) + st_src[j];
       if (!st_ragged[j]) {
         q[j] = __ldg(reinterpret_cast<const uint4*>(src));
       } else {                                                  // ragged end of the row
         uint8_t tmp[16];
-        for (int b = 0; b < 16; ++b) tmp[b] = (st_src[j] + b < (int)row_bytes) ? __ldg(src + b) : 0;
+        for (int b = 0; b < 16; ++b) tmp[b] = (st_col[j] + b < (int)row_bytes) ? __ldg(src + b) : 0;
         q[j] = *reinterpret_cast<uint4*>(tmp);
       }
     }
@@ -174,17 +175,21 @@ __global__ void __launch_bounds__(256) preprocess_tile_kernel(const uint8_t* __r
       if (st_dst[j] >= 0) *reinterpret_cast<uint4*>(s_rows[buf] + st_dst[j]) = q[j];
   };
   int t = t_first, buf = 0;
+  int s = t / dst_h, y = t - s * dst_h;                          // (stack, row) of tile t, advanced without divisions
+  const int s_step = t_step / dst_h, y_step = t_step - s_step * dst_h;
+  AxisTap ty = axis_tap(min(y, dst_h - 1), src_h, scale_y);
   if (t < n_tiles) {
-    fetch(t);
+    fetch(s, ty);
     stash(0);
   }
   __syncthreads();
   for (; t < n_tiles; t += t_step, buf ^= 1) {
     const bool more = t + t_step < n_tiles;
-    if (more) fetch(t + t_step);
-    const int s = t / dst_h, y = t - s * dst_h;
+    int s_next = s + s_step, y_next = y + y_step;
+    if (y_next >= dst_h) y_next -= dst_h, ++s_next;
+    const AxisTap ty_next = axis_tap(y_next, src_h, scale_y);
+    if (more) fetch(s_next, ty_next);
     if (x < dst_w) {
-      const AxisTap ty = axis_tap(y, src_h, scale_y);
       const uint32_t wy0 = (uint32_t)ty.a0 << 16, wy1 = (uint32_t)ty.a1 << 16;
       float v[3 * F];
 #pragma unroll
@@ -203,7 +208,8 @@ __global__ void __launch_bounds__(256) preprocess_tile_kernel(const uint8_t* __r
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const uint32_t acc = __umulhi(wy0, h[0][c] >> 4) + __umulhi(wy1, h[1][c] >> 4);           // ((a * (h >> 4)) >> 16, twice
-          const uint32_t u8 = min(255u, (acc + 2u) >> 2);
+          // the weights of an axis sum to at most 2049, so acc <= 1020 and the result needs no saturation (cv2 saturates here)
+          const uint32_t u8 = (acc + 2u) >> 2;
           v[f * 3 + c] = my_lut[(c * 256 + u8) * LUT_COPIES];
         }
       }
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(256) preprocess_tile_kernel(const uint8_t* __r
       }
     }
     if (more) stash(buf ^ 1);
+    s = s_next, y = y_next, ty = ty_next;
     __syncthreads();
   }
 }

@@ -4,9 +4,9 @@
 //
 // A CTA owns 128 token rows (8 table-token sequences of 14 in 16-row slots, or 2 temporal sequences of <= 64) for
 // ALL layers of a stage:
-//   * the fp32 residual stream lives in TMEM (128 lanes x 128 columns) for the whole stage; thread r owns row r,
-//     so LayerNorm is a per-thread reduction over tcgen05.ld'ed registers and the residual adds are TMEM
-//     read-modify-writes by the same thread;
+//   * the fp32 residual stream lives in TMEM (128 lanes x 128 columns) for the whole stage; four threads (one per
+//     warp group) own 32 columns of row r each, so LayerNorm is a per-thread reduction over tcgen05.ld'ed registers
+//     plus a four-way exchange, and the residual adds are TMEM read-modify-writes by the same thread;
 //   * GEMM A operands (LayerNorm output, attention output, ReLU(fc1)) are written as bf16 into 128-byte-swizzled
 //     K-major shared tiles, B operands are the weight matrices' own (out, in) rows streamed by TMA from one
 //     [layers*768][128] bf16 matrix through a 3-slot ring, accumulators go to TMEM columns 0..383;
@@ -15,10 +15,12 @@
 //     un-normalised probabilities as a bf16 A operand, O_h = P V_h accumulates into TMEM and is scaled by 1/sum in
 //     the epilogue (V is stored transposed, keys contiguous, so it is a K-major B operand);
 //   * bias + RoPE + bf16 packing of q/k/v run on CUDA cores straight out of TMEM;
-//   * every CUDA-core phase is split between the two warp groups (warps w and w+4 share TMEM lane quarter w): the
-//     softmax by key columns (partial maxima / sums exchanged through shared memory and a 64-thread named barrier),
-//     the attention-output epilogue by heads, everything else by column halves; the scores of head h+1 are issued
-//     together with P V of head h, so a head costs one MMA round trip.
+//   * 16 warps: every CUDA-core phase is split between four warp groups (warps q, q+4, q+8, q+12 share TMEM lane
+//     quarter q): the softmax by key columns (partial maxima / sums exchanged through shared memory and a 128-thread
+//     named barrier), the q/k/v and attention-output epilogues by heads, everything else by 32-column quarters.  The
+//     kernel is latency bound (one CTA per SM, dependent TMEM-load -> math -> store chains), so four warps per
+//     scheduler instead of two is what hides it; the scores of head h+1 are issued together with P V of head h, so a
+//     head costs one MMA round trip.
 #include <cuda.h>
 
 #include "uplift.h"
@@ -26,7 +28,9 @@
 namespace {
 
 constexpr int D = 128, HEADS = 4, HD = 32, NF = 16, NTAB = 13;
-constexpr int TC_THREADS = 256;
+constexpr int NG = 4;                                // warp groups: warps 4g .. 4g+3 cover the four TMEM lane quarters
+constexpr int TC_THREADS = 128 * NG;
+constexpr int CW = 128 / NG;                        // columns of every 128-column phase per thread
 constexpr int ROWS = 128;
 constexpr int CHUNK_BYTES = 32768;                 // 128 weight rows x 128 K bf16 = two 16 KB K-halves
 constexpr int SA_BYTES = 32768, SQ_BYTES = 128 * 384 * 2, SW_BYTES = 3 * CHUNK_BYTES;
@@ -34,15 +38,6 @@ constexpr int TC_SMEM = SA_BYTES + SQ_BYTES + SW_BYTES;
 constexpr int LAYER_ROWS = 768;                    // qkv 384 | proj 128 | fc1 128 | fc2 128
 
 enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
-
-// 32 consecutive floats of a small parameter vector (bias, LayerNorm weight): eight 128-bit uniform loads instead of 32 scalar ones
-__device__ __forceinline__ void ldg32(const float* __restrict__ p, float* out) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + j);
-    out[4 * j] = t.x, out[4 * j + 1] = t.y, out[4 * j + 2] = t.z, out[4 * j + 3] = t.w;
-  }
-}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -101,7 +96,7 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t* u = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -111,17 +106,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]),
         "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_ld4_nowait(uint32_t taddr, float* v) {
   uint32_t* u = reinterpret_cast<uint32_t*>(v);
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]), "=r"(u[9]),
+                 "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
                : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// 64-thread named barrier of the two warps that share a TMEM lane quarter (ids 1..4; 0 is __syncthreads)
-__device__ __forceinline__ void pair_barrier(int quarter) { asm volatile("bar.sync %0, 64;" ::"r"(quarter + 1) : "memory"); }
+// 128-thread named barrier of the four warps that share a TMEM lane quarter (ids 1..4; 0 is __syncthreads)
+__device__ __forceinline__ void quad_barrier(int quarter) { asm volatile("bar.sync %0, 128;" ::"r"(quarter + 1) : "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* u = reinterpret_cast<const uint32_t*>(v);
   asm volatile(
@@ -167,18 +166,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   uint8_t* sQh = sA + SA_BYTES;                 // 4 heads x [128 rows][64 B] SW64 (q); later the fc2 A operand
   uint8_t* sKh = sQh + 32768;                   // 4 heads x [128 rows][64 B] SW64 (k)
   uint8_t* sVt = sKh + 32768;                   // 4 heads x [32 dims][128 keys] as 2 SW128 halves (v transposed)
-  uint8_t* sW = sVt + 32768;
-  // 227 KB - 224 KB of operand tiles leave 3 KB of static shared memory: the exchange buffers overlay dead storage
-  __shared__ float sSum[HEADS][ROWS];           // softmax: the OTHER warp group's partial row sums of the heads a group normalises
-  __shared__ __nv_bfloat16 sMax[2][ROWS];       // softmax: partial row maxima of the two key-column halves (rounded, see below)
-  float* sMask = &sSum[0][0];                   // set-up only: additive key masks and times of the rows
-  float* sTime = &sSum[1][0];
-  float2(*sRed)[ROWS] = reinterpret_cast<float2(*)[ROWS]>(sKh);   // LayerNorm partial sums: k is dead whenever LayerNorm runs
+  uint8_t* sW = sVt + 32768;                    // weight ring, 3 slots
+  // 227 KB - 224 KB of operand tiles leave 3 KB of static shared memory, so the exchange buffers overlay dead storage:
+  // ring slot 2 is empty between the QKV GEMM and the end of the attention (the fc2 weights are fetched after it),
+  // k is dead whenever LayerNorm runs.
+  float(*sMax)[ROWS] = reinterpret_cast<float(*)[ROWS]>(sW + 2 * CHUNK_BYTES);                        // [NG][ROWS] partial row maxima
+  float(*sSum)[NG][ROWS] = reinterpret_cast<float(*)[NG][ROWS]>(sW + 2 * CHUNK_BYTES + NG * ROWS * 4);  // [HEADS][NG][ROWS] partial row sums
+  float2(*sRed)[ROWS] = reinterpret_cast<float2(*)[ROWS]>(sKh);                                        // [NG][ROWS] LayerNorm partial sums
+  __shared__ float sMask[ROWS];                 // set-up only: additive key masks and times of the rows
+  __shared__ float sTime[ROWS];
   __shared__ uint64_t bars[4];                  // full[3], mma
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(bars), bar_mma = bar_full + 24;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = (warp & 3) * 32 + lane;       // TMEM lane of this thread (warps w and w+4 share a lane quarter)
+  const int grp = warp >> 2, quarter = warp & 3;           // warps q, q+4, q+8, q+12 share TMEM lane quarter q
+  const int row = quarter * 32 + lane;                      // TMEM lane of this thread
+  const int cq = grp * CW;                                  // this thread's 32 columns of every 128-column phase
   const int T = p.T;
   const int S = MODE == MODE_POS ? NTAB + 1 : (MODE == MODE_TEMPORAL ? T : T + 1);
   constexpr int SSTRIDE = MODE == MODE_POS ? 16 : 64;      // rows per sequence slot: a warp's 32 rows hold whole slots
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   // per-row sequence bookkeeping
   const int g_row = row / SSTRIDE, s_row = row - g_row * SSTRIDE;
   const long long seq_row = seq0 + g_row;
-  const bool valid = g_row < G && s_row < S && seq_row < n_seq;
+  const bool valid = s_row < S && seq_row < n_seq;
   if (tid < ROWS) {
     float m = NEG_INF, t_row = __int_as_float(0x7fc00000);     // NaN time: no rotation (cls token / padding row)
     if (valid) {
@@ -225,12 +228,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
-  const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
   constexpr uint32_t COL_X = 384, COL_S = 0, COL_O = 128, COL_PROJ = 256, COL_FC1 = 0, COL_FC2 = 128;
-  const int k_lo = g_row * SSTRIDE, k_hi = (g_row < G) ? k_lo + S : k_lo;      // this row's key block
+  const int k_lo = g_row * SSTRIDE, k_hi = k_lo + S;        // this row's key block
   const bool q_live = sMask[row] == 0.f;
 
-  // rotary table of this thread's row (both warp groups keep a copy): angle = rint(t / 0.002) * inv_freq
+  // rotary table of this thread's row (every warp group keeps a copy): angle = rint(t / 0.002) * inv_freq
   float rc[NF], rs[NF];
   {
     const float t = sTime[row];
@@ -274,53 +277,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_phase ^= 1;
     tc_fence_after();
   };
-  // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  ALL threads: warps w and w+4 own the two 64-column halves
-  // of row `row` and exchange their partial (sum, sum of squares) through shared memory.
-  const int grp = warp >> 2, quarter = warp & 3;
-  const int chalf = grp * 64;
+  // x (+= delta [+ bias]) -> TMEM, then LayerNorm -> sA.  ALL threads: the four warps of a lane quarter own 32 columns
+  // of row `row` each and exchange their partial (sum, sum of squares) through shared memory.
   auto residual_ln = [&](bool add, uint32_t col_delta, const float* bias, const float* lnw, const float* lnb, bool do_ln, float* out_global) {
-    float v[64];
+    float v[CW];
+    tmem_ld32_nowait(lane_base + COL_X + cq, v);
+    if (add) {
+      float a[CW];
+      tmem_ld32_nowait(lane_base + col_delta + cq, a);
+      tmem_ld_wait();
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + cq + j));
+          v[j] += a[j] + bz.x, v[j + 1] += a[j + 1] + bz.y, v[j + 2] += a[j + 2] + bz.z, v[j + 3] += a[j + 3] + bz.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CW; ++j) v[j] += a[j];
+      }
+      tmem_st32(lane_base + COL_X + cq, v);
+    } else {
+      tmem_ld_wait();
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      tmem_ld32(lane_base + COL_X + chalf + c, v + c);
-      if (add) {
-        float a[32];
-        tmem_ld32(lane_base + col_delta + chalf + c, a);
-        if (bias) {
-          float bz[32];
-          ldg32(bias + chalf + c, bz);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[c + j] += a[j] + bz[j];
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[c + j] += a[j];
-        }
-        tmem_st32(lane_base + COL_X + chalf + c, v + c);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s1 += v[c + j];
-        s2 = fmaf(v[c + j], v[c + j], s2);
-      }
+    for (int j = 0; j < CW; ++j) {
+      s1 += v[j];
+      s2 = fmaf(v[j], v[j], s2);
     }
     if (add) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     if (out_global) {
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(out_global + chalf + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      for (int c = 0; c < CW; c += 4) *reinterpret_cast<float4*>(out_global + cq + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
     }
     if (!do_ln) return;
     sRed[grp][row] = make_float2(s1, s2);
-    pair_barrier(quarter);
-    const float2 t0 = sRed[0][row], t1 = sRed[1][row];      // both halves add in the same order
-    const float mean = (t0.x + t1.x) * (1.f / D);
-    const float var = fmaxf((t0.y + t1.y) * (1.f / D) - mean * mean, 0.f);
+    quad_barrier(quarter);
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {                // every group adds in the same order
+      const float2 t = sRed[g][row];
+      t1 += t.x;
+      t2 += t.y;
+    }
+    const float mean = t1 * (1.f / D);
+    const float var = fmaxf(t2 * (1.f / D) - mean * mean, 0.f);
     const float rstd = rsqrtf(var + 1e-5f);
 #pragma unroll
-    for (int c = 0; c < 64; c += 8) {
+    for (int c = 0; c < CW; c += 8) {
       uint32_t w[4];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(lnw + chalf + c)), g1 = __ldg(reinterpret_cast<const float4*>(lnw + chalf + c + 4));
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(lnb + chalf + c)), h1 = __ldg(reinterpret_cast<const float4*>(lnb + chalf + c + 4));
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(lnw + cq + c)), g1 = __ldg(reinterpret_cast<const float4*>(lnw + cq + c + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(lnb + cq + c)), h1 = __ldg(reinterpret_cast<const float4*>(lnb + cq + c + 4));
       const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, gb[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -329,13 +337,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
         const float y1 = (v[i + 1] - mean) * rstd * gw[2 * j + 1] + gb[2 * j + 1];
         w[j] = pack_bf16(y0, y1);
       }
-      *reinterpret_cast<uint4*>(sA + a_off(row, chalf + c)) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(sA + a_off(row, cq + c)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   };
-  // Softmax work split.  The keys of a row are its own slot's (k_lo .. k_hi); the two warp groups take half of the
-  // slot's columns each: NC = 8 of 16 (table-token stage) or 32 of 64 (temporal stages) score columns per thread,
+  // Softmax work split.  The keys of a row are its own slot's (k_lo .. k_hi); the warp groups take a quarter of the
+  // slot's columns each: NC = 4 of 16 (table-token stage) or 16 of 64 (temporal stages) score columns per thread,
   // starting at key `col0`.  The valid ones are a per-thread bit mask that is fixed for the whole stage.
-  constexpr int NC = SSTRIDE / 2;
+  constexpr int NC = SSTRIDE / NG;
   const int col0 = k_lo + grp * NC;
   uint32_t key_bits = 0u;
   for (int j = 0; j < NC; ++j) {
@@ -362,17 +370,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
         src = s_row == 0 ? p.cls : p.second_in + (seq_row * T + (s_row - 1)) * D;
       }
     }
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      float a[32];
+    float a[CW];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src) q = __ldg(reinterpret_cast<const float4*>(src + chalf + c + j));
-        a[j] = q.x; a[j + 1] = q.y; a[j + 2] = q.z; a[j + 3] = q.w;
-      }
-      tmem_st32(lane_base + COL_X + chalf + c, a);
+    for (int j = 0; j < CW; j += 4) {
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) q = __ldg(reinterpret_cast<const float4*>(src + cq + j));
+      a[j] = q.x; a[j + 1] = q.y; a[j + 2] = q.z; a[j + 3] = q.w;
     }
+    tmem_st32(lane_base + COL_X + cq, a);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     residual_ln(false, 0, nullptr, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
   }
@@ -393,46 +398,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       umma_commit(bar_mma);
     }
     mma_sync();
-    if (tid == 0) {
+    if (tid == 0) {                               // proj, fc1; ring slot 2 stays empty (scratch) until the attention is done
       issue_load(g0 + 3);
       issue_load(g0 + 4);
-      issue_load(g0 + 5);
     }
-    // ---- q/k/v epilogue: bias, RoPE (q, k), bf16 operands; warps 0-3 take columns 0..191, warps 4-7 192..383 -----
-    {
-      const int cbase = (warp >> 2) * 192;
+    // ---- q/k/v epilogue: bias, RoPE (q, k), bf16 operands; warp group g takes head g of q, of k and of v -----------
 #pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + 192; c0 += 32) {        // one head of q, k or v per step
-        float a[32];
-        tmem_ld32(lane_base + c0, a);
-        {
-          float bz[32];
-          ldg32(lw.qkvb + c0, bz);
+    for (int i = 0; i < 3; ++i) {
+      const int c0 = i * D + cq;
+      float a[CW];
+      tmem_ld32_nowait(lane_base + c0, a);
+      tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] += bz[j];
+      for (int j = 0; j < CW; j += 4) {
+        const float4 bz = __ldg(reinterpret_cast<const float4*>(lw.qkvb + c0 + j));
+        a[j] += bz.x, a[j + 1] += bz.y, a[j + 2] += bz.z, a[j + 3] += bz.w;
+      }
+      if (i < 2) {
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {                           // rotate pairs (2f, 2f+1)
+          const float x0 = a[2 * f], x1 = a[2 * f + 1];
+          a[2 * f] = x0 * rc[f] - x1 * rs[f];
+          a[2 * f + 1] = x0 * rs[f] + x1 * rc[f];
         }
-        const int hh = (c0 >> 5) & 3;
-        if (c0 < 256) {
+        uint8_t* base = (i == 0 ? sQh : sKh) + grp * 8192 + row * 64;
 #pragma unroll
-          for (int f = 0; f < NF; ++f) {                         // rotate pairs (2f, 2f+1)
-            const float x0 = a[2 * f], x1 = a[2 * f + 1];
-            a[2 * f] = x0 * rc[f] - x1 * rs[f];
-            a[2 * f + 1] = x0 * rs[f] + x1 * rc[f];
-          }
-          uint8_t* base = (c0 < 128 ? sQh : sKh) + hh * 8192 + row * 64;
+        for (int q4 = 0; q4 < 4; ++q4)                           // 64-byte swizzle: 16-byte chunk ^= (row >> 1) & 3
+          *reinterpret_cast<uint4*>(base + ((q4 ^ ((row >> 1) & 3)) << 4)) =
+              make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                         pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+      } else {
+        // v transposed: element (dim n, key = row) of head grp; keys contiguous, two 128-byte-swizzled halves
+        uint8_t* base = sVt + grp * 8192 + (row >> 6) * 4096;
+        const int b = (row & 63) * 2;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)                         // 64-byte swizzle: 16-byte chunk ^= (row >> 1) & 3
-            *reinterpret_cast<uint4*>(base + ((q4 ^ ((row >> 1) & 3)) << 4)) =
-                make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
-                           pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
-        } else {
-          // v transposed: element (dim n, key = row) of head hh; keys contiguous, two 128-byte-swizzled halves
-          uint8_t* base = sVt + hh * 8192 + (row >> 6) * 4096;
-          const int b = (row & 63) * 2;
-#pragma unroll
-          for (int n = 0; n < 32; ++n)
-            *reinterpret_cast<__nv_bfloat16*>(base + n * 128 + ((((b >> 4) ^ (n & 7)) << 4) | (b & 15))) = __float2bfloat16_rn(a[n]);
-        }
+        for (int n = 0; n < 32; ++n)
+          *reinterpret_cast<__nv_bfloat16*>(base + n * 128 + ((((b >> 4) ^ (n & 7)) << 4) | (b & 15))) = __float2bfloat16_rn(a[n]);
       }
     }
     // ---- attention per head on the tensor cores ---------------------------------------------------
@@ -449,7 +450,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       issue_scores(0);
       umma_commit(bar_mma);
     }
-    float own_sum[2] = {0.f, 0.f};
 #pragma unroll 1
     for (int hh = 0; hh < HEADS; ++hh) {
       mma_sync();       // S_hh is complete; for hh > 0 so is O_{hh-1}, and P (sA) is free again
@@ -458,51 +458,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
         // in shared memory; un-normalised bf16 probabilities -> sA, partial sums -> sSum (used by the O epilogue)
         float e[NC];
         if constexpr (MODE == MODE_POS) {
-          float a0[8], a1[8];                      // the warp's rows sit in two 16-row slots: load both, keep the own one
-          const uint32_t c = lane_base + COL_S + quarter * 32 + grp * 8;
-          tmem_ld8_nowait(c, a0);
-          tmem_ld8_nowait(c + 16, a1);
+          float a0[4], a1[4];                      // the warp's rows sit in two 16-row slots: load both, keep the own one
+          const uint32_t c = lane_base + COL_S + quarter * 32 + grp * 4;
+          tmem_ld4_nowait(c, a0);
+          tmem_ld4_nowait(c + 16, a1);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = (lane & 16) ? a1[j] : a0[j];
+          for (int j = 0; j < 4; ++j) e[j] = (lane & 16) ? a1[j] : a0[j];
         } else {
-          tmem_ld32(lane_base + COL_S + (quarter >> 1) * 64 + grp * 32, e);
+          tmem_ld16_nowait(lane_base + COL_S + (quarter >> 1) * 64 + grp * 16, e);
+          tmem_ld_wait();
         }
         float mx = NEG_INF;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-          e[j] *= scale;
-          if ((key_bits >> j) & 1u) mx = fmaxf(mx, e[j]);
+          e[j] = ((key_bits >> j) & 1u) ? e[j] * scale : NEG_INF;
+          mx = fmaxf(mx, e[j]);
         }
-        // any common offset is a valid softmax shift: both groups use the maximum of the two bf16-rounded partial maxima
-        const __nv_bfloat16 mxr = __float2bfloat16_rn(mx);
-        sMax[grp][row] = mxr;
-        pair_barrier(quarter);
-        mx = fmaxf(__bfloat162float(mxr), __bfloat162float(sMax[grp ^ 1][row]));
+        sMax[grp][row] = mx;
+        quad_barrier(quarter);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) mx = fmaxf(mx, sMax[g][row]);
+        if (mx == NEG_INF) mx = 0.f;              // fully masked row: every exponential below is exp(-inf) = 0 (safe softmax)
         float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < NC; ++j) {
-          e[j] = ((key_bits >> j) & 1u) ? __expf(e[j] - mx) : 0.f;
+          e[j] = __expf(e[j] - mx);
           sum += e[j];
         }
-        if ((hh >> 1) == grp) own_sum[hh & 1] = sum; else sSum[hh][row] = sum;   // group g normalises heads 2g, 2g+1
+        sSum[hh][grp][row] = sum;
+        if constexpr (MODE == MODE_POS) {
+          *reinterpret_cast<uint2*>(sA + a_off(row, col0)) = make_uint2(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]));
+        } else {
 #pragma unroll
-        for (int jj = 0; jj < NC; jj += 8)
-          *reinterpret_cast<uint4*>(sA + a_off(row, col0 + jj)) =
-              make_uint4(pack_bf16(e[jj], e[jj + 1]), pack_bf16(e[jj + 2], e[jj + 3]), pack_bf16(e[jj + 4], e[jj + 5]), pack_bf16(e[jj + 6], e[jj + 7]));
+          for (int jj = 0; jj < NC; jj += 8)
+            *reinterpret_cast<uint4*>(sA + a_off(row, col0 + jj)) =
+                make_uint4(pack_bf16(e[jj], e[jj + 1]), pack_bf16(e[jj + 2], e[jj + 3]), pack_bf16(e[jj + 4], e[jj + 5]), pack_bf16(e[jj + 6], e[jj + 7]));
+        }
         if (hh == 0) {
           // columns outside the row's slot are zero for every head: written once per layer (sA held the LayerNorm output)
           if constexpr (MODE == MODE_POS) {
-            const int own = (k_lo >> 3) + grp;     // the 8-column chunk this thread just wrote
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int ch = 2 * i + grp;
-              if (ch != own) *reinterpret_cast<uint4*>(sA + a_off(row, ch * 8)) = make_uint4(0, 0, 0, 0);
+            for (int i = 0; i < 4; ++i) {
+              const int ch = 4 * i + grp;          // 8-column chunks grp, grp + 4, ...; the slot's own two hold the probabilities
+              if ((ch >> 1) != g_row) *reinterpret_cast<uint4*>(sA + a_off(row, ch * 8)) = make_uint4(0, 0, 0, 0);
             }
           } else {
-            const int zb = ((quarter >> 1) ? 0 : 64) + grp * 32;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(sA + a_off(row, zb + i * 8)) = make_uint4(0, 0, 0, 0);
+            const int zb = ((quarter >> 1) ? 0 : 64) + grp * 16;
+            *reinterpret_cast<uint4*>(sA + a_off(row, zb)) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(sA + a_off(row, zb + 8)) = make_uint4(0, 0, 0, 0);
           }
         }
       }
@@ -521,17 +525,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       }
     }
     mma_sync();         // O of the last head is complete
-    // ---- attention output: O_h / sum -> bf16 A operand of the projection; two heads per warp group -------------
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int hh = grp * 2 + i;
+    // ---- attention output: O_h / sum -> bf16 A operand of the projection; warp group g normalises head g -------------
+    {
       float a[32];
-      tmem_ld32(lane_base + COL_O + hh * HD, a);
-      const float sum = own_sum[i] + sSum[hh][row];
+      tmem_ld32_nowait(lane_base + COL_O + grp * HD, a);
+      float sum = 0.f;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) sum += sSum[grp][g][row];
       const float is = sum > 0.f ? 1.f / sum : 0.f;      // a fully masked row sums to zero -> zero output (safe softmax)
+      tmem_ld_wait();
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
-        *reinterpret_cast<uint4*>(sA + a_off(row, hh * HD + 8 * q4)) =
+        *reinterpret_cast<uint4*>(sA + a_off(row, grp * HD + 8 * q4)) =
             make_uint4(pack_bf16(a[8 * q4] * is, a[8 * q4 + 1] * is), pack_bf16(a[8 * q4 + 2] * is, a[8 * q4 + 3] * is),
                        pack_bf16(a[8 * q4 + 4] * is, a[8 * q4 + 5] * is), pack_bf16(a[8 * q4 + 6] * is, a[8 * q4 + 7] * is));
     }
@@ -541,6 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
+      issue_load(g0 + 5);                         // fc2 weights into ring slot 2: the softmax scratch in it is dead now
       gemm(g0 + 3, smem_u32(sA), COL_PROJ);
       umma_commit(bar_mma);
     }
@@ -559,25 +565,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     }
     mma_sync();
     if (tid == 0) issue_load(g0 + 7);
-    // ---- ReLU(fc1 + b) -> bf16 A operand (in the q buffer); warps 0-3 columns 0..63, warps 4-7 64..127 ----------
+    // ---- ReLU(fc1 + b) -> bf16 A operand (in the q buffer); 32 columns per warp group ----------
     {
-      const int cbase = (warp >> 2) * 64;
-#pragma unroll 1
-      for (int c0 = cbase; c0 < cbase + 64; c0 += 32) {
-        float a[32];
-        tmem_ld32(lane_base + COL_FC1 + c0, a);
-        {
-          float bz[32];
-          ldg32(lw.fc1b + c0, bz);
+      float a[CW];
+      tmem_ld32_nowait(lane_base + COL_FC1 + cq, a);
+      tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j] + bz[j], 0.f);
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(sQh + a_off(row, c0 + 8 * q4)) =
-              make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
-                         pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+      for (int j = 0; j < CW; j += 4) {
+        const float4 bz = __ldg(reinterpret_cast<const float4*>(lw.fc1b + cq + j));
+        a[j] = fmaxf(a[j] + bz.x, 0.f), a[j + 1] = fmaxf(a[j + 1] + bz.y, 0.f), a[j + 2] = fmaxf(a[j + 2] + bz.z, 0.f), a[j + 3] = fmaxf(a[j + 3] + bz.w, 0.f);
       }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4)
+        *reinterpret_cast<uint4*>(sQh + a_off(row, cq + 8 * q4)) =
+            make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                       pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
     }
     // ---- fc2 GEMM ---------------------------------------------------------------------------
     proxy_fence();

@@ -422,78 +422,74 @@ int launch_conv_simt(const TtkConv& cv, const ConvLaunch& a, bool rounded_weight
 }
 
 // out = act(in + sum_r res_r[y >> s_r, x >> s_r])   (full-resolution fuse of a HighResolutionModule)
-// 16 bytes per thread per access (8 bf16 / 4 fp32 channels), two independent items in flight per thread.
+// 16 bytes per thread per access (8 bf16 / 4 fp32 channels), two independent items in flight per thread.  One grid row per
+// image row and shifts for the channel-vector split (c / V is a power of two), so no thread divides: the first version
+// decomposed a flat 64-bit index with three divisions per item and ran at half the HBM rate because of them.
 template <typename T>
 __global__ void __launch_bounds__(256) sum_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ res0,
                                                   const T* __restrict__ res1, const T* __restrict__ res2, int rs0, int rs1,
-                                                  int rs2, int nres, int n, int h, int w, int c, int relu) {
+                                                  int rs2, int nres, int h, int w, int c, int cv_shift, int relu) {
   constexpr int V = 16 / sizeof(T);                 // channels per 16-byte vector
-  const int cv = c / V;
-  const long long total = (long long)n * h * w * cv;
   const T* rp[3] = {res0, res1, res2};
   const int rsh[3] = {rs0, rs1, rs2};
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long e0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += 2 * stride) {
-    float v[2][V];
-    uint4 raw[2];
-    bool live[2];
+  const int y = blockIdx.y, b = blockIdx.z;
+  const int row_items = w << cv_shift;
+  const size_t row0 = ((size_t)b * h + y) * (size_t)row_items;      // in 16-byte items
+  const int e0 = blockIdx.x * 512 + threadIdx.x;
+  float v[2][V];
+  uint4 raw[2];
+  bool live[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const long long e = e0 + u * stride;
-      live[u] = e < total;
-      if (live[u]) raw[u] = *reinterpret_cast<const uint4*>(in + e * V);
+  for (int u = 0; u < 2; ++u) {
+    const int e = e0 + u * 256;
+    live[u] = e < row_items;
+    if (live[u]) raw[u] = *reinterpret_cast<const uint4*>(in + (row0 + e) * V);
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (!live[u]) continue;
+    const int e = e0 + u * 256;
+    if (sizeof(T) == 2) {
+      const uint32_t wv[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[u][2 * j] = __uint_as_float(wv[j] << 16);
+        v[u][2 * j + 1] = __uint_as_float(wv[j] & 0xffff0000u);
+      }
+    } else {
+      v[u][0] = __uint_as_float(raw[u].x); v[u][1] = __uint_as_float(raw[u].y);
+      v[u][2] = __uint_as_float(raw[u].z); v[u][3] = __uint_as_float(raw[u].w);
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (!live[u]) continue;
-      const long long e = e0 + u * stride;
+    const int x = e >> cv_shift, ci = e & ((1 << cv_shift) - 1);
+    for (int r = 0; r < nres; ++r) {
+      const int sh = rsh[r];
+      const uint4 q = *reinterpret_cast<const uint4*>(rp[r] + (((size_t)b * (h >> sh) + (y >> sh)) * (w >> sh) + (x >> sh)) * c + ci * V);
       if (sizeof(T) == 2) {
-        const uint32_t wv[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          v[u][2 * j] = __uint_as_float(wv[j] << 16);
-          v[u][2 * j + 1] = __uint_as_float(wv[j] & 0xffff0000u);
+          v[u][2 * j] += __uint_as_float(wv[j] << 16);
+          v[u][2 * j + 1] += __uint_as_float(wv[j] & 0xffff0000u);
         }
       } else {
-        v[u][0] = __uint_as_float(raw[u].x); v[u][1] = __uint_as_float(raw[u].y);
-        v[u][2] = __uint_as_float(raw[u].z); v[u][3] = __uint_as_float(raw[u].w);
+        v[u][0] += __uint_as_float(q.x); v[u][1] += __uint_as_float(q.y);
+        v[u][2] += __uint_as_float(q.z); v[u][3] += __uint_as_float(q.w);
       }
-      const int ci = (int)(e % cv);
-      long long pix = e / cv;
-      const int x = (int)(pix % w);
-      pix /= w;
-      const int y = (int)(pix % h);
-      const int b = (int)(pix / h);
-      for (int r = 0; r < nres; ++r) {
-        const int sh = rsh[r];
-        const uint4 q = *reinterpret_cast<const uint4*>(rp[r] + (((size_t)b * (h >> sh) + (y >> sh)) * (w >> sh) + (x >> sh)) * c + ci * V);
-        if (sizeof(T) == 2) {
-          const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[u][2 * j] += __uint_as_float(wv[j] << 16);
-            v[u][2 * j + 1] += __uint_as_float(wv[j] & 0xffff0000u);
-          }
-        } else {
-          v[u][0] += __uint_as_float(q.x); v[u][1] += __uint_as_float(q.y);
-          v[u][2] += __uint_as_float(q.z); v[u][3] += __uint_as_float(q.w);
-        }
-      }
-      if (relu) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
-      }
-      uint4 o;
-      if (sizeof(T) == 2) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][4 % V], v[u][5 % V]), p3 = __floats2bfloat162_rn(v[u][6 % V], v[u][7 % V]);
-        o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
-                       *reinterpret_cast<uint32_t*>(&p3));
-      } else {
-        o = make_uint4(__float_as_uint(v[u][0]), __float_as_uint(v[u][1]), __float_as_uint(v[u][2]), __float_as_uint(v[u][3]));
-      }
-      *reinterpret_cast<uint4*>(out + e * V) = o;
     }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
+    }
+    uint4 o;
+    if (sizeof(T) == 2) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][4 % V], v[u][5 % V]), p3 = __floats2bfloat162_rn(v[u][6 % V], v[u][7 % V]);
+      o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
+                     *reinterpret_cast<uint32_t*>(&p3));
+    } else {
+      o = make_uint4(__float_as_uint(v[u][0]), __float_as_uint(v[u][1]), __float_as_uint(v[u][2]), __float_as_uint(v[u][3]));
+    }
+    *reinterpret_cast<uint4*>(out + (row0 + e) * V) = o;
   }
 }
 
@@ -690,8 +686,14 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
     } else if (op.type == OP_SUM) {
       const TtkTensor& to = h->tensors[op.out];
       const int hh = H >> to.shift, ww = W >> to.shift;
-      const long long total = (long long)bs * hh * ww * (to.c / (16 / (int)sizeof(T)));
-      const int blocks = (int)std::min<long long>((total + 511) / 512, (long long)ttk_num_sms() * 16);
+      const int cv = to.c / (16 / (int)sizeof(T));
+      int cv_shift = 0;
+      while ((1 << cv_shift) < cv) ++cv_shift;
+      if ((1 << cv_shift) != cv || bs > 65535 || hh > 65535) {
+        ttk_set_error("fuse sum: %d channels / batch %d / height %d not supported", to.c, bs, hh);
+        return TTK_ERR_UNSUPPORTED;
+      }
+      const dim3 blocks(ttk_cdiv(ww << cv_shift, 512), hh, bs);
       int sh[3] = {0, 0, 0};
       const void* rp[3] = {nullptr, nullptr, nullptr};
       for (int r = 0; r < op.nres; ++r) {
@@ -699,7 +701,7 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
         sh[r] = h->tensors[op.res[r]].shift - to.shift;
       }
       sum_kernel<T><<<blocks, 256, 0, st>>>((const T*)ptr(op.in), (T*)ptr(op.out), (const T*)rp[0], (const T*)rp[1],
-                                           (const T*)rp[2], sh[0], sh[1], sh[2], op.nres, bs, hh, ww, to.c, op.relu ? 1 : 0);
+                                           (const T*)rp[2], sh[0], sh[1], sh[2], op.nres, hh, ww, to.c, cv_shift, op.relu ? 1 : 0);
       TTK_LAUNCH_CHECK();
       h->launches++;
     } else {

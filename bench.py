@@ -357,6 +357,25 @@ def main():
               'decode': {'ms': dec_ms, 'algorithmic_bytes': dec_bytes, 'gbs': dec_bytes / (dec_ms * 1e-3) / 1e9,
                          'hbm_frac': dec_bytes / (dec_ms * 1e-3) / 1e9 / peaks()['hbm_gbs'],
                          'note': 'argmax (one read of every heatmap value) + per-map L-BFGS-B fit; the %d-map batch is smaller than L2' % BATCH}}
+    # the decode's HBM-bound kernel on its own: 64 maps (231 MB, larger than L2), argmax pass timed by the library's events
+    g = torch.Generator(device=dev).manual_seed(0)
+    big = torch.randn((64, H, W), device=dev, generator=g) * 0.05
+    big[:, 100:103, 200:203] += 1.0
+    check(lib.ttk_decode_set_profile(1))
+    am_ms = []
+    for _ in range(5):
+        ops.decode_heatmaps(big, SRC[1], SRC[0], 'table')
+        a_ms, f_ms = C.c_float(), C.c_float()
+        check(lib.ttk_decode_profile_read(C.byref(a_ms), C.byref(f_ms)))
+        am_ms.append((a_ms.value, f_ms.value))
+    check(lib.ttk_decode_set_profile(0))
+    a_ms, f_ms = sorted(am_ms)[len(am_ms) // 2]
+    big_bytes = big.numel() * 4
+    stages['decode_argmax_64maps'] = {'ms': a_ms, 'fit_ms': f_ms, 'algorithmic_bytes': big_bytes, 'gbs': big_bytes / (a_ms * 1e-3) / 1e9,
+                                      'hbm_frac': big_bytes / (a_ms * 1e-3) / 1e9 / peaks()['hbm_gbs'],
+                                      'note': 'argmax_partial_kernel alone on 64 maps of 704x1280 (231 MB > L2), median of 5, CUDA events on the launching '
+                                              'stream; fit_ms is the per-map L-BFGS-B kernel (latency floor, independent of the map count)'}
+    del big
     check(lib.ttk_hrnet_set_profile(engine.h, 1))
     step_device(gather=False)
     torch.cuda.synchronize()

@@ -156,6 +156,11 @@ TTK_API size_t ttk_decode_workspace_bytes(int n_maps, int height, int width);
 TTK_API int ttk_heatmap_decode(const float* heatmaps_dev, int n_maps, int height, int width, int variant,
                        int image_width, int image_height, double* out_xyv_dev, int32_t* out_idx_dev,
                        float* out_win_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Measurement aid (bench.py): with profiling on, ttk_heatmap_decode brackets its two kernels with CUDA events on `stream`;
+ * after the caller synchronised the stream, ttk_decode_profile_read returns the durations in ms of the argmax pass (the
+ * HBM-bound kernel: one read of every heatmap value) and of the per-map fit.  Process-wide state: not for concurrent callers. */
+TTK_API int ttk_decode_set_profile(int enable);
+TTK_API int ttk_decode_profile_read(float* argmax_ms, float* fit_ms);
 
 /* ---------------------------------------------------------------------------------------
  * Trajectory filters between decode and uplift (device versions).

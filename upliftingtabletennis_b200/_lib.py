@@ -58,6 +58,8 @@ def _load():
         'ttk_vit_debug_attention': (i32, [vp, vp, vp, sz, i32, i32, i32, vp]),
         'ttk_decode_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_heatmap_decode': (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]),
+        'ttk_decode_set_profile': (i32, [i32]),
+        'ttk_decode_profile_read': (i32, [C.POINTER(C.c_float), C.POINTER(C.c_float)]),
         'ttk_filter_ball': (i32, [vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp, vp]),
         'ttk_filter_table_workspace_bytes': (sz, [i32, i32, i32]),
         'ttk_filter_table': (i32, [vp, vp, i32, i32, i32, C.c_double, C.c_double, i32, vp, vp, sz, vp]),

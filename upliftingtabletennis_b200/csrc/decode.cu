@@ -186,6 +186,27 @@ int decode_chunks(int hw) {
 
 }  // namespace
 
+namespace {
+bool g_profile = false;
+cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+}  // namespace
+
+extern "C" int ttk_decode_set_profile(int enable) {
+  if (enable && !g_ev[0])
+    for (cudaEvent_t& e : g_ev) TTK_CUDA(cudaEventCreate(&e));
+  g_profile = enable != 0;
+  return TTK_OK;
+}
+
+extern "C" int ttk_decode_profile_read(float* argmax_ms, float* fit_ms) {
+  TTK_CHECK_ARG(argmax_ms && fit_ms, "ttk_decode_profile_read: null pointer");
+  TTK_CHECK_ARG(g_ev[0], "ttk_decode_profile_read: profiling was never enabled");
+  TTK_CUDA(cudaEventSynchronize(g_ev[2]));
+  TTK_CUDA(cudaEventElapsedTime(argmax_ms, g_ev[0], g_ev[1]));
+  TTK_CUDA(cudaEventElapsedTime(fit_ms, g_ev[1], g_ev[2]));
+  return TTK_OK;
+}
+
 extern "C" size_t ttk_decode_workspace_bytes(int n_maps, int height, int width) {
   if (n_maps <= 0 || height <= 0 || width <= 0) return 0;
   return (size_t)n_maps * decode_chunks(height * width) * sizeof(Best);
@@ -209,14 +230,17 @@ extern "C" int ttk_heatmap_decode(const float* heatmaps_dev, int n_maps, int hei
   Best* partial = (Best*)workspace_dev;
   const bool vec = (hw % 4 == 0) && (((uintptr_t)heatmaps_dev & 15) == 0);
   dim3 grid(chunks, n_maps);
+  if (g_profile) TTK_CUDA(cudaEventRecord(g_ev[0], st));
   if (vec)
     argmax_partial_kernel<true><<<grid, 256, 0, st>>>(heatmaps_dev, hw, chunk_elems, partial);
   else
     argmax_partial_kernel<false><<<grid, 256, 0, st>>>(heatmaps_dev, hw, chunk_elems, partial);
   TTK_LAUNCH_CHECK();
+  if (g_profile) TTK_CUDA(cudaEventRecord(g_ev[1], st));
   decode_finalize_kernel<<<n_maps, 32, 0, st>>>(heatmaps_dev, height, width, chunks, partial, variant,
                                                 (double)image_width / width, (double)image_height / height, out_xyv_dev,
                                                 out_idx_dev, out_win_dev);
   TTK_LAUNCH_CHECK();
+  if (g_profile) TTK_CUDA(cudaEventRecord(g_ev[2], st));
   return TTK_OK;
 }

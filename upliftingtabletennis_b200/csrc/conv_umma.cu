@@ -97,6 +97,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// 256-bit read-only load: the 16 bf16 channels of one pixel (one 32-byte sector)
+__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+
 __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
   const uint32_t z = 0;
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
@@ -363,8 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               const int sh = a.rsh[0];
               const uint4* rp = reinterpret_cast<const uint4*>(
                   a.res[0] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
-              rv[sb][0] = __ldg(rp);
-              rv[sb][1] = __ldg(rp + 1);
+              ldg256(rp, rv[sb][0], rv[sb][1]);
             }
 #pragma unroll
             for (int rr = 1; rr < 3; ++rr) {
@@ -372,8 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 const int sh = a.rsh[rr];
                 const uint4* rp = reinterpret_cast<const uint4*>(
                     a.res[rr] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
-                rx[sb][rr - 1][0] = __ldg(rp);
-                rx[sb][rr - 1][1] = __ldg(rp + 1);
+                ldg256(rp, rx[sb][rr - 1][0], rx[sb][rr - 1][1]);
               }
             }
           }
@@ -418,9 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
             o[j] = *reinterpret_cast<uint32_t*>(&b2);
           }
-          uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0);
-          op[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          // one 256-bit store: the 16 channels of a pixel are a whole 32-byte sector
+          __nv_bfloat16* op = a.out + (((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0;
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]),
+                       "r"(o[5]), "r"(o[6]), "r"(o[7])
+                       : "memory");
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

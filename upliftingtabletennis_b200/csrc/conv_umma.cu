@@ -114,10 +114,11 @@ constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
 // KS: 1 or 3; S: stride 1 or 2 (3x3 only); CIN: padded input channels; COUT: output channels handled by one CTA
 // (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth;
-// RB: reserve shared memory for TMA-staged residual tiles (double buffered with the accumulators).
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
+// RB: reserve shared memory for TMA-staged residual tiles (double buffered with the accumulators);
+// KCO: channels per K-chunk when not the default (a narrower chunk buys a taller tile for the same shared memory).
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
 struct Cfg {
-  static constexpr int KC = CIN < 64 ? CIN : 64;        // channels per K-chunk = one swizzled smem row
+  static constexpr int KC = KCO ? KCO : (CIN < 64 ? CIN : 64);      // channels per K-chunk = one swizzled smem row
   static constexpr int NKC = CIN / KC;
   static constexpr int ROWB = KC * 2;
   static constexpr int PAD = KS / 2;
@@ -170,9 +171,9 @@ struct KArgs {
   int tiles_x, tiles_y, total;
 };
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
@@ -463,14 +464,25 @@ EncodeFn get_encode() {
 // output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
 int cout_tile(const TtkConv& cv) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? 64 : cv.cout_p; }
 bool fused_ky(const TtkConv& cv) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv) <= 256; }
+// channels per K-chunk (one swizzled shared-memory row).  transition1.0 (3x3, 128 -> 16) is bound by its MMA count (every 128-pixel x
+// 16-channel MMA holds the tensor pipe ~79 clk at N <= 48) and the halo rows are pure overhead: 32-channel chunks make an 8-row tile
+// fit, 3 (R + 2) / R = 3.75 MMAs per K16 step and output row instead of 5 with R = 3.
+int kc_of(const TtkConv& cv) {
+  if (cv.k == 3 && cv.stride == 1 && cv.cin_p == 128 && cv.cout_p == 16) return 32;
+  return cv.cin_p < 64 ? cv.cin_p : 64;
+}
 
 CUtensorMapSwizzle swizzle_for(int row_bytes) {
   return row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
 }
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
 int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO>;
+  if (C::KC != kc_of(cv)) {
+    ttk_set_error("conv %s: kernel K-chunk %d differs from the packed weights' %d", cv.name.c_str(), C::KC, kc_of(cv));
+    return TTK_ERR_STATE;
+  }
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -478,7 +490,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
   if (S == 2 && ((a.hin & 1) || (a.win & 1))) return TTK_ERR_UNSUPPORTED;
@@ -537,7 +549,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   occ = std::max(1, std::min(occ, 2));
   const int gx = std::max(1, std::min(k.total, ttk_num_sms() * occ / nsplit));
   dim3 grid(gx, nsplit);
-  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
@@ -603,7 +615,7 @@ int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dua
 //   otherwise          : [slice][tap][k-chunk][cout_tile][KC]
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
   const int kk = cv.k * cv.k;
-  const int KC = cv.cin_p < 64 ? cv.cin_p : 64;
+  const int KC = kc_of(cv);
   const int nkc = cv.cin_p / KC;
   const int ct = cout_tile(cv);
   const bool fused = fused_ky(cv);
@@ -635,7 +647,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   TTK_UMMA(3, 1, 64, 64, 2, 2, 0)     // stem conv2, quarter-resolution branch
   TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
   TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
-  TTK_UMMA(3, 1, 128, 16, 3, 2, 0)    // transition1.0
+  if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 8, 2, 0, 32>(cv, a, st);     // transition1.0
   TTK_UMMA(3, 1, 128, 64, 2, 1, 0)    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
   // 3x3 stride 2 (transitions and fuse down-paths)
   TTK_UMMA(3, 2, 128, 32, 1, 2, 0)

@@ -148,6 +148,7 @@ struct Cfg {
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(ACC_COLS < 64 || ACC_COLS % 64 == 0, "the epilogue drains whole groups of 64 accumulator columns");
   static_assert(COUT % 16 == 0 && COUT <= 256 && CIN % 16 == 0, "bad channel counts");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -464,11 +465,12 @@ EncodeFn get_encode() {
 // output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
 int cout_tile(const TtkConv& cv) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? 64 : cv.cout_p; }
 bool fused_ky(const TtkConv& cv) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv) <= 256; }
-// channels per K-chunk (one swizzled shared-memory row).  transition1.0 (3x3, 128 -> 16) is bound by its MMA count (every 128-pixel x
-// 16-channel MMA holds the tensor pipe ~79 clk at N <= 48) and the halo rows are pure overhead: 32-channel chunks make an 8-row tile
-// fit, 3 (R + 2) / R = 3.75 MMAs per K16 step and output row instead of 5 with R = 3.
+// channels per K-chunk (one swizzled shared-memory row).  The stride-1 3x3 layers with 64+ input channels are bound by their MMA
+// count (tensor pipe 73-85 % busy; a 128-pixel x 16-channel MMA holds it ~79 clk at N <= 48, ~1 clk per column beyond) and the halo
+// rows of a tile are pure overhead: 3 (R + 2) / R MMAs per K16 step and output row.  32-channel chunks halve the staging boxes so that
+// taller tiles fit: transition1.0 R = 3 -> 8, the 64 -> 64 layers R = 2 -> 4, and the 128 -> 128 layers get a second pipeline stage.
 int kc_of(const TtkConv& cv) {
-  if (cv.k == 3 && cv.stride == 1 && cv.cin_p == 128 && cv.cout_p == 16) return 32;
+  if (cv.k == 3 && cv.stride == 1 && cv.cin_p >= 64) return 32;
   return cv.cin_p < 64 ? cv.cin_p : 64;
 }
 
@@ -644,11 +646,12 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   if (cv.k == KS_ && cv.stride == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_>(cv, a, st);
   // 3x3 stride 1
   TTK_UMMA(3, 1, 16, 64, 4, 3, 0)     // stem conv1 (9 -> 64, input padded to 16 channels)
-  TTK_UMMA(3, 1, 64, 64, 2, 2, 0)     // stem conv2, quarter-resolution branch
+  if (cv.k == 3 && cv.stride == 1 && ci == 64 && co == 64) return launch<3, 1, 64, 64, 4, 3, 0, 32>(cv, a, st);      // stem conv2, quarter-resolution branch
+  if (cv.k == 3 && cv.stride == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0>(cv, a, st);   // no residual tiles to stage: taller tile
   TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
   TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
   if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 8, 2, 0, 32>(cv, a, st);     // transition1.0
-  TTK_UMMA(3, 1, 128, 64, 2, 1, 0)    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
+  if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 64) return launch<3, 1, 128, 64, 2, 2, 0, 32>(cv, a, st);    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
   // 3x3 stride 2 (transitions and fuse down-paths)
   TTK_UMMA(3, 2, 128, 32, 1, 2, 0)
   TTK_UMMA(3, 2, 16, 16, 4, 3, 0)

@@ -192,7 +192,7 @@ class _Detector:
         # while frames are still arriving the first passes are short (4, then 12 stacks), so that the network starts after 6 frames
         # instead of 18; afterwards full chunks
         bounds, s0 = [], 0
-        ramp = [4, 12] if ready is not None and n_stacks > self.chunk else []
+        ramp = [4, 12] if ready is not None and n_stacks >= self.chunk else []
         while s0 < n_stacks:
             ns = min(ramp.pop(0) if ramp else self.chunk, n_stacks - s0)
             bounds.append((s0, ns))

@@ -192,6 +192,21 @@ def test_wasb_bf16_bound(dev):
     assert rel < 3e-2, rel
 
 
+def test_decode_profile_hook(dev):
+    """ttk_decode_set_profile / ttk_decode_profile_read (the measurement aid bench.py uses): both kernels report a duration."""
+    import ctypes as C
+    from upliftingtabletennis_b200 import _lib, ops
+    hm = torch.randn((8, 88, 160), device=dev)
+    _lib.check(_lib.lib.ttk_decode_set_profile(1))
+    try:
+        ops.decode_heatmaps(hm, 1920, 1080, 'table')
+        a, f = C.c_float(), C.c_float()
+        _lib.check(_lib.lib.ttk_decode_profile_read(C.byref(a), C.byref(f)))
+        assert 0.0 < a.value < 50.0 and 0.0 < f.value < 50.0
+    finally:
+        _lib.check(_lib.lib.ttk_decode_set_profile(0))
+
+
 # ------------------------------------------------------------------------------------------------
 # uplifting transformer and tails
 # ------------------------------------------------------------------------------------------------

@@ -51,13 +51,17 @@ def peaks():
     return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
 
 
-def ncu_traffic(kernel_name):
+def ncu_traffic(kernel_name, images_per_launch):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
     capture (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if that kernel was not captured."""
     p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     if not os.path.exists(p):
         return None
-    return json.load(open(p)).get(kernel_name, {}).get('dram_bytes_per_launch')
+    rec = json.load(open(p)).get(kernel_name)
+    if not rec:
+        return None
+    # the capture ran a smaller sub-batch per launch than the bench does: DRAM traffic of these streaming kernels scales with the images
+    return rec['dram_bytes_per_launch'] * images_per_launch / rec.get('images_per_launch', images_per_launch)
 
 
 class ClockSampler:
@@ -419,7 +423,8 @@ def main():
         'peak': pk['hbm_gbs'] if hbm_bound else pk['bf16_tflops_sustained'],
         'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
         'frac': (achieved_gbs / pk['hbm_gbs']) if hbm_bound else (achieved_tf / pk['bf16_tflops_sustained']),
-        'traffic': ncu_traffic(name),
+        'traffic': ncu_traffic(name, BATCH / top[3]),
+        'traffic_note': 'dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture (profiles/ncu_traffic.json, 4 images per launch), scaled to the images of one bench launch',
         'peak_source': pk['source'] + (', copy bandwidth' if hbm_bound else ', sustained bf16 (kernel timed inside a long step)'),
         'intensity_flop_per_byte': intensity, 'ridge_flop_per_byte': ridge,
         'algorithmic_bytes_per_launch': top[2] / top[3], 'algorithmic_flops_per_launch': top[1] / top[3],

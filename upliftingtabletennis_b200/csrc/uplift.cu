@@ -536,9 +536,9 @@ extern "C" int ttk_uplift_set_param(ttk_uplift* h, int i, const float* data_host
 extern "C" size_t ttk_uplift_workspace_bytes(const ttk_uplift* h, int batch, int seq_len, int dtype) {
   (void)dtype;
   if (!h || batch <= 0 || seq_len <= 0) return 0;
-  // X [B*T][128] + table_emb [B*13][128] (+ embed(pos) [B*T][128] without skip connection)
+  // X [B*T][128] + table_emb [B*13][128] (+ embed(pos) [B*T][128] without skip connection) + bf16 attention rows [B*T][128]
   size_t tokens = (size_t)batch * seq_len * (h->skip ? 1 : 2) + (size_t)batch * NTAB;
-  return tokens * D * sizeof(float) + 1024;
+  return tokens * D * sizeof(float) + (size_t)batch * seq_len * D * 2 + 1024;
 }
 
 extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const float* table_dev, const float* mask_dev,
@@ -607,6 +607,7 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
     io.X = X;
     io.table_emb = table_emb;
     io.second_emb = second_emb;
+    io.attn_rows = second_emb + (h->skip ? 0 : ntok * D);
     int rc = ttk_uplift_tc_stage(h, MODE_POS, io, st);
     if (rc) return rc;
     rc = ttk_uplift_tc_stage(h, MODE_TEMPORAL, io, st);

@@ -42,6 +42,7 @@ struct UpliftIO {
   int batch, T;
   float *rot_out, *pos_out;
   float *X, *table_emb, *second_emb;     // workspace slices
+  void* attn_rows;                       // bf16 [batch*T][128]: attention output of the ball tokens in the last table-token layer
 };
 
 // uplift_tc.cu

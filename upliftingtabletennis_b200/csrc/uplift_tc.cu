@@ -156,6 +156,12 @@ struct TcParams {
   const float* cls;
   const float* second_in;
   float* out_rows;                // POS/TEMPORAL: X; SECOND: [batch][128] cls rows
+  // Hand-over between the table-token stage and the temporal stage.  Only the ball token of a table-token sequence is used
+  // afterwards (model.py:375-378), so the last table-token layer stops after its attention: the ball rows' residual stream
+  // (-> X) and normalised attention output (-> attn_rows, bf16) leave the kernel, and the temporal kernel, whose 128 rows are
+  // exactly such ball rows, starts with that layer's projection + MLP ("tail") before its own layers.  1/14 of the rows
+  // pay for the tail instead of all of them.
+  __nv_bfloat16* attn_rows;
 };
 
 template <int MODE>
@@ -249,19 +255,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     }
   }
 
+  // weight chunks of 128 rows: 6 per layer (qkv 3, proj, fc1, fc2).  The temporal stage starts with chunks -3, -2, -1: proj, fc1 and
+  // fc2 of the last table-token layer (the layer before layer_first); ring slot and mbarrier parity follow gchunk + 3.
+  constexpr bool TAIL = MODE == MODE_TEMPORAL, HEADLESS_LAST = MODE == MODE_POS;
   const int total_chunks = p.n_layers * 6;
   auto issue_load = [&](int gchunk) {           // thread 0 only
     if (gchunk >= total_chunks) return;
-    const int slot = gchunk % 3;
-    const int wrow = (p.layer_first + gchunk / 6) * LAYER_ROWS + (gchunk % 6) * 128;
+    const int slot = (gchunk + 3) % 3;
+    const int wrow = gchunk >= 0 ? (p.layer_first + gchunk / 6) * LAYER_ROWS + (gchunk % 6) * 128 : (p.layer_first - 1) * LAYER_ROWS + (6 + gchunk) * 128;
     mbar_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
     const uint32_t dst = smem_u32(sW + slot * CHUNK_BYTES);
     tma_load_2d(dst, &wmap, bar_full + 8 * slot, 0, wrow);
     tma_load_2d(dst + 16384, &wmap, bar_full + 8 * slot, 64, wrow);
   };
   auto gemm = [&](int gchunk, uint32_t a_base, uint32_t col) {   // thread 0 only: D[128 x 128] at TMEM column `col`
-    const int slot = gchunk % 3;
-    mbar_wait(bar_full + 8 * slot, (gchunk / 3) & 1);
+    const int slot = (gchunk + 3) % 3;
+    mbar_wait(bar_full + 8 * slot, ((gchunk + (TAIL ? 3 : 0)) / 3) & 1);
     tc_fence_after();
     const uint32_t b_base = smem_u32(sW + slot * CHUNK_BYTES);
 #pragma unroll
@@ -340,6 +349,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       *reinterpret_cast<uint4*>(sA + a_off(row, cq + c)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   };
+  // ReLU(fc1 + b) -> bf16 A operand of fc2 (in the q buffer); 32 columns per warp group
+  auto relu_fc1 = [&](const float* fc1b) {
+    float a[CW];
+    tmem_ld32_nowait(lane_base + COL_FC1 + cq, a);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < CW; j += 4) {
+      const float4 bz = __ldg(reinterpret_cast<const float4*>(fc1b + cq + j));
+      a[j] = fmaxf(a[j] + bz.x, 0.f), a[j + 1] = fmaxf(a[j + 1] + bz.y, 0.f), a[j + 2] = fmaxf(a[j + 2] + bz.z, 0.f), a[j + 3] = fmaxf(a[j + 3] + bz.w, 0.f);
+    }
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      *reinterpret_cast<uint4*>(sQh + a_off(row, cq + 8 * q4)) =
+          make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
+                     pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
+  };
   // Softmax work split.  The keys of a row are its own slot's (k_lo .. k_hi); the warp groups take a quarter of the
   // slot's columns each: NC = 4 of 16 (table-token stage) or 16 of 64 (temporal stages) score columns per thread,
   // starting at key `col0`.  The valid ones are a per-thread bit mask that is fixed for the whole stage.
@@ -352,9 +377,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   }
 
   if (tid == 0) {
-    issue_load(0);
-    issue_load(1);
-    issue_load(2);
+    issue_load(TAIL ? -3 : 0);
+    issue_load(TAIL ? -2 : 1);
+    issue_load(TAIL ? -1 : 2);
   }
 
   // ---- prologue: residual rows -> TMEM, first LayerNorm -> sA --------------------------------
@@ -379,7 +404,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     }
     tmem_st32(lane_base + COL_X + cq, a);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    residual_ln(false, 0, nullptr, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
+    if constexpr (!TAIL) {
+      residual_ln(false, 0, nullptr, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
+    } else {
+      // ---- tail of the last table-token layer on its ball rows: x += attn Wproj^T; x += fc2(ReLU(fc1(LN2(x)))) -------------
+      const LayerW tw = p.layers[-1];
+      {
+        uint4 o[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (valid) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.attn_rows + (seq_row * T + s_row) * D + cq);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) o[q4] = __ldg(ap + q4);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) *reinterpret_cast<uint4*>(sA + a_off(row, cq + 8 * q4)) = o[q4];
+      }
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        gemm(-3, smem_u32(sA), COL_PROJ);
+        umma_commit(bar_mma);
+      }
+      mma_sync();
+      if (tid == 0) issue_load(0);
+      residual_ln(true, COL_PROJ, nullptr, tw.ln2w, tw.ln2b, true, nullptr);
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        gemm(-2, smem_u32(sA), COL_FC1);
+        umma_commit(bar_mma);
+      }
+      mma_sync();
+      if (tid == 0) issue_load(1);
+      relu_fc1(tw.fc1b);
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        gemm(-1, smem_u32(sQh), COL_FC2);
+        umma_commit(bar_mma);
+      }
+      mma_sync();
+      if (tid == 0) issue_load(2);
+      residual_ln(true, COL_FC2, tw.fc2b, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
+    }
   }
 
   const float scale = 0.17677669529663687f;     // 1/sqrt(32)
@@ -398,7 +471,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       umma_commit(bar_mma);
     }
     mma_sync();
-    if (tid == 0) {                               // proj, fc1; ring slot 2 stays empty (scratch) until the attention is done
+    const bool headless = HEADLESS_LAST && l + 1 == p.n_layers;     // last table-token layer: stops after the attention (see TcParams)
+    if (tid == 0 && !headless) {                  // proj, fc1; ring slot 2 stays empty (scratch) until the attention is done
       issue_load(g0 + 3);
       issue_load(g0 + 4);
     }
@@ -534,6 +608,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       for (int g = 0; g < NG; ++g) sum += sSum[grp][g][row];
       const float is = sum > 0.f ? 1.f / sum : 0.f;      // a fully masked row sums to zero -> zero output (safe softmax)
       tmem_ld_wait();
+      if (headless) {
+        // hand the ball rows over to the temporal kernel: attention output (bf16, as the projection would read it) and residual stream
+        float x[CW];
+        tmem_ld32_nowait(lane_base + COL_X + cq, x);      // warp-collective: every lane loads, the ball rows store
+        tmem_ld_wait();
+        if (valid && s_row == 0) {
+          uint4* ap = reinterpret_cast<uint4*>(p.attn_rows + seq_row * D + grp * HD);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            ap[q4] = make_uint4(pack_bf16(a[8 * q4] * is, a[8 * q4 + 1] * is), pack_bf16(a[8 * q4 + 2] * is, a[8 * q4 + 3] * is),
+                                pack_bf16(a[8 * q4 + 4] * is, a[8 * q4 + 5] * is), pack_bf16(a[8 * q4 + 6] * is, a[8 * q4 + 7] * is));
+          float* xp = p.out_rows + seq_row * D + cq;
+#pragma unroll
+          for (int c = 0; c < CW; c += 4) *reinterpret_cast<float4*>(xp + c) = make_float4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+        }
+        break;
+      }
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4)
         *reinterpret_cast<uint4*>(sA + a_off(row, grp * HD + 8 * q4)) =
@@ -566,21 +657,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     mma_sync();
     if (tid == 0) issue_load(g0 + 7);
     // ---- ReLU(fc1 + b) -> bf16 A operand (in the q buffer); 32 columns per warp group ----------
-    {
-      float a[CW];
-      tmem_ld32_nowait(lane_base + COL_FC1 + cq, a);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < CW; j += 4) {
-        const float4 bz = __ldg(reinterpret_cast<const float4*>(lw.fc1b + cq + j));
-        a[j] = fmaxf(a[j] + bz.x, 0.f), a[j + 1] = fmaxf(a[j + 1] + bz.y, 0.f), a[j + 2] = fmaxf(a[j + 2] + bz.z, 0.f), a[j + 3] = fmaxf(a[j + 3] + bz.w, 0.f);
-      }
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4)
-        *reinterpret_cast<uint4*>(sQh + a_off(row, cq + 8 * q4)) =
-            make_uint4(pack_bf16(a[8 * q4], a[8 * q4 + 1]), pack_bf16(a[8 * q4 + 2], a[8 * q4 + 3]),
-                       pack_bf16(a[8 * q4 + 4], a[8 * q4 + 5]), pack_bf16(a[8 * q4 + 6], a[8 * q4 + 7]));
-    }
+    relu_fc1(lw.fc1b);
     // ---- fc2 GEMM ---------------------------------------------------------------------------
     proxy_fence();
     tc_fence_before();
@@ -712,6 +789,7 @@ int ttk_uplift_tc_stage(ttk_uplift* h, int mode, const UpliftIO& io, cudaStream_
   p.times = io.times;
   p.cls = h->dev("cls_token");
   p.second_in = h->skip ? io.X : io.second_emb;
+  p.attn_rows = (__nv_bfloat16*)io.attn_rows;
   const long long ntok = (long long)io.batch * io.T;
   if (mode == MODE_POS) {
     p.layers = h->layers_dev;

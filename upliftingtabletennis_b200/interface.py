@@ -209,10 +209,24 @@ class _Detector:
             else:
                 x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
                 hm = self.model.heatmaps_from_nhwc16(x)
-            # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian
-            pos.append(ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table'))
+            # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian.  It runs on a second stream:
+            # the per-map fit is a latency-bound kernel of one warp per map (~0.3 ms whatever the number of maps) that fits beside the
+            # persistent convolution CTAs, so the decode of pass i hides under the network of pass i + 1.
+            side = getattr(self, '_decode_stream', None)
+            if side is None:
+                side = self._decode_stream = torch.cuda.Stream(device=hm.device)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                p = ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table')
+            hm.record_stream(side)
+            pos.append(p)
             if return_heatmaps:
                 hms.append(hm)
+        main.wait_stream(side)
+        for p in pos:
+            p.record_stream(main)
         return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
 
     def _upload(self, images, dev):

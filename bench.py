@@ -494,8 +494,11 @@ def main():
 
 
 if __name__ == '__main__':
-    # stdout carries exactly one JSON line: everything else the libraries print (model loaders etc.) goes to stderr
-    _real_stdout = sys.stdout
+    # stdout carries exactly one JSON line: everything else the libraries print (model loaders, and NCCL's version banner, which is a
+    # C-level write to file descriptor 1) goes to stderr
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
     _orig_print = print
 

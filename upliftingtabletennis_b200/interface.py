@@ -179,6 +179,7 @@ def _uplifting_transform(ball_coords, table_coords, times):
 class _Detector:
     frames_per_stack = 1
     chunk = 16                     # stacks per network pass: bounds the workspace and lets uploads overlap compute
+    ramp = (4, 12)                 # stacks of the first passes while a clip's frames are still being uploaded
 
     def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps, ready=None):
         """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None.
@@ -191,13 +192,7 @@ class _Detector:
         waited = 0
         # while frames are still arriving the first passes are short (4, then 12 stacks), so that the network starts after 6 frames
         # instead of 18; afterwards full chunks
-        bounds, s0 = [], 0
-        ramp = [4, 12] if ready is not None and n_stacks >= self.chunk else []
-        while s0 < n_stacks:
-            ns = min(ramp.pop(0) if ramp else self.chunk, n_stacks - s0)
-            bounds.append((s0, ns))
-            s0 += ns
-        for s0, ns in bounds:
+        for s0, ns in self._pass_plan(n_stacks, self.chunk, ready is not None, self.ramp):
             f0 = s0 * stack_stride
             f_hi = f0 + (ns - 1) * stack_stride + self.frames_per_stack - 1
             while ready is not None and waited < len(ready) and (waited == 0 or ready[waited - 1][0] < f_hi):
@@ -228,6 +223,18 @@ class _Detector:
         for p in pos:
             p.record_stream(main)
         return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
+
+    @staticmethod
+    def _pass_plan(n_stacks, chunk, streaming, ramp=(4, 12)):
+        """[(first stack, stacks)] of the network passes over a clip: full chunks, except that a clip whose frames are still being
+        uploaded starts with two short passes (4, then 12 stacks)."""
+        bounds, s0 = [], 0
+        ramp = list(ramp) if streaming and n_stacks >= chunk else []
+        while s0 < n_stacks:
+            ns = min(ramp.pop(0) if ramp else chunk, n_stacks - s0)
+            bounds.append((s0, ns))
+            s0 += ns
+        return bounds
 
     def _upload(self, images, dev):
         """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames are staged through a cached
@@ -261,7 +268,7 @@ class _Detector:
                 else:
                     view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
                     out[i].copy_(self._stage[i], non_blocking=True)
-                if i % 4 == 3 or i == len(uniq) - 1:
+                if i % 2 == 1 or i == len(uniq) - 1:      # an event every other frame: the first pass (4 stacks) starts after 6 frames
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                     ready.append((i, ev))

@@ -328,8 +328,16 @@ def main():
     clip = torch.from_numpy(synthetic.frames_1080p(CLIP_FRAMES, seed=200 + rank)).pin_memory()
     rallies = [[clip[i] for i in range(r0, r0 + RALLY_FRAMES)] for r0 in range(0, CLIP_FRAMES, RALLY_FRAMES)]
 
+    from upliftingtabletennis_b200 import sharding
+
     def pipe_step():
-        return [pipe.predict(r, 50.0) for r in rallies]
+        out = [pipe.predict(r, 50.0) for r in rallies]
+        if world > 1:
+            # configs[4]: clips are sharded over the ranks; one NCCL all_gather of the fixed-size per-clip records (616 B each) per step
+            recs = torch.stack([sharding.pack_record(sp, torch.as_tensor(p3)) for sp, p3 in out]).to(dev)
+            table = sharding.gather_records(recs, world * len(rallies), world)
+            assert table.shape == (world * len(rallies), sharding.RECORD_FLOATS)
+        return out
     pipe_steps = 2
     pipe_ms = timed(pipe_step, pipe_steps, 1)
     res = pipe_step()
@@ -479,7 +487,7 @@ def main():
                        'f32': {'value': vit_res['f32'][0], 'ms_per_step': vit_res['f32'][1]}}
     line['pipeline'] = {'value': world * CLIP_FRAMES * pipe_steps / (pipe_ms * 1e-3), 'unit': 'frames/s', 'clips_per_sec': world * pipe_steps / (pipe_ms * 1e-3),
                         'ms_per_clip': pipe_ms / pipe_steps, 'frames_per_clip': CLIP_FRAMES, 'dtype': args.dtype, 'finite_outputs': pipe_ok, 'trajectory_lengths': pipe_detections,
-                        'workload': 'configs[2]: hubconf.full_pipeline().predict(...) on a 300-frame pinned host 1080p clip, as 6 rallies of 50 frames '
+                        'workload': 'configs[2] (one GPU) / configs[4] (clips sharded over the ranks, NCCL all_gather of the per-clip result records): hubconf.full_pipeline().predict(...) on a 300-frame pinned host 1080p clip per rank, as 6 rallies of 50 frames '
                                     '(the uplifting model takes < 50 detections): WASB main + aux on 288 stacks, HRNet main + aux on 300 frames, '
                                     '8376 heatmap decodes, both agreement filters, uplift; end to end',
                         'h2d_bytes_per_clip': CLIP_FRAMES * SRC[0] * SRC[1] * 3}

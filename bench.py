@@ -257,6 +257,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     t0 = time.perf_counter()
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    # the reference's default call also returns the heatmaps (B, 1, h, w) float32 to the host: 3.6 MB per stack
+    ms_e2e_hm = timed(lambda: det.predict(triples), args.steps, args.warmup)
     value = world * BATCH * args.steps / (ms_dev * 1e-3)
     e2e_value = world * BATCH * args.steps / (ms_e2e * 1e-3)
 
@@ -485,6 +487,9 @@ def main():
                        'tensor_frac': VIT_GFLOP_PER_STACK * vit_res['bf16'][0] / 1e3 / world / pk['bf16_tflops_sustained'],
                        'gpu_launches': vit_res['bf16'][2], 'bf16_vs_f32_rel_l2': vit_rel,
                        'f32': {'value': vit_res['f32'][0], 'ms_per_step': vit_res['f32'][1]}}
+    line['e2e']['with_heatmaps'] = {'value': world * BATCH * args.steps / (ms_e2e_hm * 1e-3), 'unit': 'frames/s',
+                                    'd2h_bytes_per_step': BATCH * 24 + heat.numel() * 4,
+                                    'api': "hubconf.ball_detection('wasb').predict(triples)  (reference default: heatmaps returned as numpy)"}
     line['pipeline'] = {'value': world * CLIP_FRAMES * pipe_steps / (pipe_ms * 1e-3), 'unit': 'frames/s', 'clips_per_sec': world * pipe_steps / (pipe_ms * 1e-3),
                         'ms_per_clip': pipe_ms / pipe_steps, 'frames_per_clip': CLIP_FRAMES, 'dtype': args.dtype, 'finite_outputs': pipe_ok, 'trajectory_lengths': pipe_detections,
                         'workload': 'configs[2] (one GPU) / configs[4] (clips sharded over the ranks, NCCL all_gather of the per-clip result records): hubconf.full_pipeline().predict(...) on a 300-frame pinned host 1080p clip per rank, as 6 rallies of 50 frames '

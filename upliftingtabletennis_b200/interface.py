@@ -181,8 +181,11 @@ class _Detector:
     chunk = 16                     # stacks per network pass: bounds the workspace and lets uploads overlap compute
     ramp = (4, 12)                 # stacks of the first passes while a clip's frames are still being uploaded
 
-    def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps, ready=None):
+    def _run(self, frames_u8, stack_stride, n_stacks, return_heatmaps, ready=None, heatmaps_to_host=False):
         """frames_u8: (n, H, W, 3) uint8 CUDA.  Returns positions (n_stacks, C, 3) float64 CUDA and heatmaps or None.
+        heatmaps_to_host: the heatmaps come back as ONE pinned host tensor (n_stacks, C, h, w) instead of a CUDA tensor: each pass's
+        maps are copied out on a third stream while the next pass computes (predict() returns 3.6 MB per map to the host, like the
+        reference does; through pageable memory that copy alone cost more than the network).
         `ready`: [(last frame index, event)] from _upload -- a chunk starts as soon as its frames have arrived, so the
         host->device copy of later frames overlaps the network on earlier ones."""
         w, h = self.model.resolution
@@ -217,11 +220,24 @@ class _Detector:
                 p = ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table')
             hm.record_stream(side)
             pos.append(p)
-            if return_heatmaps:
+            if return_heatmaps and heatmaps_to_host:
+                if not hms:                     # pinned blocks come from torch's caching host allocator: no cudaHostAlloc per call
+                    hms.append(torch.empty((n_stacks,) + tuple(hm.shape[1:]), dtype=hm.dtype, pin_memory=True))
+                    if getattr(self, '_d2h_stream', None) is None:
+                        self._d2h_stream = torch.cuda.Stream(device=hm.device)
+                d2h = self._d2h_stream
+                with torch.cuda.stream(d2h):
+                    d2h.wait_event(done)
+                    hms[0][s0:s0 + ns].copy_(hm, non_blocking=True)
+                hm.record_stream(d2h)
+            elif return_heatmaps:
                 hms.append(hm)
         main.wait_stream(side)
         for p in pos:
             p.record_stream(main)
+        if return_heatmaps and heatmaps_to_host:
+            self._d2h_stream.synchronize()
+            return torch.cat(pos), hms[0]
         return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
 
     @staticmethod
@@ -289,10 +305,10 @@ class BallDetector(_Detector):
     def predict(self, images, return_heatmaps=True):
         """images: list (length B) of (prev, curr, next) HWC uint8 BGR frames.
         Returns pred_pos (B, 3) float64 [x, y, 1.0] and the heatmaps (B, 1, h, w) float32 (None if return_heatmaps=False)."""
-        pos, hm = self.predict_device(images, return_heatmaps)
-        return pos.cpu().numpy(), (hm.cpu().numpy() if return_heatmaps else None)
+        pos, hm = self.predict_device(images, return_heatmaps, heatmaps_to_host=True)
+        return pos.cpu().numpy(), (hm.numpy() if return_heatmaps else None)
 
-    def predict_device(self, images, return_heatmaps=False):
+    def predict_device(self, images, return_heatmaps=False, heatmaps_to_host=False):
         """predict() without the device->host copy: positions (B, 3) float64 and heatmaps stay CUDA tensors."""
         flat = [im for triple in images for im in (triple[0], triple[1], triple[2])]
         frames, order, ready = self._upload(flat, self.device)
@@ -305,7 +321,7 @@ class BallDetector(_Detector):
                 torch.cuda.current_stream().wait_event(ready[-1][1])
                 frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
-            pos, hm = self._run(frames, stride, len(images), return_heatmaps, ready)
+            pos, hm = self._run(frames, stride, len(images), return_heatmaps, ready, heatmaps_to_host)
         return pos[:, 0], hm
 
     def filter_trajectory(self, ball_positions, ball_positions_aux, fps):
@@ -326,16 +342,16 @@ class TableDetector(_Detector):
 
     def predict(self, images, return_heatmaps=True):
         """images: list of HWC uint8 BGR frames -> pred_pos (B, 13, 3) float64, heatmaps (B, 1, 13, h, w)."""
-        pos, hm = self.predict_device(images, return_heatmaps)
-        return pos.cpu().numpy(), (hm[:, None].cpu().numpy() if return_heatmaps else None)
+        pos, hm = self.predict_device(images, return_heatmaps, heatmaps_to_host=True)
+        return pos.cpu().numpy(), (hm[:, None].numpy() if return_heatmaps else None)
 
-    def predict_device(self, images, return_heatmaps=False):
+    def predict_device(self, images, return_heatmaps=False, heatmaps_to_host=False):
         frames, order, ready = self._upload(list(images), self.device)
         if order != list(range(len(images))):
             torch.cuda.current_stream().wait_event(ready[-1][1])
             frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
-            pos, hm = self._run(frames, 1, len(images), return_heatmaps, ready)
+            pos, hm = self._run(frames, 1, len(images), return_heatmaps, ready, heatmaps_to_host)
         return pos, hm
 
     def calibrate_camera(self, keypoints):

@@ -175,6 +175,17 @@ def _uplifting_transform(ball_coords, table_coords, times):
     return b, t, ti, m
 
 
+_POOL = None
+
+
+def _staging_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix='ttk-stage')
+    return _POOL
+
+
 # ---- public classes ---------------------------------------------------------------------------------
 class _Detector:
     frames_per_stack = 1
@@ -258,7 +269,12 @@ class _Detector:
         tensor, per input image its row in it, and [(frame index, event)] marking how far the copy has got."""
         slots, order, uniq = {}, [], []
         for im in images:
-            k = id(im)
+            # frames are recognised by their memory, not by the Python object: clip[i] creates a new view object on every indexing,
+            # and a sliding window over a clip names every frame three times
+            if isinstance(im, torch.Tensor):
+                k = (im.data_ptr(), tuple(im.shape), tuple(im.stride()))
+            else:
+                k = (im.__array_interface__['data'][0], im.shape, im.strides)
             if k not in slots:
                 slots[k] = len(uniq)
                 uniq.append(im)
@@ -275,6 +291,16 @@ class _Detector:
         copy_stream = getattr(self, '_copy_stream', None)
         if copy_stream is None:
             copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+        staged = None
+        if not all_torch:
+            # numpy frames (what cv2 delivers): the copies into the pinned staging buffer run on a few host threads (numpy releases the
+            # GIL for them) and frame i is sent as soon as it is staged, so the host memcpy pipelines with the PCIe transfer
+            copy_stream.synchronize()           # an earlier call's transfers have left the staging buffer
+
+            def stage_one(i):
+                u = uniq[i]
+                view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
+            staged = [_staging_pool().submit(stage_one, i) for i in range(len(uniq))]
         copy_stream.wait_stream(torch.cuda.current_stream())
         ready = []
         with torch.cuda.stream(copy_stream):
@@ -282,7 +308,7 @@ class _Detector:
                 if all_torch:
                     out[i].copy_(u, non_blocking=True)
                 else:
-                    view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
+                    staged[i].result()
                     out[i].copy_(self._stage[i], non_blocking=True)
                 if i % 2 == 1 or i == len(uniq) - 1:      # an event every other frame: the first pass (4 stacks) starts after 6 frames
                     ev = torch.cuda.Event()

@@ -24,3 +24,19 @@ def test_unsupported_detector_names_raise():
     from upliftingtabletennis_b200 import interface
     with pytest.raises(NotImplementedError):
         raise interface._unsupported('segformerpp_b2')
+
+
+def test_frame_key_follows_memory_not_objects():
+    """A sliding window over a clip names every frame three times through fresh view objects: they must map to one upload."""
+    import numpy as np
+    import torch
+    from upliftingtabletennis_b200.interface import _Detector
+    clip = np.zeros((5, 4, 6, 3), np.uint8)
+    assert _Detector._frame_key(clip[2]) == _Detector._frame_key(clip[2])
+    assert clip[2] is not clip[2]
+    assert len({_Detector._frame_key(clip[i]) for i in range(5)}) == 5
+    assert _Detector._frame_key(clip[1]) != _Detector._frame_key(clip[1][:, :3])       # a crop is a different frame
+    t = torch.from_numpy(clip)
+    assert _Detector._frame_key(t[3]) == _Detector._frame_key(t[3])
+    triples = [(t[i], t[i + 1], t[i + 2]) for i in range(3)]
+    assert len({_Detector._frame_key(f) for tr in triples for f in tr}) == 5

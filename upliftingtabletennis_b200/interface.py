@@ -252,6 +252,13 @@ class _Detector:
         return torch.cat(pos), (torch.cat(hms) if return_heatmaps else None)
 
     @staticmethod
+    def _frame_key(im):
+        """Identity of a host frame: its memory (address, shape, strides), for numpy arrays and torch CPU tensors alike."""
+        if isinstance(im, torch.Tensor):
+            return (im.data_ptr(), tuple(im.shape), tuple(im.stride()))
+        return (im.__array_interface__['data'][0], tuple(im.shape), tuple(im.strides))
+
+    @staticmethod
     def _pass_plan(n_stacks, chunk, streaming, ramp=(4, 12)):
         """[(first stack, stacks)] of the network passes over a clip: full chunks, except that a clip whose frames are still being
         uploaded starts with two short passes (4, then 12 stacks)."""
@@ -271,10 +278,7 @@ class _Detector:
         for im in images:
             # frames are recognised by their memory, not by the Python object: clip[i] creates a new view object on every indexing,
             # and a sliding window over a clip names every frame three times
-            if isinstance(im, torch.Tensor):
-                k = (im.data_ptr(), tuple(im.shape), tuple(im.stride()))
-            else:
-                k = (im.__array_interface__['data'][0], im.shape, im.strides)
+            k = self._frame_key(im)
             if k not in slots:
                 slots[k] = len(uniq)
                 uniq.append(im)

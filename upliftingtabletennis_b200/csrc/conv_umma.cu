@@ -471,6 +471,8 @@ bool fused_ky(const TtkConv& cv) { return cv.k == 3 && cv.stride == 1 && 3 * cou
 // taller tiles fit: transition1.0 R = 3 -> 8, the 64 -> 64 layers R = 2 -> 4, and the 128 -> 128 layers get a second pipeline stage.
 int kc_of(const TtkConv& cv) {
   if (cv.k == 3 && cv.stride == 1 && cv.cin_p >= 64) return 32;
+  // stride 2 with 64+ input channels (transition1.1 1.74 -> 1.49 ms): two-row tiles and a third pipeline stage in the same shared memory
+  if (cv.k == 3 && cv.stride == 2 && cv.cin_p >= 64) return 32;
   return cv.cin_p < 64 ? cv.cin_p : 64;
 }
 
@@ -653,7 +655,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 8, 2, 0, 32>(cv, a, st);     // transition1.0
   if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 64) return launch<3, 1, 128, 64, 2, 2, 0, 32>(cv, a, st);    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
   // 3x3 stride 2 (transitions and fuse down-paths)
-  TTK_UMMA(3, 2, 128, 32, 1, 2, 0)
+  if (cv.k == 3 && cv.stride == 2 && ci == 128 && co == 32) return launch<3, 2, 128, 32, 2, 3, 0, 32>(cv, a, st);
   TTK_UMMA(3, 2, 16, 16, 4, 3, 0)
   TTK_UMMA(3, 2, 16, 32, 4, 3, 0)
   TTK_UMMA(3, 2, 16, 64, 4, 3, 0)
@@ -661,7 +663,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   TTK_UMMA(3, 2, 32, 32, 4, 2, 0)
   TTK_UMMA(3, 2, 32, 64, 4, 2, 0)
   TTK_UMMA(3, 2, 32, 128, 2, 2, 0)
-  TTK_UMMA(3, 2, 64, 64, 1, 2, 0)     // 64 -> 128 as two output slices
+  if (cv.k == 3 && cv.stride == 2 && ci == 64 && co == 64) return launch<3, 2, 64, 64, 2, 3, 0, 32>(cv, a, st);       // 64 -> 128 as two output slices
   // 1x1
   TTK_UMMA(1, 1, 64, 32, 4, 2, 0)     // bottleneck conv1, fuse 64 -> 32
   TTK_UMMA(1, 1, 32, 128, 2, 3, 1)    // bottleneck conv3 (+ projection shortcut as residual)

@@ -35,6 +35,17 @@ def test_ball_detector_predict(weights, golden):
     # independent (copied) triples take the stride-3 path and give the same answer
     pos2, _ = bd.predict([tuple(f.copy() for f in t) for t in triples], return_heatmaps=False)
     assert np.array_equal(pos, pos2)
+    # a sliding window named through fresh view objects of one clip array (clip[i] is a new object every time) uploads every frame
+    # once, takes the stride-1 path and gives the same answer; pinned torch frames likewise
+    clip = np.stack(frames[:6])
+    windows = [(clip[i - 1], clip[i], clip[i + 1]) for i in range(1, 5)]
+    up, order, _ = bd._upload([f for t in windows for f in t], bd.device)
+    assert up.shape[0] == 6 and order == [i + j for i in range(4) for j in range(3)]
+    pos3, hm3 = bd.predict(windows)
+    assert np.array_equal(pos, pos3) and np.array_equal(hm, hm3)
+    tclip = torch.from_numpy(clip).pin_memory()
+    pos4, _ = bd.predict([(tclip[i - 1], tclip[i], tclip[i + 1]) for i in range(1, 5)], return_heatmaps=False)
+    assert np.array_equal(pos, pos4)
     # the transform seam works on the reference's dicts (HWC float64 out)
     out = bd.transform({'image': frames[1], 'prev_image': frames[0], 'next_image': frames[2]})
     assert out['image'].shape == (88, 160, 3) and out['image'].dtype == np.float64

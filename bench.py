@@ -139,13 +139,75 @@ def cpu_reference_step(wasb_sd, frames, n_stacks):
     return time.perf_counter() - t0
 
 
+def gpu_eager_baseline(dev, steps=3, warmup=2, wasb_sub=8, uplift_batch=4096):
+    """SURVEY.md section 2a's bar: stock PyTorch eager on the SAME B200 for the two network stages, i.e. what the reference's
+    code does on a GPU (cuDNN convolutions + ATen batch norm / ReLU / add kernels, cuBLAS + SDPA for the transformer).  The
+    reference's modules cannot travel to the GPU box, so the functional restatement in oracle/ is moved to CUDA as it is --
+    same F.conv2d / F.batch_norm / F.linear / F.scaled_dot_product_attention calls.  Modes: torch defaults (cuDNN TF32 on,
+    matmul fp32), strict fp32 (TF32 off), and bf16 channels-last / bf16 autocast-free weights."""
+    from oracle import hrnet as ohr, uplift as oup
+    from upliftingtabletennis_b200 import synthetic
+    out = {}
+
+    def timed(fn, n_units):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return n_units * steps / (e0.elapsed_time(e1) * 1e-3)
+
+    sd = {k: v.to(dev) for k, v in synthetic.hrnet_state_dict(ohr.state_dict_layout(9, 3), seed=1).items()}
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn((wasb_sub, 9, RES[1], RES[0]), device=dev, generator=g)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        wasb = {}
+        torch.backends.cudnn.allow_tf32 = True
+        wasb['tf32_default'] = timed(lambda: ohr.wasb_forward(sd, x), wasb_sub)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        wasb['tf32_channels_last'] = timed(lambda: ohr.wasb_forward(sd, xcl), wasb_sub)
+        torch.backends.cudnn.allow_tf32 = False
+        wasb['fp32_strict'] = timed(lambda: ohr.wasb_forward(sd, x), wasb_sub)
+        torch.backends.cudnn.allow_tf32 = True
+        sd16 = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in sd.items()}
+        x16 = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        wasb['bf16_channels_last'] = timed(lambda: ohr.wasb_forward(sd16, x16), wasb_sub)
+        out['wasb_forward'] = {'unit': 'stacks/s', 'sub_batch': wasb_sub, **wasb,
+                               'note': 'network only (no resize / decode), %dx%d input, cudnn.benchmark on' % RES}
+        del sd16, x16, xcl, x
+        usd = {k: v.to(dev) for k, v in oup.random_state_dict(3).items()}
+        ua = [torch.from_numpy(a).to(dev) for a in synthetic.trajectories(uplift_batch, seed=7)]
+        up = {}
+        for b in (512, uplift_batch):
+            ub = [a[:b] for a in ua]
+            up['fp32_sdpa_b%d' % b] = timed(lambda: oup.uplift_forward(usd, *ub, sdpa=True), b)
+        usd16 = {k: v.to(torch.bfloat16) for k, v in usd.items()}
+        ub16 = [a.to(torch.bfloat16) for a in ua]
+        try:
+            up['bf16_sdpa_b%d' % uplift_batch] = timed(lambda: oup.uplift_forward(usd16, *ub16, sdpa=True), uplift_batch)
+        except Exception as e:      # noqa: BLE001 - report, the leg is informative only
+            up['bf16_sdpa_error'] = str(e)[:200]
+        out['uplift_forward'] = {'unit': 'trajectories/s', **up, 'note': 'cuBLAS + SDPA + ATen elementwise, matmul TF32 off (torch default)'}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    # this arm must not map the product library: weights layout from the oracle, synthetic inputs from the pure-numpy generators
+    from oracle import hrnet as ohr
     from upliftingtabletennis_b200 import synthetic
-    from upliftingtabletennis_b200.detector import HRNetEngine
     torch.set_num_threads(os.cpu_count())
-    sd = synthetic.hrnet_state_dict(HRNetEngine(9, 3, 1, 1).state_dict_layout(), seed=1)
+    sd = synthetic.hrnet_state_dict(ohr.state_dict_layout(9, 3), seed=1)
     per_step = 2
     frames = synthetic.frames_1080p(per_step + 2, seed=100)
     for _ in range(args.warmup):

@@ -1,5 +1,5 @@
 """torch.hub entry points -- same names, defaults and `dependencies` contract as the reference's hubconf.py:1-34."""
-dependencies = ['torch', 'numpy', 'scipy', 'sklearn']
+dependencies = ['torch', 'numpy']      # the reference also lists scipy / sklearn / cv2 / ...: their arithmetic runs in libttk here
 
 import os
 import sys
@@ -14,19 +14,21 @@ IMAGES_ZIP_URL = "https://mediastore.rz.uni-augsburg.de/get/51XbRH38ZY/"
 IMAGES_ZIP_FILENAME = "example_images.zip"
 
 
-def ball_detection(model_name='segformerpp_b2', **kwargs):
-    """Loads the Ball Detection Model.  B200 kernels exist for 'wasb' and 'vitpose' (see DESIGN.md for the segformer++ status)."""
-    return BallDetector(model_name=model_name)
+def ball_detection(model_name='segformerpp_b2', dtype=None, **kwargs):
+    """Loads the Ball Detection Model.  B200 kernels exist for 'wasb' and 'vitpose'; the reference's default name is kept, but
+    segformer++ is not part of the reference repository and raises NotImplementedError before anything is downloaded.
+    dtype: 'tf32' (WASB default: tensor cores at the precision class of the reference's cuDNN convolutions), 'fp32', 'bf16'."""
+    return BallDetector(model_name=model_name, dtype=dtype)
 
 
-def table_detection(model_name='segformerpp_b2', **kwargs):
+def table_detection(model_name='segformerpp_b2', dtype=None, **kwargs):
     """Loads the Table Detection Model.  B200 kernels exist for 'hrnet' and 'vitpose'."""
-    return TableDetector(model_name=model_name)
+    return TableDetector(model_name=model_name, dtype=dtype)
 
 
-def full_pipeline():
-    """Loads the End-to-End Pipeline (Ball + Table + Uplifting)."""
-    return TableTennisPipeline()
+def full_pipeline(dtype=None, **kwargs):
+    """Loads the End-to-End Pipeline (Ball + Table + Uplifting).  kwargs: ball_model / ball_model_aux / table_model / table_model_aux."""
+    return TableTennisPipeline(dtype=dtype, **kwargs)
 
 
 def download_example_images(local_folder='example_images'):

@@ -27,7 +27,9 @@ extern "C" {
 #define TTK_API __attribute__((visibility("default")))
 
 enum { TTK_OK = 0, TTK_ERR_ARG = -1, TTK_ERR_CUDA = -2, TTK_ERR_STATE = -3, TTK_ERR_UNSUPPORTED = -4 };
-enum { TTK_F32 = 0, TTK_BF16 = 1 };                 /* arithmetic/storage type of a path */
+/* Arithmetic / storage type of a path.  TTK_TF32: fp32 storage, tensor-core products with TF32 operands (inputs rounded to
+ * nearest-even TF32 by TMA, fp32 accumulate) -- the class cuDNN uses for the reference's convolutions on a GPU. */
+enum { TTK_F32 = 0, TTK_BF16 = 1, TTK_TF32 = 2 };
 enum { TTK_DECODE_TABLE = 0, TTK_DECODE_BALL = 1 }; /* the two live sub-pixel variants */
 enum { TTK_LAYOUT_NCHW_F32 = 0, TTK_LAYOUT_NHWC16 = 1 };
 
@@ -78,7 +80,9 @@ TTK_API int ttk_hrnet_set_conv(ttk_hrnet* h, int i, const float* w_host, const f
 TTK_API size_t ttk_hrnet_workspace_bytes(const ttk_hrnet* h, int batch, int height, int width, int dtype);
 /* x_dev: batch x H x W x 16 (NHWC16, dtype); heatmaps_dev: batch x out_count x H x W float32.
  * H and W must be multiples of 8.  dtype TTK_F32: fp32 SIMT path (parity with the CPU
- * reference); TTK_BF16: tcgen05 tensor-core path (bf16 storage, fp32 accumulate). */
+ * reference at 1e-4); TTK_TF32: x and the activations are float32, the convolutions run on the
+ * tcgen05 tensor cores with TF32 operands (the reference-on-GPU class, balldetection/models/wasb.py:29-105
+ * through cuDNN's default TF32); TTK_BF16: tcgen05 path with bf16 storage, fp32 accumulate. */
 TTK_API int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int height, int width, int dtype,
                       float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* kernels launched by the last ttk_hrnet_forward on this handle (for bench accounting) */
@@ -93,7 +97,8 @@ TTK_API int ttk_hrnet_set_subbatch(ttk_hrnet* h, int images);
  * (inputs + outputs + weights once). */
 TTK_API int ttk_hrnet_set_force_simt(ttk_hrnet* h, int enable);   /* bf16 path through the SIMT kernels (cross-check of the tcgen05 path) */
 /* Test hook: run one convolution of the plan on caller buffers (NHWC, channels padded to 16): out = act(conv(in) + bias [+ res]).
- * path 0: fp32 SIMT (float32 tensors), 1: bf16 SIMT, 2: bf16 tcgen05 (TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel). */
+ * path 0: fp32 SIMT (float32 tensors), 1: bf16 SIMT, 2: bf16 tcgen05, 3: TF32 tcgen05 on float32 tensors (2 / 3 return
+ * TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel). */
 TTK_API int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, const void* res_dev,
                          int relu, int path, void* out_dev, void* stream);
 /* Test hook: one BasicBlock (convs conv_index and conv_index + 1, 16 or 32 padded channels) through the fused tcgen05 kernel:

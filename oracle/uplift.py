@@ -110,7 +110,7 @@ def rope(x, times, inv_freq):
     return out
 
 
-def attention(sd, p, x, mask, times, num_cls, heads):
+def attention(sd, p, x, mask, times, num_cls, heads, sdpa=False):
     B, N, C = x.shape
     hd = C // heads
     qkv = F.linear(x, sd[p + 'attn.qkv.weight'], sd[p + 'attn.qkv.bias'])
@@ -119,6 +119,9 @@ def attention(sd, p, x, mask, times, num_cls, heads):
     inv = sd[p + 'attn.rotary_emb.inv_freq']
     q = torch.cat((q[:, :, :num_cls], rope(q[:, :, num_cls:], times, inv)), dim=2)
     k = torch.cat((k[:, :, :num_cls], rope(k[:, :, num_cls:], times, inv)), dim=2)
+    if sdpa:      # the reference's own call (model.py:218-224); used by bench.py's stock-PyTorch-on-GPU leg
+        o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask[:, None, None, :] + mask[:, None, :, None])
+        return F.linear(o.transpose(1, 2).reshape(B, N, C), sd[p + 'attn.proj.weight'])
     s = (q @ k.transpose(-2, -1)) / math.sqrt(hd)
     s = s + (mask[:, None, None, :] + mask[:, None, :, None])
     m = s.max(dim=-1, keepdim=True).values
@@ -130,10 +133,10 @@ def attention(sd, p, x, mask, times, num_cls, heads):
     return F.linear(o, sd[p + 'attn.proj.weight'])
 
 
-def layer(sd, p, x, mask, times, num_cls, heads):
+def layer(sd, p, x, mask, times, num_cls, heads, sdpa=False):
     C = x.shape[-1]
     h = F.layer_norm(x, (C,), sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], 1e-5)
-    x = attention(sd, p, h, mask, times, num_cls, heads) + x
+    x = attention(sd, p, h, mask, times, num_cls, heads, sdpa) + x
     h = F.layer_norm(x, (C,), sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], 1e-5)
     h = F.linear(F.relu(F.linear(h, sd[p + 'mlp1.fc1.weight'], sd[p + 'mlp1.fc1.bias'])),
                  sd[p + 'mlp1.fc2.weight'], sd[p + 'mlp1.fc2.bias'])
@@ -153,37 +156,37 @@ def head(sd, p, x):
 def check_mask(mask):
     """model.py:541-546: {0,1} masks only (an all-ones or all-zeros mask raises like the reference)."""
     if mask.min() == 0 and mask.max() == 1:
-        return torch.where(mask == 0, torch.tensor(float('-inf')), torch.tensor(0.0))
+        return torch.where(mask == 0, float('-inf'), 0.0).to(mask.dtype)
     if mask.max() == 0 and mask.min() < -1e8:
         return mask
     raise ValueError('wrong format for masks. Should be 0, 1 or -1e9, 0.')
 
 
-def uplift_forward(sd, ball, table, mask, times, size='large', use_skipconnection=True):
+def uplift_forward(sd, ball, table, mask, times, size='large', use_skipconnection=True, sdpa=False):
     """ball (B,T,2), table (B,13,3), mask (B,T) in {0,1}, times (B,T) -> rot (B,3), pos (B,T,3)."""
     dim, depth, heads = SIZES[size]
     with torch.no_grad():
         B, T, _ = ball.shape
         mask = check_mask(mask)
         x = mlp2(sd, 'firststage.ball_embed', ball)                                   # (B,T,D)
-        tmask = torch.where(table[:, :, 2] == 1, 0.0, float('-inf'))
-        tmask = torch.cat((torch.zeros(B, 1), tmask), dim=1)                            # (B,14)
+        tmask = torch.where(table[:, :, 2] == 1, 0.0, float('-inf')).to(table.dtype)
+        tmask = torch.cat((table.new_zeros(B, 1), tmask), dim=1)                           # (B,14)
         tmask = tmask[:, None, :].expand(B, T, NUM_TABLE + 1).reshape(B * T, NUM_TABLE + 1)
-        ttimes = torch.arange(NUM_TABLE, dtype=table.dtype) / (MAX_FPS / 5)
+        ttimes = torch.arange(NUM_TABLE, dtype=table.dtype, device=table.device) / (MAX_FPS / 5)
         ttimes = ttimes[None, :].expand(B * T, NUM_TABLE)
         tab = mlp2(sd, 'firststage.table_embed', table[..., :2])                      # (B,13,D)
         seq = torch.cat((x[:, :, None, :], tab[:, None, :, :].expand(B, T, NUM_TABLE, dim)), dim=2)
         seq = seq.reshape(B * T, NUM_TABLE + 1, dim)
         for i in range(4):
-            seq = layer(sd, 'firststage.pos_layers.%d.' % i, seq, tmask, ttimes, 1, heads)
+            seq = layer(sd, 'firststage.pos_layers.%d.' % i, seq, tmask, ttimes, 1, heads, sdpa)
         x = seq.reshape(B, T, NUM_TABLE + 1, dim)[:, :, 0, :]
         for i in range(depth - 4):
-            x = layer(sd, 'firststage.layers.%d.' % i, x, mask, times, 0, heads)
+            x = layer(sd, 'firststage.layers.%d.' % i, x, mask, times, 0, heads, sdpa)
         pos = head(sd, 'firststage.position_head', x)
         y = x if use_skipconnection else mlp2(sd, 'embed', pos)
         y = torch.cat((sd['cls_token'].expand(B, 1, dim), y), dim=1)
-        mask2 = torch.cat((torch.zeros(B, 1), mask), dim=1)
+        mask2 = torch.cat((mask.new_zeros(B, 1), mask), dim=1)
         for i in range(4):
-            y = layer(sd, 'secondstage.%d.' % i, y, mask2, times, 1, heads)
+            y = layer(sd, 'secondstage.%d.' % i, y, mask2, times, 1, heads, sdpa)
         rot = head(sd, 'rotation_head', y[:, 0, :])
         return rot, pos

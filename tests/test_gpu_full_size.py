@@ -126,8 +126,8 @@ def test_full_pipeline_1080p_rally(dev, tmp_path):
               'randdet_prob': 0.0, 'randmiss_prob': 0.0, 'tablemiss_prob': 0.0})):
         os.makedirs(os.path.join(w, sub), exist_ok=True)
         torch.save({'model_state_dict': sd, 'identifier': 'synthetic', 'additional_info': info}, os.path.join(w, sub, 'model.pt'))
-    pipe = TableTennisPipeline()
-    pipe.ball_detector_aux, pipe.table_detector_aux = BallDetector('wasb'), TableDetector('hrnet')
+    pipe = TableTennisPipeline(ball_model='wasb', ball_model_aux='wasb', table_model='hrnet', table_model_aux='hrnet')
+    assert pipe.ball_detector is not pipe.ball_detector_aux and pipe.ball_detector.model.compute_dtype == 'tf32'
     frames = list(synthetic.frames_1080p(50, seed=9))
     spin, pos3d = pipe.predict(frames, 50.0)
     assert spin.shape == (3,) and pos3d.shape == (48, 3)

@@ -24,7 +24,7 @@ def test_ball_detector_predict(weights, golden):
     from upliftingtabletennis_b200.interface import BallDetector
     g = golden('interface')
     frames = list(g['frames'])
-    bd = BallDetector('wasb')
+    bd = BallDetector('wasb', dtype='fp32')          # strict parity path; the default ('tf32') is checked below and in test_gpu_output_parity.py
     assert isinstance(bd.model, torch.nn.Module) and not bd.model.training and bd.resolution == (1920, 1080)
     triples = [(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 5)]
     pos, hm = bd.predict(triples)
@@ -49,6 +49,11 @@ def test_ball_detector_predict(weights, golden):
     # the transform seam works on the reference's dicts (HWC float64 out)
     out = bd.transform({'image': frames[1], 'prev_image': frames[0], 'next_image': frames[2]})
     assert out['image'].shape == (88, 160, 3) and out['image'].dtype == np.float64
+    # the default arithmetic class is the TF32 tensor-core path: same API, heatmaps inside the stated TF32 bound of the reference's
+    bd_tf = BallDetector('wasb')
+    assert bd_tf.model.compute_dtype == 'tf32' and BallDetector('wasb', dtype=torch.bfloat16).model.compute_dtype == 'bf16'
+    pos_tf, hm_tf = bd_tf.predict(triples)
+    assert hm_tf.dtype == np.float32 and np.abs(hm_tf - g['ball_hm']).max() <= 1e-2 * np.abs(g['ball_hm']).max()
     p1 = np.array([[10.0, 10, 1], [50, 50, 1], [90, 90, 1]])
     p2 = np.array([[12.0, 11, 1], [90, 50, 1], [90, 91, 0]])
     f, idx, t = bd.filter_trajectory(p1, p2, 50)
@@ -59,7 +64,7 @@ def test_table_detector_predict(weights, golden):
     from upliftingtabletennis_b200.interface import TableDetector
     g = golden('interface')
     frames = list(g['frames'])
-    td = TableDetector('hrnet')
+    td = TableDetector('hrnet', dtype='fp32')
     pos, hm = td.predict(frames[:2])
     assert pos.shape == (2, 13, 3) and hm.shape == (2, 1, 13, 88, 160)
     np.testing.assert_allclose(hm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
@@ -75,12 +80,12 @@ def test_vitpose_detectors_predict(weights, golden):
     write_vitpose_checkpoints(weights)
     g = golden('interface_vitpose')
     frames = list(g['frames'])
-    bd = hubconf.ball_detection('vitpose')
+    bd = hubconf.ball_detection('vitpose', dtype='fp32')
     pos, hm = bd.predict([(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 4)])
     assert hm.shape == g['ball_hm'].shape and hm.dtype == np.float32 and pos.shape == (3, 3)
     np.testing.assert_allclose(hm, g['ball_hm'], rtol=0, atol=1e-4 * np.abs(g['ball_hm']).max() + 1e-5)
     np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=1e-3)
-    td = hubconf.table_detection('vitpose')
+    td = hubconf.table_detection('vitpose', dtype='fp32')
     tpos, thm = td.predict(frames[:2])
     assert thm.shape == g['table_hm'].shape
     np.testing.assert_allclose(thm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
@@ -107,7 +112,9 @@ def test_full_pipeline_runs(weights, golden):
     from upliftingtabletennis_b200.interface import TableTennisPipeline
     g = golden('interface')
     frames = list(g['frames'])
-    pipe = TableTennisPipeline()
+    # main and auxiliary detectors from the same checkpoints (random-init detectors of different architectures never agree)
+    pipe = TableTennisPipeline(ball_model='wasb', ball_model_aux='wasb', table_model='hrnet', table_model_aux='hrnet', dtype='fp32')
+    assert pipe.ball_detector is not pipe.ball_detector_aux and pipe.table_detector is not pipe.table_detector_aux
     spin, pos3d = pipe.predict(frames, 50.0)
     # oracle chain
     sd_b, sd_t, sd_u = ohr.random_state_dict(9, 3, seed=31), ohr.random_state_dict(3, 13, seed=32), oup.random_state_dict(33)

@@ -140,7 +140,7 @@ def _heat_tol(ref):
 def test_wasb_fp32_golden(dev, golden):
     from upliftingtabletennis_b200.detector import WASBNet
     g = golden('hrnet')
-    m = WASBNet().to(dev).eval()
+    m = WASBNet(dtype='fp32').to(dev).eval()
     m.load_state_dict(ohr.random_state_dict(9, 3, seed=int(g['wasb_seed'])))
     y, none = m(torch.from_numpy(g['wasb_x']).to(dev))
     assert none is None and y.shape == (2, 1, 64, 96)
@@ -150,7 +150,7 @@ def test_wasb_fp32_golden(dev, golden):
 def test_table_hrnet_fp32_golden(dev, golden):
     from upliftingtabletennis_b200.detector import MyHRNet
     g = golden('hrnet')
-    m = MyHRNet().to(dev).eval()
+    m = MyHRNet(dtype='fp32').to(dev).eval()
     m.load_state_dict(ohr.random_state_dict(3, 13, seed=int(g['table_seed'])))
     y = m(torch.from_numpy(g['table_x']).to(dev))
     assert y.shape == (1, 13, 64, 96)
@@ -165,7 +165,7 @@ def test_wasb_fp32_vs_oracle_shapes(dev, shape):
     sd = ohr.random_state_dict(9, 3, seed=77)
     x = rng.standard_normal((B, 9, H, W)).astype(np.float32)
     ref = ohr.wasb_forward(sd, torch.from_numpy(x)).numpy()
-    m = WASBNet().to(dev).eval()
+    m = WASBNet(dtype='fp32').to(dev).eval()
     m.load_state_dict(sd)
     y, _ = m(torch.from_numpy(x).to(dev))
     np.testing.assert_allclose(y.cpu().numpy(), ref, rtol=0, atol=_heat_tol(ref))

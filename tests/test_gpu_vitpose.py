@@ -26,12 +26,12 @@ def close(y, ref, rel=1e-4):
 def test_vitpose_fp32_golden(dev, golden):
     from upliftingtabletennis_b200.vitpose import TableVitPose, VitPose
     g = golden('vitpose')
-    m = VitPose(in_frames=3, model_size='small', resolution=(96, 64)).to(dev).eval()
+    m = VitPose(in_frames=3, model_size='small', resolution=(96, 64), dtype='fp32').to(dev).eval()
     m.load_state_dict(ov.random_state_dict(int(g['ball_seed']), 9, 24, 1), strict=True)
     y, none = m(torch.from_numpy(g['ball_x']).to(dev))
     assert none is None and tuple(y.shape) == g['ball_y'].shape
     close(y.cpu().numpy(), g['ball_y'])
-    t = TableVitPose(model_size='small', resolution=(96, 64)).to(dev).eval()
+    t = TableVitPose(model_size='small', resolution=(96, 64), dtype='fp32').to(dev).eval()
     t.load_state_dict(ov.random_state_dict(int(g['table_seed']), 3, 24, 13), strict=True)
     yt = t(torch.from_numpy(g['table_x']).to(dev))
     close(yt.cpu().numpy(), g['table_y'])
@@ -43,7 +43,7 @@ def test_vitpose_fp32_vs_oracle(dev, res, batch):
     from upliftingtabletennis_b200.vitpose import VitPose
     hp, wp = ov.tokens_hw(res[1], res[0])
     sd = ov.random_state_dict(7, 9, hp * wp, 1)
-    m = VitPose(in_frames=3, resolution=res).to(dev).eval()
+    m = VitPose(in_frames=3, resolution=res, dtype='fp32').to(dev).eval()
     m.load_state_dict(sd, strict=True)
     x = np.random.default_rng(1).standard_normal((batch, 9, res[1], res[0])).astype(np.float32)
     y, _ = m(torch.from_numpy(x).to(dev))
@@ -147,7 +147,7 @@ def test_vitpose_bf16_bound(dev, golden):
     for res, batch in (((96, 64), 2), ((1152, 640), 1)):
         hp, wp = ov.tokens_hw(res[1], res[0])
         sd = ov.random_state_dict(7, 9, hp * wp, 1)
-        m = VitPose(in_frames=3, resolution=res).to(dev).eval()
+        m = VitPose(in_frames=3, resolution=res, dtype='fp32').to(dev).eval()
         m.load_state_dict(sd, strict=True)
         x = np.random.default_rng(1).standard_normal((batch, 9, res[1], res[0])).astype(np.float32)
         y32, _ = m(torch.from_numpy(x).to(dev))

@@ -26,16 +26,6 @@ using namespace umma;
 constexpr int BW = 128, WO = 126, TW = 130, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-  const uint32_t z = 0;
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
-}
 
 template <int C, int R, int SLOTS>
 struct BCfg {
@@ -83,18 +73,6 @@ __device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint3
         mma(d, make_desc(arow + k16 * 32, 8 * ROWB, LAYOUT), make_desc(brow + k16 * 32, 8 * ROWB, LAYOUT), idesc, 1u);
     }
   }
-}
-
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 
 // Tiles of a CTA are numbered t = 0, 1, 2, ... in the order it takes them; tile t lives in input buffer t % NX and in slot t % SLOTS

@@ -1,12 +1,19 @@
-// bf16 implicit-GEMM convolution (3x3 stride 1/2, 1x1) on the 5th-generation tensor cores:
+// Implicit-GEMM convolution (3x3 stride 1/2, 1x1) on the 5th-generation tensor cores:
 // tcgen05.mma with TMEM accumulators, operands staged by TMA, fused bias / residual / ReLU epilogue.
+// Two arithmetic classes share the kernel (template parameter ESZ = bytes per activation element):
+//   ESZ 2: bf16 activations and weights, kind::f16;
+//   ESZ 4: fp32 activations in HBM, kind::tf32 -- the class cuDNN uses for the reference's convolutions on a GPU (torch enables
+//          TF32 for cuDNN by default).  The tensor map of the input has data type TFLOAT32, so TMA rounds every element to TF32
+//          (nearest-even) on its way into shared memory; the weights are rounded once on the host; kind::tf32 ignores the low 13
+//          mantissa bits, which are zero by then (tools/tf32_probe.cu, profiles/r02_tf32_probe.log).  Accumulation, bias,
+//          residual adds and ReLU are fp32, and the stored activations are full fp32 like the reference's.
 // Reference ops: the Conv2d + BatchNorm2d(eval) + ReLU (+ residual / fuse sum) groups of
 // balldetection/models/wasb.py:35-105, :179-245, :383-416.
 //
 // Mapping (NHWC bf16 activations):
 //   M = 128 consecutive output pixels of one image row, N = Cout (or a 64-wide slice of it), K = taps x Cin.
 //   A CTA tile is R output rows x 128 pixels.  ONE TMA box brings the (R+2) x 130 pixel halo of a
-//   K-chunk (<= 64 channels = one swizzled row of 32/64/128 bytes per pixel) into shared memory;
+//   K-chunk (<= 128 bytes of channels = one swizzled row of 32/64/128 bytes per pixel) into shared memory;
 //   the 9 taps are NOT re-loaded: tap (ky,kx) of output row r is the same staged tile with the
 //   matrix descriptor's start address moved by ((r+ky)*130 + kx) pixel rows.  tools/umma_probe.cu
 //   established on a B200 that the 32/64/128-byte swizzles are applied to absolute shared-memory
@@ -25,89 +32,20 @@
 // Pipelines: smem full/empty ring over load units, double-buffered TMEM accumulators (tmem full/empty).
 #include <cuda.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
 #include "hrnet.h"
+#include "umma_prims.h"
 
 namespace {
 
+using namespace umma;
+
 constexpr int BW = 128;          // output pixels per tile row = MMA M
 constexpr int THREADS = 192;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n\t"
-      "@p bra LAB_DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "LAB_DONE:\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO | SBO | version 1 | layout
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                                   // LBO (ignored for swizzled K-major layouts)
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(layout & 7) << 61;
-  return d;
-}
-// kind::f16 instruction descriptor: D f32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
-
-// 256-bit read-only load: the 16 bf16 channels of one pixel (one 32-byte sector)
-__device__ __forceinline__ void ldg256(const void* p, uint4& lo, uint4& hi) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
-               : "l"(p));
-}
-
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
-  const uint32_t z = 0;
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
-}
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
@@ -116,11 +54,13 @@ constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 // (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth;
 // RB: reserve shared memory for TMA-staged residual tiles (double buffered with the accumulators);
 // KCO: channels per K-chunk when not the default (a narrower chunk buys a taller tile for the same shared memory).
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
 struct Cfg {
-  static constexpr int KC = KCO ? KCO : (CIN < 64 ? CIN : 64);      // channels per K-chunk = one swizzled smem row
+  static constexpr int KCMAX = 128 / ESZ;                           // a swizzled smem row holds at most 128 bytes
+  static constexpr int KC = KCO ? KCO : (CIN < KCMAX ? CIN : KCMAX);      // channels per K-chunk = one swizzled smem row
   static constexpr int NKC = CIN / KC;
-  static constexpr int ROWB = KC * 2;
+  static constexpr int ROWB = KC * ESZ;
+  static constexpr int KSTEPS = ROWB / 32;                          // MMAs per row: K = 16 bf16 or 8 tf32 = 32 bytes each
   static constexpr int PAD = KS / 2;
   static constexpr bool FUSE = KS == 3 && S == 1 && 3 * COUT <= 256;   // vertical tap fusion
   static constexpr int NPY = S == 2 ? 2 : 1;            // row-parity units per K-chunk
@@ -136,10 +76,10 @@ struct Cfg {
   static constexpr int W_BYTES_AL = al1024(W_BYTES);
   static constexpr int ACC_COLS = R * COUT;
   static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
-  // residual staging: boxes of CB channels (<= 64 = 128 swizzled bytes per pixel) x 128 px x R rows
-  static constexpr int CB = COUT < 64 ? COUT : 64;
+  // residual staging: boxes of CB channels (<= 128 swizzled bytes per pixel) x 128 px x R rows
+  static constexpr int CB = COUT < KCMAX ? COUT : KCMAX;
   static constexpr int NRB = COUT / CB;
-  static constexpr int RROWB = CB * 2;
+  static constexpr int RROWB = CB * ESZ;
   static constexpr int RBOX_BYTES = R * BW * RROWB;     // multiple of 1024
   static constexpr int RES_BYTES = RB ? 2 * NRB * RBOX_BYTES : 0;
   static constexpr uint32_t RSWZ = RROWB == 32 ? 1u : RROWB == 64 ? 3u : 7u;
@@ -148,7 +88,10 @@ struct Cfg {
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
-  static_assert(ACC_COLS < 64 || ACC_COLS % 64 == 0, "the epilogue drains whole groups of 64 accumulator columns");
+  static constexpr int GCOLS = ACC_COLS < (ESZ == 2 ? 64 : 32) ? ACC_COLS : (ESZ == 2 ? 64 : 32);     // accumulator columns fetched per TMEM wait
+  static_assert(ESZ == 2 || ESZ == 4, "bf16 or tf32-in-fp32 elements");
+  static_assert(ACC_COLS % GCOLS == 0, "the epilogue drains whole groups of accumulator columns");
+  static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "a K-chunk is one 32/64/128-byte swizzled row");
   static_assert(COUT % 16 == 0 && COUT <= 256 && CIN % 16 == 0, "bad channel counts");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -159,22 +102,22 @@ struct KMaps {
 };
 
 struct KArgs {
-  const __nv_bfloat16* w;      // packed weights, see ttk_conv_umma_pack
+  const void* w;               // packed weights, see ttk_conv_umma_pack
   const float* bias;
-  __nv_bfloat16* out;
-  const __nv_bfloat16* res[3];
+  void* out;
+  const void* res[3];
   int rsh[3];
   int nres;
   int res_tma;                 // res[0] (shift 0) arrives through shared memory
-  int dual;                    // 1x1 only: K-chunk kc is read from tensor map m[kc] (two concatenated inputs)
+  int dual;                    // 1x1 only, two K-concatenated inputs: the first `dual` K-chunks come from tensor map m[0], the rest from m[1]
   int n, h, w_img, cout_total;
   int relu;
   int tiles_x, tiles_y, total;
 };
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
 __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO>;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
@@ -213,14 +156,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // weights: generic-proxy writes -> async proxy (tensor core)
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(C::TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
+  fence_async_smem();              // weights: generic-proxy writes -> async proxy (tensor core)
+  if (warp == 2) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);
+  fence_before();
   __syncthreads();
-  tc_fence_after();
+  fence_after();
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
@@ -236,8 +176,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           mbar_expect_tx(bar_full + 8 * s, C::NBOX * C::BOX_BYTES);
           const uint32_t dst = smem_u32(sA + s * C::STAGE_BYTES);
           if (S == 1) {
-            if (KS == 1 && a.dual)
-              tma_load_4d(dst, &maps.m[kc], bar_full + 8 * s, 0, tx * BW, ty * R, img);     // channels beyond the tensor are zero filled
+            if (KS == 1 && a.dual)     // channels beyond the first tensor are zero filled
+              tma_load_4d(dst, &maps.m[kc < a.dual ? 0 : 1], bar_full + 8 * s, (kc < a.dual ? kc : kc - a.dual) * C::KC, tx * BW, ty * R, img);
             else
               tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
           } else {
@@ -262,17 +202,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t wbase = smem_u32(sW);
+      auto issue = [](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc) {      // every MMA accumulates (the epilogue zeroes what it drains)
+        if (ESZ == 2) mma(d, da, db, idesc, 1u);
+        else mma_tf32(d, da, db, idesc, 1u);
+      };
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph);      // accumulators drained and zeroed by the epilogue
-        tc_fence_after();
+        fence_after();
         const uint32_t d_acc = tmem + acc * C::ACC_COLS;
         for (int u = 0; u < C::UNITS; ++u, ++it) {
           const int kc = u / C::NPY, py = u % C::NPY;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
+          fence_after();
           const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES);
           if (C::FUSE) {
             // input (halo) row hr = yi + 1 feeds output rows yo = yi + 1 - ky; row yo lives in column block R-1-yo
@@ -281,19 +225,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               const int yi = hr - 1;
               const int k0 = yi + 2 - R > 0 ? yi + 2 - R : 0;
               const int k1 = yi + 1 < 2 ? yi + 1 : 2;
-              const uint32_t idesc = make_idesc(128, (k1 - k0 + 1) * COUT);
+              const uint32_t idesc = ESZ == 2 ? make_idesc(128, (k1 - k0 + 1) * COUT) : make_idesc_tf32(128, (k1 - k0 + 1) * COUT);
               const uint32_t d_tmem = d_acc + (R - 2 - yi + k0) * COUT;
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
                 const uint32_t arow = abase + (hr * C::TW + kx) * C::ROWB;
                 const uint32_t brow = wbase + (((kc * 3 + kx) * 3 + k0) * COUT) * C::ROWB;
 #pragma unroll
-                for (int k16 = 0; k16 < C::KC / 16; ++k16)
-                  umma(d_tmem, make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT), idesc, 1u);
+                for (int ks = 0; ks < C::KSTEPS; ++ks)
+                  issue(d_tmem, make_desc(arow + ks * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + ks * 32, 8 * C::ROWB, C::LAYOUT), idesc);
               }
             }
           } else {
-            constexpr uint32_t idesc = make_idesc(128, COUT);
+            constexpr uint32_t idesc = ESZ == 2 ? make_idesc(128, COUT) : make_idesc_tf32(128, COUT);
 #pragma unroll 1
             for (int r = 0; r < R; ++r) {
               const uint32_t d_tmem = d_acc + (R - 1 - r) * COUT;
@@ -310,32 +254,46 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 }
                 const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
 #pragma unroll
-                for (int k16 = 0; k16 < C::KC / 16; ++k16)
-                  umma(d_tmem, make_desc(arow + k16 * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + k16 * 32, 8 * C::ROWB, C::LAYOUT), idesc, 1u);
+                for (int ks = 0; ks < C::KSTEPS; ++ks)
+                  issue(d_tmem, make_desc(arow + ks * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + ks * 32, 8 * C::ROWB, C::LAYOUT), idesc);
               }
             }
           }
-          umma_commit(bar_empty + 8 * s);          // smem stage reusable once these MMAs have read it
+          commit(bar_empty + 8 * s);          // smem stage reusable once these MMAs have read it
         }
-        umma_commit(bar_tfull + 8 * acc);          // accumulators complete
+        commit(bar_tfull + 8 * acc);          // accumulators complete
       }
     }
   } else {
     // ===== epilogue warps 2..5: TMEM lane quarter (warp % 4) =====
     const int q = warp & 3;
     const int m = q * 32 + lane;                   // pixel within the tile row = TMEM lane
-    constexpr int GCOLS = C::ACC_COLS < 64 ? C::ACC_COLS : 64;      // accumulator columns fetched per TMEM wait
+    constexpr int GCOLS = C::GCOLS;                // accumulator columns fetched per TMEM wait
     constexpr int NSUB = GCOLS / 16;
+    constexpr int RW = 4 * ESZ;                    // 32-bit words of the 16 channels of a pixel: 8 (bf16, one sector) or 16 (fp32, two)
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
     // zero both accumulator buffers, then open them for the MMA warp
     for (int c = 0; c < 2 * C::ACC_COLS; c += 16) tmem_zero16(lane_base + c);
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    tc_fence_before();
+    tmem_wait_st();
+    fence_before();
     __syncwarp();
     if (lane == 0) {
       mbar_arrive(bar_tempty);
       mbar_arrive(bar_tempty + 8);
     }
+    // f += the 16 channels held in w: bf16 pairs are widened by bit placement (keeps the conversion pipe free)
+    auto add_words = [](float* f, const uint32_t* w) {
+      if (ESZ == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          f[2 * j] += __uint_as_float(w[j] << 16);
+          f[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] += __uint_as_float(w[j]);
+      }
+    };
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
       const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
@@ -343,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       const int ox = tx * BW + m;
       if (res_tma) mbar_wait(bar_rfull + 8 * acc, aph);
       mbar_wait(bar_tfull + 8 * acc, aph);
-      tc_fence_after();
+      fence_after();
 #pragma unroll 1
       for (int g0 = 0; g0 < C::ACC_COLS; g0 += GCOLS) {
         uint32_t v[NSUB][16];
@@ -352,40 +310,41 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
         for (int sb = 0; sb < NSUB; ++sb) tmem_ld16(taddr + sb * 16, v[sb]);
         // residual operands for the same columns, all fetched before the TMEM wait so that the latencies overlap (the
         // lower-resolution fuse terms used to be loaded one by one at their point of use: 0.25 ms per stage-3/4 fuse conv)
-        uint4 rv[NSUB][2], rx[NSUB][2][2];
+        uint32_t rv[NSUB][RW], rx[NSUB][2][RW];
         const int nres = a.nres;
 #pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) {
           const int col = g0 + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
           const int oy = ty * R + r;
           const bool live = ox < a.w_img && oy < a.h;
-          rv[sb][0] = rv[sb][1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int j = 0; j < RW; ++j) rv[sb][j] = 0;
           if (nres > 0) {
             if (res_tma) {
-              const uint32_t base = smem_u32(sR + (acc * C::NRB + c0 / C::CB) * C::RBOX_BYTES);
-              uint32_t ad = base + (r * BW + m) * C::RROWB + (c0 % C::CB) * 2;
-              ad ^= ((ad >> 7) & C::RSWZ) << 4;
-              const uint32_t ad2 = (base + (r * BW + m) * C::RROWB + (c0 % C::CB) * 2 + 16) ^ ((((base + (r * BW + m) * C::RROWB) >> 7) & C::RSWZ) << 4);
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[sb][0].x), "=r"(rv[sb][0].y), "=r"(rv[sb][0].z), "=r"(rv[sb][0].w) : "r"(ad));
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[sb][1].x), "=r"(rv[sb][1].y), "=r"(rv[sb][1].z), "=r"(rv[sb][1].w) : "r"(ad2));
+              const uint32_t row = smem_u32(sR + (acc * C::NRB + c0 / C::CB) * C::RBOX_BYTES) + (r * BW + m) * C::RROWB;
+              const uint32_t swz = ((row >> 7) & C::RSWZ) << 4;       // a pixel row never crosses a 128-byte line: one XOR for all its chunks
+#pragma unroll
+              for (int i = 0; i < RW / 4; ++i) lds128((row + (c0 % C::CB) * ESZ + 16 * i) ^ swz, &rv[sb][4 * i]);
             } else if (live) {
               const int sh = a.rsh[0];
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  a.res[0] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
-              ldg256(rp, rv[sb][0], rv[sb][1]);
+              const char* rp = (const char*)a.res[0] +
+                               ((((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0) * ESZ;
+#pragma unroll
+              for (int i = 0; i < RW / 8; ++i) ldg256(rp + 32 * i, &rv[sb][8 * i]);
             }
 #pragma unroll
             for (int rr = 1; rr < 3; ++rr) {
               if (rr < nres && live) {
                 const int sh = a.rsh[rr];
-                const uint4* rp = reinterpret_cast<const uint4*>(
-                    a.res[rr] + (((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0);
-                ldg256(rp, rx[sb][rr - 1][0], rx[sb][rr - 1][1]);
+                const char* rp = (const char*)a.res[rr] +
+                                 ((((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0) * ESZ;
+#pragma unroll
+                for (int i = 0; i < RW / 8; ++i) ldg256(rp + 32 * i, &rx[sb][rr - 1][8 * i]);
               }
             }
           }
         }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        tmem_wait_ld();
 #pragma unroll
         for (int sb = 0; sb < NSUB; ++sb) tmem_zero16(taddr + sb * 16);     // leave the columns zeroed for the next tile
 #pragma unroll
@@ -397,94 +356,90 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[sb][j]) + sBias[c0 + j];
           if (nres > 0) {
-            const uint32_t rw[8] = {rv[sb][0].x, rv[sb][0].y, rv[sb][0].z, rv[sb][0].w, rv[sb][1].x, rv[sb][1].y, rv[sb][1].z, rv[sb][1].w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {            // bf16 -> f32 by bit placement (keeps the conversion pipe free)
-              f[2 * j] += __uint_as_float(rw[j] << 16);
-              f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
-            }
+            add_words(f, rv[sb]);
 #pragma unroll
             for (int rr = 1; rr < 3; ++rr) {
               if (rr >= nres) break;
-              const uint4 r0 = rx[sb][rr - 1][0], r1 = rx[sb][rr - 1][1];
-              const uint32_t xw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[2 * j] += __uint_as_float(xw[j] << 16);
-                f[2 * j + 1] += __uint_as_float(xw[j] & 0xffff0000u);
-              }
+              add_words(f, rx[sb][rr - 1]);
             }
           }
           if (a.relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          uint32_t o[8];
+          // 256-bit stores: the 16 channels of a pixel are one (bf16) or two (fp32) whole 32-byte sectors
+          char* op = (char*)a.out + ((((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0) * ESZ;
+          if (ESZ == 2) {
+            uint32_t o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            o[j] = *reinterpret_cast<uint32_t*>(&b2);
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              o[j] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            stg256(op, o);
+          } else {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(f[j]);
+            stg256(op, o);
+            stg256(op + 32, o + 8);
           }
-          // one 256-bit store: the 16 channels of a pixel are a whole 32-byte sector
-          __nv_bfloat16* op = a.out + (((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0;
-          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]),
-                       "r"(o[5]), "r"(o[6]), "r"(o[7])
-                       : "memory");
         }
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
+      tmem_wait_st();
+      fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
     }
   }
-  tc_fence_before();
+  fence_before();
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS));
+  if (warp == 2) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn get_encode() {
-  static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    cudaDriverEntryPointQueryResult q;
-    void* p = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeFn)p;
-  }
-  return fn;
-}
-
 // output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
-int cout_tile(const TtkConv& cv) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? 64 : cv.cout_p; }
-bool fused_ky(const TtkConv& cv) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv) <= 256; }
+int cout_tile(const TtkConv& cv, int esz) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? (esz == 2 ? 64 : 32) : cv.cout_p; }
+bool fused_ky(const TtkConv& cv, int esz) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv, esz) <= 256; }
 // channels per K-chunk (one swizzled shared-memory row).  The stride-1 3x3 layers with 64+ input channels are bound by their MMA
-// count (tensor pipe 73-85 % busy; a 128-pixel x 16-channel MMA holds it ~79 clk at N <= 48, ~1 clk per column beyond) and the halo
-// rows of a tile are pure overhead: 3 (R + 2) / R MMAs per K16 step and output row.  32-channel chunks halve the staging boxes so that
-// taller tiles fit: transition1.0 R = 3 -> 8, the 64 -> 64 layers R = 2 -> 4, and the 128 -> 128 layers get a second pipeline stage.
-int kc_of(const TtkConv& cv) {
-  if (cv.k == 3 && cv.stride == 1 && cv.cin_p >= 64) return 32;
-  // stride 2 with 64+ input channels (transition1.1 1.74 -> 1.49 ms): two-row tiles and a third pipeline stage in the same shared memory
-  if (cv.k == 3 && cv.stride == 2 && cv.cin_p >= 64) return 32;
-  return cv.cin_p < 64 ? cv.cin_p : 64;
+// count (a 128-pixel x 32-byte MMA holds the tensor pipe 45.5 clk at N <= 48 and N / 2 clk from N = 96 on, tools/tf32_probe.cu) and
+// the halo rows of a tile are pure overhead: 3 (R + 2) / R MMAs per K step and output row.  Narrow chunks shrink the staging boxes so
+// that taller tiles fit: bf16 transition1.0 R = 3 -> 8, the 64 -> 64 layers R = 2 -> 4, and the 128 -> 128 layers get a second
+// pipeline stage.  With fp32 elements the 3x3 weights of the wide layers take up to 147 KB, which leaves room for 8-channel chunks.
+int kc_of(const TtkConv& cv, int esz) {
+  if (esz == 2) {
+    if (cv.k == 3 && cv.stride == 1 && cv.cin_p >= 64) return 32;
+    // stride 2 with 64+ input channels (transition1.1 1.74 -> 1.49 ms): two-row tiles and a third pipeline stage in the same shared memory
+    if (cv.k == 3 && cv.stride == 2 && cv.cin_p >= 64) return 32;
+    return cv.cin_p < 64 ? cv.cin_p : 64;
+  }
+  if (cv.k == 3 && cv.cin_p >= 64) return 8;
+  if (cv.k == 3 && cv.stride == 2 && cv.cin_p == 32 && cv.cout_p == 128) return 8;
+  if (cv.k == 3) return 16;
+  return 32;
 }
 
 CUtensorMapSwizzle swizzle_for(int row_bytes) {
   return row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
 }
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0>
+float round_tf32(float v) {      // nearest-even on the 13 dropped mantissa bits (finite inputs)
+  uint32_t u;
+  memcpy(&u, &v, 4);
+  u += 0xfffu + ((u >> 13) & 1u);
+  u &= ~0x1fffu;
+  memcpy(&v, &u, 4);
+  return v;
+}
+
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
 int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO>;
-  if (C::KC != kc_of(cv)) {
-    ttk_set_error("conv %s: kernel K-chunk %d differs from the packed weights' %d", cv.name.c_str(), C::KC, kc_of(cv));
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>;
+  if (C::KC != kc_of(cv, ESZ) || COUT != cout_tile(cv, ESZ)) {
+    ttk_set_error("conv %s: kernel K-chunk %d / output slice %d differ from the packed weights' %d / %d", cv.name.c_str(), C::KC, COUT,
+                  kc_of(cv, ESZ), cout_tile(cv, ESZ));
     return TTK_ERR_STATE;
   }
   EncodeFn encode = get_encode();
@@ -494,20 +449,24 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM_BYTES));
     attr = true;
   }
   if (S == 2 && ((a.hin & 1) || (a.win & 1))) return TTK_ERR_UNSUPPORTED;
+  // the input map's TFLOAT32 type makes TMA round fp32 to TF32 (nearest-even) while it fills shared memory
+  const CUtensorMapDataType in_type = ESZ == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
+  const CUtensorMapDataType res_type = ESZ == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   KMaps maps;
   cuuint32_t box[4] = {(cuuint32_t)C::KC, (cuuint32_t)C::TW, (cuuint32_t)C::TR, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   for (int i = 0; i < (S == 2 ? 4 : 1); ++i) {
     const int py = i >> 1, px = i & 1;
     cuuint64_t dims[4] = {(cuuint64_t)CIN, (cuuint64_t)(a.win / S), (cuuint64_t)(a.hin / S), (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)CIN * 2 * S, (cuuint64_t)a.win * CIN * 2 * S, (cuuint64_t)a.hin * a.win * CIN * 2};
-    void* base = (char*)const_cast<void*>(a.in) + ((size_t)py * a.win + px) * CIN * 2;
-    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle_for(C::ROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t strides[3] = {(cuuint64_t)CIN * ESZ * S, (cuuint64_t)a.win * CIN * ESZ * S, (cuuint64_t)a.hin * a.win * CIN * ESZ};
+    void* base = (char*)const_cast<void*>(a.in) + ((size_t)py * a.win + px) * CIN * ESZ;
+    const CUresult r = encode(&maps.m[i], in_type, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::ROWB),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       ttk_set_error("cuTensorMapEncodeTiled failed (%d) for conv %s", (int)r, cv.name.c_str());
       return TTK_ERR_CUDA;
@@ -518,22 +477,21 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   maps.res = maps.m[0];
   if (res_tma) {
     cuuint64_t dims[4] = {(cuuint64_t)a.cout, (cuuint64_t)a.wout, (cuuint64_t)a.hout, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)a.cout * 2, (cuuint64_t)a.wout * a.cout * 2, (cuuint64_t)a.hout * a.wout * a.cout * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)a.cout * ESZ, (cuuint64_t)a.wout * a.cout * ESZ, (cuuint64_t)a.hout * a.wout * a.cout * ESZ};
     cuuint32_t rbox[4] = {(cuuint32_t)C::CB, (cuuint32_t)BW, (cuuint32_t)R, 1};
-    const CUresult r = encode(&maps.res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(a.res[0]), dims, strides, rbox, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(C::RROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode(&maps.res, res_type, 4, const_cast<void*>(a.res[0]), dims, strides, rbox, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_for(C::RROWB), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       ttk_set_error("cuTensorMapEncodeTiled (residual) failed (%d) for conv %s", (int)r, cv.name.c_str());
       return TTK_ERR_CUDA;
     }
   }
   KArgs k;
-  k.w = cv.w_umma;
+  k.w = ESZ == 2 ? (const void*)cv.w_umma : (const void*)cv.w_umma32;
   k.bias = cv.bias;
-  k.out = (__nv_bfloat16*)a.out;
+  k.out = a.out;
   for (int i = 0; i < 3; ++i) {
-    k.res[i] = (const __nv_bfloat16*)a.res[i];
+    k.res[i] = a.res[i];
     k.rsh[i] = a.res_shift[i];
   }
   k.nres = a.nres;
@@ -553,31 +511,34 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   occ = std::max(1, std::min(occ, 2));
   const int gx = std::max(1, std::min(k.total, ttk_num_sms() * occ / nsplit));
   dim3 grid(gx, nsplit);
-  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
-int launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st) {
-  constexpr int R = 2, STAGES = 3;
-  using C = Cfg<1, 1, 128, 128, R, STAGES, 0>;
+// Bottleneck tail: out = relu(W3 a + Wd x + bias) with a (32 channels) and x (64 channels) K-concatenated.  bf16: two 64-channel
+// K-chunks (the first box reaches past the 32-channel tensor, TMA zero fills); tf32: three 32-channel chunks (a | x[0:32] | x[32:64]).
+template <int ESZ>
+int launch_dual(const void* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st) {
+  constexpr int R = 2, STAGES = 3, KC = 128 / ESZ, CINK = ESZ == 2 ? 128 : 96;
+  using C = Cfg<1, 1, CINK, 128, R, STAGES, 0, 0, ESZ>;
   EncodeFn encode = get_encode();
   if (!encode) return TTK_ERR_UNSUPPORTED;
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1, 1, 128, 128, R, STAGES, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1, 1, CINK, 128, R, STAGES, 0, 0, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
   KMaps maps;
-  cuuint32_t box[4] = {64, (cuuint32_t)BW, (cuuint32_t)R, 1};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BW, (cuuint32_t)R, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   const void* ins[2] = {a.in, a.in2};
   const int cins[2] = {a.cin, a.cin2};
   for (int i = 0; i < 2; ++i) {
     cuuint64_t dims[4] = {(cuuint64_t)cins[i], (cuuint64_t)a.win, (cuuint64_t)a.hin, (cuuint64_t)a.n};
-    cuuint64_t strides[3] = {(cuuint64_t)cins[i] * 2, (cuuint64_t)a.win * cins[i] * 2, (cuuint64_t)a.hin * a.win * cins[i] * 2};
-    const CUresult r = encode(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ins[i]), dims, strides, box, es,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    cuuint64_t strides[3] = {(cuuint64_t)cins[i] * ESZ, (cuuint64_t)a.win * cins[i] * ESZ, (cuuint64_t)a.hin * a.win * cins[i] * ESZ};
+    const CUresult r = encode(&maps.m[i], ESZ == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(ins[i]),
+                              dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return TTK_ERR_UNSUPPORTED;      // e.g. a driver that rejects a box wider than the tensor
   }
@@ -585,7 +546,7 @@ int launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvL
   KArgs k;
   k.w = w_dual;
   k.bias = bias_dual;
-  k.out = (__nv_bfloat16*)a.out;
+  k.out = a.out;
   for (int i = 0; i < 3; ++i) {
     k.res[i] = nullptr;
     k.rsh[i] = 0;
@@ -602,77 +563,137 @@ int launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvL
   k.tiles_y = ttk_cdiv(a.hout, R);
   k.total = k.tiles_x * k.tiles_y * a.n;
   const int gx = std::max(1, std::min(k.total, ttk_num_sms()));
-  conv_umma_kernel<1, 1, 128, 128, R, STAGES, 0><<<gx, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  conv_umma_kernel<1, 1, CINK, 128, R, STAGES, 0, 0, ESZ><<<gx, THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
 }  // namespace
 
-int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st) {
+int ttk_conv_umma_launch_dual(const void* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st, int esz) {
   if (a.cin != 32 || a.cin2 != 64 || a.cout != 128) return TTK_ERR_UNSUPPORTED;
-  return launch_dual(w_dual, bias_dual, a, st);
+  return esz == 2 ? launch_dual<2>(w_dual, bias_dual, a, st) : launch_dual<4>(w_dual, bias_dual, a, st);
 }
 
-// Weights for the tensor-core path: bf16 rows of KC input channels (K-major), zero padded, per output-channel slice:
+// Host image of the fused bottleneck tail's B operand: [k-chunk][cout 128][KC], chunk 0 = conv3 (32 input channels, zero padded to KC),
+// then the projection shortcut's 64 input channels.  bf16: KC = 64 (2 chunks); tf32: KC = 32 (3 chunks), values rounded to TF32.
+void ttk_conv_umma_pack_dual(const float* w3, const float* wd, int esz, std::vector<uint8_t>& out) {
+  const int KC = 128 / esz, nk = esz == 2 ? 2 : 3;
+  out.assign((size_t)nk * 128 * KC * esz, 0);
+  auto put = [&](int kc, int co, int c, float v) {
+    const size_t i = ((size_t)kc * 128 + co) * KC + c;
+    if (esz == 2) reinterpret_cast<__nv_bfloat16*>(out.data())[i] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(out.data())[i] = round_tf32(v);
+  };
+  for (int co = 0; co < 128; ++co) {
+    for (int ci = 0; ci < 32; ++ci) put(0, co, ci, w3[(size_t)co * 32 + ci]);
+    for (int ci = 0; ci < 64; ++ci) put(1 + ci / KC, co, ci % KC, wd[(size_t)co * 64 + ci]);
+  }
+}
+
+// Weights for the tensor-core path: rows of KC input channels (K-major), zero padded, per output-channel slice:
 //   fused 3x3 stride 1 : [slice][k-chunk][kx][ky][cout_tile][KC]   (B = the three vertical taps side by side)
 //   otherwise          : [slice][tap][k-chunk][cout_tile][KC]
+// bf16 (w_umma) and TF32-rounded fp32 (w_umma32) images are both kept; they differ in KC and in the slice width of the 128-wide layers.
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
   const int kk = cv.k * cv.k;
-  const int KC = kc_of(cv);
-  const int nkc = cv.cin_p / KC;
-  const int ct = cout_tile(cv);
-  const bool fused = fused_ky(cv);
-  std::vector<__nv_bfloat16> w((size_t)kk * cv.cin_p * cv.cout_p, __float2bfloat16_rn(0.f));
-  for (int co = 0; co < cv.cout; ++co)
-    for (int ci = 0; ci < cv.cin; ++ci)
-      for (int t = 0; t < kk; ++t) {
-        const int kc = ci / KC, c = ci % KC, sl = co / ct, cl = co % ct;
-        size_t row;
-        if (fused) {
-          const int ky = t / 3, kx = t % 3;
-          row = (((size_t)sl * nkc + kc) * 3 + kx) * 3 + ky;
-        } else {
-          row = ((size_t)sl * kk + t) * nkc + kc;
+  for (int esz = 2; esz <= 4; esz += 2) {
+    const int KC = kc_of(cv, esz);
+    const int nkc = cv.cin_p / KC;
+    const int ct = cout_tile(cv, esz);
+    const bool fused = fused_ky(cv, esz);
+    const size_t count = (size_t)kk * cv.cin_p * cv.cout_p;
+    std::vector<uint8_t> w(count * esz, 0);
+    for (int co = 0; co < cv.cout; ++co)
+      for (int ci = 0; ci < cv.cin; ++ci)
+        for (int t = 0; t < kk; ++t) {
+          const int kc = ci / KC, c = ci % KC, sl = co / ct, cl = co % ct;
+          size_t row;
+          if (fused) {
+            const int ky = t / 3, kx = t % 3;
+            row = (((size_t)sl * nkc + kc) * 3 + kx) * 3 + ky;
+          } else {
+            row = ((size_t)sl * kk + t) * nkc + kc;
+          }
+          const float v = w_host[((size_t)co * cv.cin + ci) * kk + t];
+          const size_t i = (row * ct + cl) * KC + c;
+          if (esz == 2) reinterpret_cast<__nv_bfloat16*>(w.data())[i] = __float2bfloat16_rn(v);
+          else reinterpret_cast<float*>(w.data())[i] = round_tf32(v);
         }
-        w[(row * ct + cl) * KC + c] = __float2bfloat16_rn(w_host[((size_t)co * cv.cin + ci) * kk + t]);
-      }
-  if (!cv.w_umma) TTK_CUDA(cudaMalloc((void**)&cv.w_umma, w.size() * sizeof(__nv_bfloat16)));
-  TTK_CUDA(cudaMemcpy(cv.w_umma, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    void** dst = esz == 2 ? (void**)&cv.w_umma : (void**)&cv.w_umma32;
+    if (!*dst) TTK_CUDA(cudaMalloc(dst, w.size()));
+    TTK_CUDA(cudaMemcpy(*dst, w.data(), w.size(), cudaMemcpyHostToDevice));
+  }
   return TTK_OK;
 }
 
-int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  const int ci = cv.cin_p, co = cout_tile(cv);
+int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st, int esz) {
+  const int ci = cv.cin_p, co = cout_tile(cv, esz);
+  const int k = cv.k, s = cv.stride;
+  if (esz == 2) {
 #define TTK_UMMA(KS_, S_, CI_, CO_, R_, ST_, RB_) \
-  if (cv.k == KS_ && cv.stride == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_>(cv, a, st);
-  // 3x3 stride 1
-  TTK_UMMA(3, 1, 16, 64, 4, 3, 0)     // stem conv1 (9 -> 64, input padded to 16 channels)
-  if (cv.k == 3 && cv.stride == 1 && ci == 64 && co == 64) return launch<3, 1, 64, 64, 4, 3, 0, 32>(cv, a, st);      // stem conv2, quarter-resolution branch
-  if (cv.k == 3 && cv.stride == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0>(cv, a, st);   // no residual tiles to stage: taller tile
-  TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
-  TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
-  if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 8, 2, 0, 32>(cv, a, st);     // transition1.0
-  if (cv.k == 3 && cv.stride == 1 && ci == 128 && co == 64) return launch<3, 1, 128, 64, 2, 2, 0, 32>(cv, a, st);    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
-  // 3x3 stride 2 (transitions and fuse down-paths)
-  if (cv.k == 3 && cv.stride == 2 && ci == 128 && co == 32) return launch<3, 2, 128, 32, 2, 3, 0, 32>(cv, a, st);
-  TTK_UMMA(3, 2, 16, 16, 4, 3, 0)
-  TTK_UMMA(3, 2, 16, 32, 4, 3, 0)
-  TTK_UMMA(3, 2, 16, 64, 4, 3, 0)
-  TTK_UMMA(3, 2, 16, 128, 2, 3, 0)
-  TTK_UMMA(3, 2, 32, 32, 4, 2, 0)
-  TTK_UMMA(3, 2, 32, 64, 4, 2, 0)
-  TTK_UMMA(3, 2, 32, 128, 2, 2, 0)
-  if (cv.k == 3 && cv.stride == 2 && ci == 64 && co == 64) return launch<3, 2, 64, 64, 2, 3, 0, 32>(cv, a, st);       // 64 -> 128 as two output slices
-  // 1x1
-  TTK_UMMA(1, 1, 64, 32, 4, 2, 0)     // bottleneck conv1, fuse 64 -> 32
-  TTK_UMMA(1, 1, 32, 128, 2, 3, 1)    // bottleneck conv3 (+ projection shortcut as residual)
-  TTK_UMMA(1, 1, 64, 128, 2, 3, 0)    // bottleneck projection shortcut
-  TTK_UMMA(1, 1, 32, 16, 4, 3, 0)     // fuse layers (low -> high resolution)
-  TTK_UMMA(1, 1, 64, 16, 4, 3, 0)
-  TTK_UMMA(1, 1, 128, 16, 4, 2, 0)
-  TTK_UMMA(1, 1, 128, 32, 4, 2, 0)
-  TTK_UMMA(1, 1, 128, 64, 2, 2, 0)
+  if (k == KS_ && s == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_>(cv, a, st);
+    // 3x3 stride 1
+    TTK_UMMA(3, 1, 16, 64, 4, 3, 0)     // stem conv1 (9 -> 64, input padded to 16 channels)
+    if (k == 3 && s == 1 && ci == 64 && co == 64) return launch<3, 1, 64, 64, 4, 3, 0, 32>(cv, a, st);      // stem conv2, quarter-resolution branch
+    if (k == 3 && s == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0>(cv, a, st);   // no residual tiles to stage: taller tile
+    TTK_UMMA(3, 1, 32, 32, 4, 2, 1)     // bottleneck conv2, half-resolution branch
+    TTK_UMMA(3, 1, 16, 16, 8, 3, 1)     // full-resolution branch
+    if (k == 3 && s == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 8, 2, 0, 32>(cv, a, st);     // transition1.0
+    if (k == 3 && s == 1 && ci == 128 && co == 64) return launch<3, 1, 128, 64, 2, 2, 0, 32>(cv, a, st);    // eighth-resolution branch (128 -> 128 as two 64-channel output slices)
+    // 3x3 stride 2 (transitions and fuse down-paths)
+    if (k == 3 && s == 2 && ci == 128 && co == 32) return launch<3, 2, 128, 32, 2, 3, 0, 32>(cv, a, st);
+    TTK_UMMA(3, 2, 16, 16, 4, 3, 0)
+    TTK_UMMA(3, 2, 16, 32, 4, 3, 0)
+    TTK_UMMA(3, 2, 16, 64, 4, 3, 0)
+    TTK_UMMA(3, 2, 16, 128, 2, 3, 0)
+    TTK_UMMA(3, 2, 32, 32, 4, 2, 0)
+    TTK_UMMA(3, 2, 32, 64, 4, 2, 0)
+    TTK_UMMA(3, 2, 32, 128, 2, 2, 0)
+    if (k == 3 && s == 2 && ci == 64 && co == 64) return launch<3, 2, 64, 64, 2, 3, 0, 32>(cv, a, st);       // 64 -> 128 as two output slices
+    // 1x1
+    TTK_UMMA(1, 1, 64, 32, 4, 2, 0)     // bottleneck conv1, fuse 64 -> 32
+    TTK_UMMA(1, 1, 32, 128, 2, 3, 1)    // bottleneck conv3 (+ projection shortcut as residual)
+    TTK_UMMA(1, 1, 64, 128, 2, 3, 0)    // bottleneck projection shortcut
+    TTK_UMMA(1, 1, 32, 16, 4, 3, 0)     // fuse layers (low -> high resolution)
+    TTK_UMMA(1, 1, 64, 16, 4, 3, 0)
+    TTK_UMMA(1, 1, 128, 16, 4, 2, 0)
+    TTK_UMMA(1, 1, 128, 32, 4, 2, 0)
+    TTK_UMMA(1, 1, 128, 64, 2, 2, 0)
 #undef TTK_UMMA
+    return TTK_ERR_UNSUPPORTED;
+  }
+  // ---- TF32 (fp32 activations): same tiles, re-sized for 4-byte elements (shared memory: weights + STAGES boxes + residual tiles) ----
+#define TTK_UMMA32(KS_, S_, CI_, CO_, R_, ST_, RB_, KC_) \
+  if (k == KS_ && s == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_, KC_, 4>(cv, a, st);
+  // 3x3 stride 1
+  TTK_UMMA32(3, 1, 16, 64, 4, 3, 0, 16)      // stem conv1
+  TTK_UMMA32(3, 1, 64, 64, 4, 3, 0, 8)       // stem conv2, quarter-resolution branch: 147 KB of weights + three 25 KB boxes
+  if (k == 3 && s == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0, 16, 4>(cv, a, st);
+  TTK_UMMA32(3, 1, 32, 32, 4, 3, 0, 16)      // half-resolution branch (residual read from global memory: no room for staged tiles)
+  if (k == 3 && s == 1 && ci == 16 && co == 16 && a.nres == 0) return launch<3, 1, 16, 16, 8, 2, 0, 16, 4>(cv, a, st);
+  TTK_UMMA32(3, 1, 16, 16, 4, 3, 1, 16)      // full-resolution branch, residual tiles staged by TMA
+  TTK_UMMA32(3, 1, 128, 16, 8, 3, 0, 8)      // transition1.0
+  TTK_UMMA32(3, 1, 128, 32, 4, 3, 0, 8)      // eighth-resolution branch (128 -> 128 as four 32-channel output slices)
+  // 3x3 stride 2
+  TTK_UMMA32(3, 2, 128, 32, 2, 3, 0, 8)
+  TTK_UMMA32(3, 2, 16, 16, 4, 2, 0, 16)
+  TTK_UMMA32(3, 2, 16, 32, 4, 2, 0, 16)
+  TTK_UMMA32(3, 2, 16, 64, 4, 2, 0, 16)
+  TTK_UMMA32(3, 2, 16, 128, 2, 2, 0, 16)
+  TTK_UMMA32(3, 2, 32, 32, 4, 2, 0, 16)
+  TTK_UMMA32(3, 2, 32, 64, 2, 3, 0, 16)
+  TTK_UMMA32(3, 2, 32, 128, 2, 3, 0, 8)
+  TTK_UMMA32(3, 2, 64, 32, 2, 3, 0, 8)       // 64 -> 128 as four output slices
+  // 1x1
+  TTK_UMMA32(1, 1, 64, 32, 4, 3, 0, 32)
+  TTK_UMMA32(1, 1, 32, 128, 2, 3, 0, 32)
+  TTK_UMMA32(1, 1, 64, 128, 2, 3, 0, 32)
+  TTK_UMMA32(1, 1, 32, 16, 4, 3, 0, 32)
+  TTK_UMMA32(1, 1, 64, 16, 4, 3, 0, 32)
+  TTK_UMMA32(1, 1, 128, 16, 4, 3, 0, 32)
+  TTK_UMMA32(1, 1, 128, 32, 4, 3, 0, 32)
+  TTK_UMMA32(1, 1, 128, 64, 2, 3, 0, 32)
+#undef TTK_UMMA32
   return TTK_ERR_UNSUPPORTED;
 }

@@ -18,12 +18,6 @@ using namespace umma;
 constexpr int BM = 128, BK = 64, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STG_ROW = 80;         // bytes per staged output row piece (64 + 16 padding: conflict-free 16-byte accesses)
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 
 // implicit transposed-convolution mode: an M tile is a 16 x 8 pixel patch of the input grid (pixel-major rows of the A operand)
 constexpr int PW = 16, PH = 8;

@@ -537,7 +537,7 @@ int profile_mark(ttk_hrnet* h, int oi, int bs, int H, int W, size_t elem, cudaSt
     r.flops = 2.0 * opix * c.cin * c.cout * c.k * c.k;
     r.bytes = (numel(op.in) + numel(op.out)) * elem + (double)c.cin_p * c.cout_p * c.k * c.k * elem;
     for (int k = 0; k < op.nres; ++k) r.bytes += numel(op.res[k]) * elem;
-    if (elem == 2 && h->dual_ready && h->use_dual && !h->force_simt && oi == h->dual_c3_op) {
+    if (h->cur_esz && h->dual_ready && h->use_dual && oi == h->dual_c3_op) {
       // fused bottleneck tail: the projection shortcut's GEMM rides along and its output tensor never exists
       const TtkOp& ds = h->ops[h->dual_ds_op];
       const TtkConv& dc = h->convs[ds.conv];
@@ -556,21 +556,21 @@ int profile_mark(ttk_hrnet* h, int oi, int bs, int H, int W, size_t elem, cudaSt
   return TTK_OK;
 }
 
-// [kc=2][cout 128][64] bf16: chunk 0 = conv3 weights (32 input channels, zero padded), chunk 1 = projection shortcut (64)
+// B operands of the fused bottleneck tail (conv3 and the projection shortcut K-concatenated), bf16 and TF32 images
 int prepare_dual(ttk_hrnet* h) {
   if (h->dual_ds_op < 0) return TTK_OK;
   const TtkConv& ds = h->convs[h->ops[h->dual_ds_op].conv];
   const TtkConv& c3 = h->convs[h->ops[h->dual_c3_op].conv];
   if (ds.w_host.empty() || c3.w_host.empty()) return TTK_OK;
-  std::vector<__nv_bfloat16> w((size_t)2 * 128 * 64, __float2bfloat16_rn(0.f));
   std::vector<float> b(128);
-  for (int co = 0; co < 128; ++co) {
-    for (int ci = 0; ci < 32; ++ci) w[((size_t)0 * 128 + co) * 64 + ci] = __float2bfloat16_rn(c3.w_host[(size_t)co * 32 + ci]);
-    for (int ci = 0; ci < 64; ++ci) w[((size_t)1 * 128 + co) * 64 + ci] = __float2bfloat16_rn(ds.w_host[(size_t)co * 64 + ci]);
-    b[co] = c3.b_host[co] + ds.b_host[co];
+  for (int co = 0; co < 128; ++co) b[co] = c3.b_host[co] + ds.b_host[co];
+  for (int esz = 2; esz <= 4; esz += 2) {
+    std::vector<uint8_t> w;
+    ttk_conv_umma_pack_dual(c3.w_host.data(), ds.w_host.data(), esz, w);
+    void** dst = esz == 2 ? &h->w_dual : &h->w_dual32;
+    if (!*dst) TTK_CUDA(cudaMalloc(dst, w.size()));
+    TTK_CUDA(cudaMemcpy(*dst, w.data(), w.size(), cudaMemcpyHostToDevice));
   }
-  if (!h->w_dual) TTK_CUDA(cudaMalloc((void**)&h->w_dual, w.size() * sizeof(__nv_bfloat16)));
-  TTK_CUDA(cudaMemcpy(h->w_dual, w.data(), w.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   if (!h->bias_dual) TTK_CUDA(cudaMalloc((void**)&h->bias_dual, 128 * sizeof(float)));
   TTK_CUDA(cudaMemcpy(h->bias_dual, b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
   h->dual_ready = true;
@@ -590,8 +590,11 @@ bool is_basic_block(const ttk_hrnet* h, size_t oi) {
   return true;
 }
 
+// esz: 0 = SIMT kernels on T storage, 2 = bf16 tcgen05 path, 4 = TF32 tcgen05 path on fp32 storage
 template <typename T>
-int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, char* ws, bool umma, cudaStream_t st) {
+int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, char* ws, int esz, cudaStream_t st) {
+  const bool umma = esz != 0;
+  h->cur_esz = esz;
   bool dual_skipped = false;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const TtkOp& op = h->ops[oi];
@@ -658,7 +661,7 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
         d.nres = 0;
         d.in2 = ptr(ds.in);
         d.cin2 = h->convs[ds.conv].cin_p;
-        rc = ttk_conv_umma_launch_dual(h->w_dual, h->bias_dual, d, st);
+        rc = ttk_conv_umma_launch_dual(esz == 2 ? h->w_dual : h->w_dual32, h->bias_dual, d, st, esz);
         if (rc == TTK_ERR_UNSUPPORTED) {      // driver refused the maps: run the two convolutions separately from now on
           h->use_dual = 0;
           ConvLaunch s0;
@@ -671,14 +674,14 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
           for (int r = 0; r < 3; ++r) { s0.res[r] = nullptr; s0.res_shift[r] = 0; }
           s0.n = bs; s0.hin = H >> dti.shift; s0.win = W >> dti.shift; s0.hout = H >> dto.shift; s0.wout = W >> dto.shift;
           s0.cin = dcv.cin_p; s0.cout = dcv.cout_p; s0.relu = 0;
-          rc = ttk_conv_umma_launch(dcv, s0, st);
+          rc = ttk_conv_umma_launch(dcv, s0, st, esz);
           if (rc == TTK_ERR_UNSUPPORTED) rc = launch_conv_simt<T>(dcv, s0, sizeof(T) == 2, st);
           if (rc != TTK_OK) return rc;
           h->launches++;
-          rc = ttk_conv_umma_launch(cv, a, st);
+          rc = ttk_conv_umma_launch(cv, a, st, esz);
         }
       } else if (umma) {
-        rc = ttk_conv_umma_launch(cv, a, st);
+        rc = ttk_conv_umma_launch(cv, a, st, esz);
       }
       if (rc == TTK_ERR_UNSUPPORTED) rc = launch_conv_simt<T>(cv, a, sizeof(T) == 2, st);
       if (rc != TTK_OK) return rc;
@@ -761,8 +764,10 @@ extern "C" void ttk_hrnet_destroy(ttk_hrnet* h) {
     cudaFree(c.w_bfr);
     cudaFree(c.bias);
     cudaFree(c.w_umma);
+    cudaFree(c.w_umma32);
   }
   cudaFree(h->w_dual);
+  cudaFree(h->w_dual32);
   cudaFree(h->bias_dual);
   cudaFree(h->final_w);
   cudaFree(h->final_b);
@@ -831,13 +836,13 @@ extern "C" int ttk_hrnet_set_conv(ttk_hrnet* h, int i, const float* w_host, cons
 extern "C" size_t ttk_hrnet_workspace_bytes(const ttk_hrnet* h, int batch, int height, int width, int dtype) {
   if (!h || batch <= 0 || height <= 0 || width <= 0) return 0;
   const int bs = std::min(batch, h->subbatch);
-  return plan_memory(const_cast<ttk_hrnet*>(h), bs, height, width, dtype == TTK_BF16 ? 2 : 4);
+  return plan_memory(const_cast<ttk_hrnet*>(h), bs, height, width, dtype == TTK_BF16 ? 2 : 4);      // TTK_TF32 stores fp32
 }
 
 extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int height, int width, int dtype,
                                  float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_hrnet_forward: null handle");
-  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16, "ttk_hrnet_forward: bad dtype %d", dtype);
+  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32, "ttk_hrnet_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0 && height > 0 && width > 0 && height % 8 == 0 && width % 8 == 0,
                 "ttk_hrnet_forward: height and width must be positive multiples of 8 (got %dx%d)", height, width);
   for (const TtkConv& c : h->convs)
@@ -847,7 +852,7 @@ extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int
     }
   h->launches = 0;
   h->recs.clear();
-  if (!h->dual_ready && dtype == TTK_BF16) {
+  if (!h->dual_ready && dtype != TTK_F32) {
     int rc = prepare_dual(h);
     if (rc) return rc;
   }
@@ -864,9 +869,11 @@ extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int
     float* heat = heatmaps_dev + (size_t)b0 * h->out_count * height * width;
     int rc;
     if (dtype == TTK_F32)
-      rc = run_plan<float>(h, x, nb, height, width, heat, (char*)workspace_dev, false, st);
+      rc = run_plan<float>(h, x, nb, height, width, heat, (char*)workspace_dev, 0, st);
+    else if (dtype == TTK_TF32)
+      rc = run_plan<float>(h, x, nb, height, width, heat, (char*)workspace_dev, h->force_simt ? 0 : 4, st);
     else
-      rc = run_plan<__nv_bfloat16>(h, x, nb, height, width, heat, (char*)workspace_dev, !h->force_simt, st);
+      rc = run_plan<__nv_bfloat16>(h, x, nb, height, width, heat, (char*)workspace_dev, h->force_simt ? 0 : 2, st);
     if (rc != TTK_OK) return rc;
   }
   if (h->profile && !h->recs.empty()) TTK_CUDA(cudaEventRecord(h->events[h->recs.size()], st));
@@ -908,7 +915,8 @@ extern "C" int ttk_hrnet_set_force_simt(ttk_hrnet* h, int enable) {
 }
 
 // Test hook: run ONE convolution of the plan (bias + optional same-shape residual + optional ReLU) on caller buffers.
-// path: 0 = fp32 SIMT (float tensors), 1 = bf16 SIMT, 2 = bf16 tcgen05 (returns TTK_ERR_UNSUPPORTED if the shape has no kernel).
+// path: 0 = fp32 SIMT (float tensors), 1 = bf16 SIMT, 2 = bf16 tcgen05, 3 = TF32 tcgen05 on float tensors (2 and 3 return
+// TTK_ERR_UNSUPPORTED if the shape has no kernel).
 extern "C" int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, const void* res_dev,
                                     int relu, int path, void* out_dev, void* stream) {
   TTK_CHECK_ARG(h && conv_index >= 0 && conv_index < (int)h->convs.size() - 1, "ttk_hrnet_debug_conv: bad conv index %d", conv_index);
@@ -933,7 +941,7 @@ extern "C" int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in
   cudaStream_t st = (cudaStream_t)stream;
   if (path == 0) return launch_conv_simt<float>(cv, a, false, st);
   if (path == 1) return launch_conv_simt<__nv_bfloat16>(cv, a, true, st);
-  return ttk_conv_umma_launch(cv, a, st);
+  return ttk_conv_umma_launch(cv, a, st, path == 3 ? 4 : 2);
 }
 
 // Test hook: one BasicBlock (conv_index = its conv1, conv_index + 1 = its conv2) through the fused tcgen05 kernel on caller buffers:

@@ -1,5 +1,7 @@
 // HRNet executor internals shared between hrnet.cu (plan + SIMT kernels) and conv_umma.cu (tcgen05 path).
 #pragma once
+#include <stdint.h>
+
 #include <string>
 #include <vector>
 
@@ -13,7 +15,8 @@ struct TtkConv {
   float* w_f32 = nullptr;       // device, [k*k][cin_p][cout_p] float32 (SIMT path)
   float* w_bfr = nullptr;       // device, same layout, values rounded to bf16 (SIMT path on bf16 storage)
   float* bias = nullptr;        // device, [cout_p] float32
-  __nv_bfloat16* w_umma = nullptr;  // device, tcgen05 B-operand image (see ttk_conv_umma_pack)
+  __nv_bfloat16* w_umma = nullptr;  // device, tcgen05 B-operand image, bf16 (see ttk_conv_umma_pack)
+  float* w_umma32 = nullptr;        // device, tcgen05 B-operand image for kind::tf32: fp32 containers, values rounded to TF32
   std::vector<float> w_host, b_host; // folded weights as set by the host (used to build fused variants)
 };
 
@@ -62,10 +65,12 @@ struct ttk_hrnet {
   float* final_b = nullptr;
   // bottleneck fusion: conv3 (1x1, 32->128) and the projection shortcut (1x1, 64->128) as ONE K-concatenated GEMM
   int dual_ds_op = -1, dual_c3_op = -1;
-  __nv_bfloat16* w_dual = nullptr;
+  void* w_dual = nullptr;           // bf16 image
+  void* w_dual32 = nullptr;         // TF32 image
   float* bias_dual = nullptr;
   bool dual_ready = false;
   int use_dual = 1;
+  int cur_esz = 0;              // element size of the tensor-core path the running forward uses (0: SIMT), for the profile records
   int use_block_fusion = 0;     // BasicBlocks of the 16- and 32-channel branches as one kernel (block_umma.cu).  Off: measured
                                 // break-even (31.8 vs 31.2-32.0 ms per 32 stacks); the thin-channel MMAs cost ~79 clk each on the
                                 // tensor pipe whatever N <= 48 is, and the fused tile needs 9 of them per output row (halo rows of
@@ -77,12 +82,14 @@ struct ttk_hrnet {
   std::vector<Rec> recs;
 };
 
-// conv_umma.cu: bf16 implicit-GEMM convolution on tcgen05/TMEM fed by TMA.
-// Returns TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel (caller falls back to SIMT on bf16).
-int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st);
+// conv_umma.cu: implicit-GEMM convolution on tcgen05/TMEM fed by TMA.  esz = bytes per activation element: 2 = bf16 (kind::f16),
+// 4 = fp32 activations multiplied as TF32 (kind::tf32).
+// Returns TTK_ERR_UNSUPPORTED when the shape has no tensor-core kernel (caller falls back to SIMT on the same storage type).
+int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st, int esz = 2);
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host);
 // out = relu(W3 a + Wd x + bias): a.in = a (32 ch), a.in2 = x (64 ch); returns TTK_ERR_UNSUPPORTED if the driver rejects the maps
-int ttk_conv_umma_launch_dual(const __nv_bfloat16* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st);
+int ttk_conv_umma_launch_dual(const void* w_dual, const float* bias_dual, const ConvLaunch& a, cudaStream_t st, int esz = 2);
+void ttk_conv_umma_pack_dual(const float* w3, const float* wd, int esz, std::vector<uint8_t>& out);
 
 // block_umma.cu: y = relu(conv2(relu(conv1(x))) + x) for the 3x3 stride-1 pairs of a BasicBlock with 16 or 32 (padded) channels.
 int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st);

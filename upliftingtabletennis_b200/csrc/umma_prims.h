@@ -1,6 +1,8 @@
-// PTX wrappers shared by the tcgen05 kernels of the ViT detector (gemm_umma.cu, attn_umma.cu): mbarriers, TMA tile loads,
-// shared-memory matrix descriptors, tcgen05.mma / commit / ld, TMEM allocation.  Same encodings as csrc/conv_umma.cu, whose
-// descriptor semantics were established on the B200 with tools/umma_probe.cu (profiles/r01_umma_probe.log).
+// PTX wrappers shared by all tcgen05 kernels of the library (conv_umma.cu, block_umma.cu, gemm_umma.cu, attn_umma.cu,
+// uplift_tc.cu): mbarriers, TMA tile loads, shared-memory matrix descriptors, tcgen05.mma / commit / ld / st, TMEM allocation.
+// The descriptor semantics were established on the B200 with tools/umma_probe.cu (profiles/r01_umma_probe.log), the TF32
+// operand handling (TMA's TFLOAT32 type rounds to nearest-even, kind::tf32 truncates) with tools/tf32_probe.cu
+// (profiles/r02_tf32_probe.log).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -29,6 +31,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
@@ -38,6 +51,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
 }
 // K-major shared-memory matrix descriptor: start >> 4 | LBO | SBO | version 1 | layout (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
@@ -57,6 +76,18 @@ __device__ __forceinline__ void mma(uint32_t tmem_d, uint64_t da, uint64_t db, u
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Operand formats of the instruction descriptor (bits 7-9: A, 10-12: B): 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32, fp32 containers
+// whose low 13 mantissa bits the tensor core ignores)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -95,6 +126,24 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
       "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+// 256-bit read-only load / store: one 32-byte sector per access (SASS LDG.E.ENL2.256 / STG.E.ENL2.256)
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+               "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t* w) {
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }

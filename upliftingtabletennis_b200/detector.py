@@ -12,6 +12,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
+from .precision import PrecisionMixin, TF32, FP32, BF16, lib_enum, storage_dtype
 
 BN_EPS = 1e-5
 
@@ -71,13 +72,17 @@ class HRNetEngine:
             check(lib.ttk_hrnet_set_conv(self.h, i, ptr(w32), ptr(b32)))
         self.loaded = True
 
-    def forward_nhwc16(self, x, out=None):
-        """x: (B, H, W, 16) float32 or bfloat16 CUDA tensor -> (B, out_count, H, W) float32."""
+    def forward_nhwc16(self, x, out=None, precision=None):
+        """x: (B, H, W, 16) float32 or bfloat16 CUDA tensor -> (B, out_count, H, W) float32.
+        precision: 'tf32' / 'fp32' for float32 tensors (default 'fp32': the strict SIMT path), 'bf16' for bfloat16 tensors."""
         assert self.loaded, 'weights not loaded'
         assert x.is_cuda and x.dim() == 4 and x.shape[3] == 16 and x.is_contiguous()
         B, H, W, _ = x.shape
-        dt = _lib.F32 if x.dtype == torch.float32 else _lib.BF16
         assert x.dtype in (torch.float32, torch.bfloat16)
+        if precision is None:
+            precision = FP32 if x.dtype == torch.float32 else BF16
+        assert storage_dtype(precision) == x.dtype, 'precision %r needs %s tensors' % (precision, storage_dtype(precision))
+        dt = lib_enum(precision)
         need = lib.ttk_hrnet_workspace_bytes(self.h, B, H, W, dt)
         if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
             self._ws = torch.empty((need,), dtype=torch.uint8, device=x.device)
@@ -103,12 +108,17 @@ def _attach(root, key, tensor, is_param):
         m.register_buffer(parts[-1], tensor)
 
 
-class _HRNetModule(nn.Module):
-    """nn.Module shell: holds the reference-named tensors, folds them into the engine lazily."""
-    compute_dtype = torch.float32    # torch.bfloat16 selects the tcgen05 tensor-core path
+class _HRNetModule(PrecisionMixin, nn.Module):
+    """nn.Module shell: holds the reference-named tensors, folds them into the engine lazily.
+    ``compute_dtype`` (constructor argument ``dtype``): 'tf32' (default: tcgen05 tensor cores at the precision class of the
+    reference's cuDNN convolutions), 'fp32' (SIMT, strict parity), 'bf16' (tcgen05, bf16 storage)."""
+    default_precision = TF32
+    supported_precisions = (TF32, FP32, BF16)
 
-    def __init__(self, in_ch, out_ch, out_first, out_count):
+    def __init__(self, in_ch, out_ch, out_first, out_count, dtype=None):
         super().__init__()
+        if dtype is not None:
+            self.compute_dtype = dtype
         self.engine = HRNetEngine(in_ch, out_ch, out_first, out_count)
         self.in_ch = in_ch
         for key, shape in self.engine.state_dict_layout():
@@ -126,27 +136,30 @@ class _HRNetModule(nn.Module):
             self.engine.load(self.state_dict())
             self._dirty = False
 
-    def heatmaps_from_nhwc16(self, x):
+    def heatmaps_from_nhwc16(self, x, precision=None):
+        """x in the storage type of the path; precision defaults to this module's compute_dtype when the tensor type fits it."""
         self._sync()
-        return self.engine.forward_nhwc16(x)
+        if precision is None:
+            precision = self.compute_dtype if storage_dtype(self.compute_dtype) == x.dtype else None
+        return self.engine.forward_nhwc16(x, precision=precision)
 
     def _forward_nchw(self, x):
         if not x.is_cuda:
             raise RuntimeError('upliftingtabletennis_b200 runs on a B200 GPU only; move the input to CUDA (there is no CPU fallback)')
         B, Cc, H, W = x.shape
         assert Cc == self.in_ch, 'expected %d input channels, got %d' % (self.in_ch, Cc)
-        y = torch.zeros((B, H, W, 16), dtype=self.compute_dtype, device=x.device)
+        y = torch.zeros((B, H, W, 16), dtype=self.storage_dtype, device=x.device)
         y[..., :Cc] = x.permute(0, 2, 3, 1)
-        return self.heatmaps_from_nhwc16(y)
+        return self.heatmaps_from_nhwc16(y, self.compute_dtype)
 
 
 class WASBNet(_HRNetModule):
     """Drop-in for balldetection/models/wasb.py:WASBNet (in_frames=3): forward -> (heatmap (B,1,H,W), None)."""
 
-    def __init__(self, in_frames=3, resolution=(1280, 704), pretraining=False, classify_invisible=False):
+    def __init__(self, in_frames=3, resolution=(1280, 704), pretraining=False, classify_invisible=False, dtype=None):
         if classify_invisible or pretraining:
             raise NotImplementedError('classify_invisible / pretraining are training-time options outside the inference hot path')
-        super().__init__(3 * in_frames, 3, 1, 1)
+        super().__init__(3 * in_frames, 3, 1, 1, dtype=dtype)
         self.resolution = tuple(resolution)
 
     def forward(self, x):
@@ -156,9 +169,9 @@ class WASBNet(_HRNetModule):
 class MyHRNet(_HRNetModule):
     """Drop-in for tabledetection/models/hrnet.py:MyHRNet: forward -> heatmaps (B,13,H,W)."""
 
-    def __init__(self, resolution=(1280, 704), pretraining=False):
+    def __init__(self, resolution=(1280, 704), pretraining=False, dtype=None):
         assert not pretraining
-        super().__init__(3, 13, 0, 13)
+        super().__init__(3, 13, 0, 13, dtype=dtype)
         self.resolution = tuple(resolution)
 
     def forward(self, x):

@@ -87,14 +87,25 @@ def _unsupported(model_name):
         "KieDani/SegformerPlusPlus at construction time); available: 'wasb' / 'hrnet' / 'vitpose'")
 
 
-def load_ball_model(model_path):
+BALL_MODELS, TABLE_MODELS = ('wasb', 'vitpose'), ('hrnet', 'vitpose')      # architectures that are part of the reference repository
+
+
+def _check_model_name(model_name, available):
+    """Unsupported names fail before anything is downloaded or unpickled."""
+    if model_name not in available:
+        raise _unsupported(model_name)
+
+
+def load_ball_model(model_path, dtype=None):
+    """inference/inference_balldetection.py:40-61.  dtype: arithmetic class ('tf32' / 'fp32' / 'bf16', see precision.py);
+    None = the architecture's default."""
     load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
     info = load_dict['additional_info']
     model_name, resolution, in_frames = info['model_name'], info['image_resolution'], info['in_frames']
     if model_name == 'wasb':                 # get_model, balldetection/train.py:249-271
-        model = WASBNet(in_frames=in_frames, resolution=resolution, pretraining=False)
+        model = WASBNet(in_frames=in_frames, resolution=resolution, pretraining=False, dtype=dtype)
     elif model_name == 'vitpose':
-        model = VitPose(in_frames=in_frames, model_size='small', resolution=resolution, pretraining=False)
+        model = VitPose(in_frames=in_frames, model_size='small', resolution=resolution, pretraining=False, dtype=dtype)
     else:
         raise _unsupported(model_name)
     model.load_state_dict(load_dict['model_state_dict'])
@@ -104,14 +115,15 @@ def load_ball_model(model_path):
     return model, _DetectorTransform(resolution)
 
 
-def load_table_model(model_path):
+def load_table_model(model_path, dtype=None):
+    """inference/inference_tabledetection.py:40-57."""
     load_dict = torch.load(model_path, map_location=torch.device('cpu'), weights_only=False)
     info = load_dict['additional_info']
     model_name, resolution = info['model_name'], info['image_resolution']
     if model_name == 'hrnet':                # get_model, tabledetection/train.py:205-225
-        model = MyHRNet(resolution=resolution, pretraining=False)
+        model = MyHRNet(resolution=resolution, pretraining=False, dtype=dtype)
     elif model_name == 'vitpose':
-        model = TableVitPose(model_size='small', resolution=resolution, pretraining=False)
+        model = TableVitPose(model_size='small', resolution=resolution, pretraining=False, dtype=dtype)
     else:
         raise _unsupported(model_name)
     model.load_state_dict(load_dict['model_state_dict'])
@@ -131,10 +143,11 @@ class NormalizeImgCoords:
         return data
 
 
-def load_uplifting_model(model_path):
+def load_uplifting_model(model_path, dtype=None):
+    """inference/inference_uplifting.py:33-58."""
     d = torch.load(model_path, weights_only=False, map_location=torch.device('cpu'))
     info = d['additional_info']
-    model = get_uplifting_model(info['name'], size=info['size'], mode=info['tabletoken_mode'], time_rotation=info['time_rotation'])
+    model = get_uplifting_model(info['name'], size=info['size'], mode=info['tabletoken_mode'], time_rotation=info['time_rotation'], dtype=dtype)
     model.load_state_dict(d['model_state_dict'])
     model.eval()
     print(f"Loaded Uplifting model: {info['name']} with size {info['size']}, tabletoken_mode: {info['tabletoken_mode']}, "
@@ -200,7 +213,7 @@ class _Detector:
         `ready`: [(last frame index, event)] from _upload -- a chunk starts as soon as its frames have arrived, so the
         host->device copy of later frames overlaps the network on earlier ones."""
         w, h = self.model.resolution
-        dt = self.model.compute_dtype
+        prec, dt = self.model.compute_dtype, self.model.storage_dtype
         pos, hms = [], []
         main = torch.cuda.current_stream()
         waited = 0
@@ -217,7 +230,7 @@ class _Detector:
                 hm = self.model.heatmaps(x)
             else:
                 x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
-                hm = self.model.heatmaps_from_nhwc16(x)
+                hm = self.model.heatmaps_from_nhwc16(x, prec)
             # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian.  It runs on a second stream:
             # the per-map fit is a latency-bound kernel of one warp per map (~0.3 ms whatever the number of maps) that fits beside the
             # persistent convolution CTAs, so the decode of pass i hides under the network of pass i + 1.
@@ -325,10 +338,12 @@ class BallDetector(_Detector):
     """interface.py:83-134."""
     frames_per_stack = 3
 
-    def __init__(self, model_name='segformerpp_b2'):
+    def __init__(self, model_name='segformerpp_b2', dtype=None):
+        """dtype: 'tf32' / 'fp32' / 'bf16' (precision.py); None = the architecture's default tensor-core path."""
+        _check_model_name(model_name, BALL_MODELS)
         self.device = _device()
         self.resolution = (WIDTH, HEIGHT)
-        self.model, self.transform = load_ball_model(model_path=_get_weights_path(f"inference_balldetection/{model_name}/model.pt"))
+        self.model, self.transform = load_ball_model(model_path=_get_weights_path(f"inference_balldetection/{model_name}/model.pt"), dtype=dtype)
         self.model.to(self.device)
         self.model.eval()
 
@@ -362,11 +377,12 @@ class TableDetector(_Detector):
     """interface.py:137-186."""
     frames_per_stack = 1
 
-    def __init__(self, model_name='segformerpp_b2'):
+    def __init__(self, model_name='segformerpp_b2', dtype=None):
+        _check_model_name(model_name, TABLE_MODELS)
         self.device = _device()
         self.resolution = (WIDTH, HEIGHT)
         self.KEYPOINT_VISIBLE = KEYPOINT_VISIBLE
-        self.model, self.transform = load_table_model(model_path=_get_weights_path(f"inference_tabledetection/{model_name}/model.pt"))
+        self.model, self.transform = load_table_model(model_path=_get_weights_path(f"inference_tabledetection/{model_name}/model.pt"), dtype=dtype)
         self.model.to(self.device)
         self.model.eval()
 
@@ -410,9 +426,9 @@ def calibrate_camera(table_coords):
 class UpliftingModel:
     """interface.py:189-247."""
 
-    def __init__(self):
+    def __init__(self, dtype=None):
         self.device = _device()
-        self.model, self.transform, self.transform_mode = load_uplifting_model(model_path=_get_weights_path("inference_uplifting/ours/model.pt"))
+        self.model, self.transform, self.transform_mode = load_uplifting_model(model_path=_get_weights_path("inference_uplifting/ours/model.pt"), dtype=dtype)
         self.model.to(self.device)
         self.model.eval()
 
@@ -437,17 +453,18 @@ class UpliftingModel:
 
 
 class TableTennisPipeline:
-    """interface.py:251-312.  The reference hard-codes segformerpp_b2 for the main detectors; their architecture
-    is not in the reference repository, so the in-repo WASB / HRNet checkpoints serve as main *and* auxiliary
-    models unless overridden (substitution 4)."""
+    """interface.py:251-312.  The reference pairs segformerpp_b2 (main) with wasb / hrnet (auxiliary) and rejects frames where
+    the two disagree.  The segformer++ architecture is not in the reference repository, so the main detectors default to the
+    other in-repo architecture, ViTPose; the auxiliary detectors are the reference's own.  Like the reference, four separate
+    detector objects are built (main and auxiliary never share one, even when they name the same model)."""
 
-    def __init__(self, ball_model='wasb', ball_model_aux='wasb', table_model='hrnet', table_model_aux='hrnet'):
+    def __init__(self, ball_model='vitpose', ball_model_aux='wasb', table_model='vitpose', table_model_aux='hrnet', dtype=None):
         self.device = _device()
-        self.ball_detector = BallDetector(model_name=ball_model)
-        self.ball_detector_aux = self.ball_detector if ball_model_aux == ball_model else BallDetector(model_name=ball_model_aux)
-        self.table_detector = TableDetector(model_name=table_model)
-        self.table_detector_aux = self.table_detector if table_model_aux == table_model else TableDetector(model_name=table_model_aux)
-        self.uplifting_model = UpliftingModel()
+        self.ball_detector = BallDetector(model_name=ball_model, dtype=dtype)
+        self.ball_detector_aux = BallDetector(model_name=ball_model_aux, dtype=dtype)
+        self.table_detector = TableDetector(model_name=table_model, dtype=dtype)
+        self.table_detector_aux = TableDetector(model_name=table_model_aux, dtype=dtype)
+        self.uplifting_model = UpliftingModel(dtype=dtype)
         self.KEYPOINT_VISIBLE = self.table_detector.KEYPOINT_VISIBLE
 
     def predict(self, images, fps):
@@ -462,16 +479,10 @@ class TableTennisPipeline:
             frames, ready = frames[torch.tensor(order, device=self.device)], None
         with torch.no_grad():
             ball_positions = self.ball_detector._run(frames, 1, n - 2, False, ready)[0][:, 0]       # sliding (prev, cur, next) window
-            if self.ball_detector_aux is self.ball_detector:
-                ball_positions_aux = ball_positions
-            else:
-                ball_positions_aux = self.ball_detector_aux._run(frames, 1, n - 2, False, None)[0][:, 0]
+            ball_positions_aux = self.ball_detector_aux._run(frames, 1, n - 2, False, None)[0][:, 0]
             ball_xy, _, times_ball, offsets = ops.filter_ball(ball_positions, ball_positions_aux, float(fps))
             table_keypoints = self.table_detector._run(frames, 1, n, False, None)[0]
-            if self.table_detector_aux is self.table_detector:
-                table_keypoints_aux = table_keypoints
-            else:
-                table_keypoints_aux = self.table_detector_aux._run(frames, 1, n, False, None)[0]
+            table_keypoints_aux = self.table_detector_aux._run(frames, 1, n, False, None)[0]
         filtered_table_keypoints = ops.filter_table(table_keypoints, table_keypoints_aux)
         ball_coords, table_coords, times, mask = ops.trajectory_pack(ball_xy, times_ball, offsets, filtered_table_keypoints[None],
                                                                     SEQ_LEN, WIDTH, HEIGHT)

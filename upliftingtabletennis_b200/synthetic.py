@@ -28,6 +28,52 @@ def hrnet_state_dict(layout, seed):
     return sd
 
 
+def hrnet_blob_state_dict(layout, seed, in_ch=9, signal_out=1, leak=0.003, background=0.1):
+    """Random weights as above, except that channel 0 of the full-resolution tensors carries a blurred copy of the middle
+    frame's brightness from the input to the heatmap, so that a bright blob in the frames yields a genuine, well separated heatmap
+    peak (random-init heatmaps are noise and make an argmax / sub-pixel comparison vacuous).  Every other channel stays random and
+    leaks into channel 0 with weight `leak`, so the peak region still depends on the whole network.
+    signal_out: output channel of the final 1x1 conv that receives the signal (1 = the channel WASBNet returns)."""
+    sd = hrnet_state_dict(layout, seed)
+    mid = list(range(in_ch // 3, 2 * (in_ch // 3))) if in_ch >= 3 else [0]      # channels of the middle frame (or the only frame)
+
+    def ident_bn(prefix):
+        for t, v in (('weight', 1.0), ('bias', 0.0), ('running_mean', 0.0), ('running_var', 1.0 - 1e-5)):
+            sd['%s.%s' % (prefix, t)][0] = v
+
+    def row0(key, blur_from=None, leak_scale=0.0):
+        w = sd[key + '.weight']
+        w[0] *= leak_scale
+        if blur_from is not None:
+            k = w.shape[-1]
+            for c in blur_from:
+                w[0, c] = 1.0 / (k * k * len(blur_from))
+
+    row0('model.conv1', blur_from=mid)
+    ident_bn('model.bn1')
+    row0('model.conv2', blur_from=[0])
+    ident_bn('model.bn2')
+    row0('model.layer1.0.conv3', leak_scale=leak)
+    ident_bn('model.layer1.0.bn3')
+    row0('model.layer1.0.downsample.0', blur_from=[0])
+    ident_bn('model.layer1.0.downsample.1')
+    row0('model.transition1.0.0', blur_from=[0])
+    ident_bn('model.transition1.0.1')
+    for stage in (2, 3, 4):
+        for blk in range(2):
+            p = 'model.stage%d.0.branches.0.%d' % (stage, blk)
+            row0(p + '.conv2', leak_scale=leak)          # the block's residual carries channel 0 on
+            ident_bn(p + '.bn2')
+        for j in range(1, stage):
+            p = 'model.stage%d.0.fuse_layers.0.%d' % (stage, j)
+            row0(p + '.0', leak_scale=leak)
+            ident_bn(p + '.1')
+    fw = sd['model.final_layers.0.weight']
+    fw[signal_out, 1:] *= background
+    fw[signal_out, 0] = 1.0
+    return sd
+
+
 def uplift_state_dict(module, seed):
     rng = np.random.default_rng(seed)
     sd = {}

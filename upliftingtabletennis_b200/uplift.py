@@ -11,6 +11,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 from .detector import _attach
+from .precision import PrecisionMixin, lib_enum
 
 SIZES = {'small': (32, 8, 4), 'base': (64, 12, 4), 'large': (128, 16, 4), 'huge': (192, 16, 8)}   # uplifting/model.py:574-603
 PARAM_SHAPES = {'cls_token': lambda d: (1, 1, d)}
@@ -47,7 +48,7 @@ class UpliftEngine:
         assert self.loaded
         B, T, _ = ball.shape
         dev = ball.device
-        dt = _lib.F32 if dtype == torch.float32 else _lib.BF16
+        dt = lib_enum(dtype)
         args = [a.to(torch.float32).contiguous() for a in (ball, table, mask, times)]
         need = lib.ttk_uplift_workspace_bytes(self.h, B, T, dt)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -78,12 +79,15 @@ def _shape_of(name, numel, dim):
     raise KeyError(name)
 
 
-class MultiStageModel(nn.Module):
-    """Drop-in for uplifting/model.py:MultiStageModel (tabletoken_mode 'dynamic', time_rotation 'new')."""
-    compute_dtype = torch.float32
+class MultiStageModel(PrecisionMixin, nn.Module):
+    """Drop-in for uplifting/model.py:MultiStageModel (tabletoken_mode 'dynamic', time_rotation 'new').
+    ``compute_dtype`` (constructor argument ``dtype``): 'fp32' (default: the reference's Linear layers are fp32 on a GPU too) or
+    'bf16' (tcgen05 tensor cores)."""
 
-    def __init__(self, dim, depth, num_heads, mode='dynamic', time_rotation='new', use_skipconnection=False):
+    def __init__(self, dim, depth, num_heads, mode='dynamic', time_rotation='new', use_skipconnection=False, dtype=None):
         super().__init__()
+        if dtype is not None:
+            self.compute_dtype = dtype
         if mode != 'dynamic' or time_rotation != 'new':
             raise NotImplementedError("only tabletoken_mode='dynamic' with time_rotation='new' (the released 'ours' model) has kernels")
         self.engine = UpliftEngine(dim, num_heads, depth, use_skipconnection)
@@ -115,7 +119,7 @@ class MultiStageModel(nn.Module):
         return self.engine.forward(ball_pos, table_pos, mask, times, self.compute_dtype)
 
 
-def get_model(name='singlestage', size='small', mode='stacked', time_rotation='new'):
+def get_model(name='singlestage', size='small', mode='stacked', time_rotation='new', dtype=None):
     """uplifting/model.py:574-603.  Only the multi-stage family is on the hot path."""
     assert time_rotation in ['old', 'new'], 'time_rotation should be either "old" or "new"'
     if name not in ('multistage', 'connectstage'):
@@ -123,6 +127,6 @@ def get_model(name='singlestage', size='small', mode='stacked', time_rotation='n
     if size not in SIZES:
         raise ValueError(f'Unknown model size {size}')
     dim, depth, heads = SIZES[size]
-    model = MultiStageModel(dim, depth, heads, mode=mode, time_rotation=time_rotation, use_skipconnection=(name == 'connectstage'))
+    model = MultiStageModel(dim, depth, heads, mode=mode, time_rotation=time_rotation, use_skipconnection=(name == 'connectstage'), dtype=dtype)
     model.time_rotation = time_rotation
     return model

@@ -10,6 +10,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
+from .precision import BF16, PrecisionMixin, lib_enum
 from .detector import _attach
 
 
@@ -52,7 +53,7 @@ class VitEngine:
             'expected (B, %d, %d, %d) float32 CUDA, got %s' % (self.in_ch, self.height, self.width, tuple(x.shape))
         x = x.contiguous()
         B = x.shape[0]
-        dt = _lib.F32 if dtype == torch.float32 else _lib.BF16
+        dt = lib_enum(dtype)
         need = lib.ttk_vit_workspace_bytes(self.h, B, dt)
         if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
             self._ws = torch.empty((max(need, 8),), dtype=torch.uint8, device=x.device)
@@ -88,12 +89,16 @@ def state_dict_layout(in_ch, tokens, out_ch):
     return out
 
 
-class _VitModule(nn.Module):
-    compute_dtype = torch.float32        # torch.bfloat16 selects the tcgen05 tensor-core path
+class _VitModule(PrecisionMixin, nn.Module):
+    """``compute_dtype`` (constructor argument ``dtype``): 'bf16' (default: the tcgen05 tensor-core path of this architecture) or
+    'fp32' (SIMT kernels, strict parity with the CPU reference at 1e-4)."""
+    default_precision = BF16
     input_layout = 'nchw'
 
-    def __init__(self, in_ch, out_ch, resolution):
+    def __init__(self, in_ch, out_ch, resolution, dtype=None):
         super().__init__()
+        if dtype is not None:
+            self.compute_dtype = dtype
         self.resolution = tuple(resolution)                       # (W, H) like the reference's config
         self.engine = VitEngine(in_ch, out_ch, self.resolution[1], self.resolution[0])
         self.in_ch = in_ch
@@ -122,10 +127,10 @@ class _VitModule(nn.Module):
 class VitPose(_VitModule):
     """Drop-in for balldetection/models/vitpose.py:VitPose (model_size 'small'): forward -> (heatmap (B,1,h,w), None)."""
 
-    def __init__(self, in_frames=3, model_size='small', pretraining=False, resolution=(1152, 640), classify_invisible=False):
+    def __init__(self, in_frames=3, model_size='small', pretraining=False, resolution=(1152, 640), classify_invisible=False, dtype=None):
         if classify_invisible or pretraining:
             raise NotImplementedError('classify_invisible / pretraining are training-time options outside the inference hot path')
-        super().__init__(3 * in_frames, 1, resolution)       # the reference builds the 'small' config whatever model_size says (:51)
+        super().__init__(3 * in_frames, 1, resolution, dtype=dtype)       # the reference builds the 'small' config whatever model_size says (:51)
 
     def forward(self, x):
         return self.heatmaps(x), None
@@ -134,9 +139,9 @@ class VitPose(_VitModule):
 class TableVitPose(_VitModule):
     """Drop-in for tabledetection/models/vitpose.py:VitPose: forward -> heatmaps (B,13,h,w)."""
 
-    def __init__(self, model_size='small', pretraining=False, resolution=(1152, 640)):
+    def __init__(self, model_size='small', pretraining=False, resolution=(1152, 640), dtype=None):
         assert not pretraining
-        super().__init__(3, 13, resolution)
+        super().__init__(3, 13, resolution, dtype=dtype)
 
     def forward(self, x):
         return self.heatmaps(x)

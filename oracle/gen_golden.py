@@ -355,6 +355,39 @@ def gen_interface(w):
                         spin=spin.numpy(), pos3d=pos3d)
 
 
+def process_trajectory_inputs(seed=700, n_frames=8, res=(160, 88)):
+    """Seeded inputs of gen_process_trajectory / tests/test_gpu_interface.py::test_process_trajectory_seams: pre-transformed
+    detector tensors as inference/inference_combined.py hands them to process_trajectory_* -- (1, T, 9, h, w) ball stacks and
+    (1, T, 3, h, w) table frames, float32 -- built with the oracle's bit-exact restatement of the reference transform."""
+    from oracle import preprocess as opre
+    rng = np.random.default_rng(seed)
+    frames = synthetic_frames(rng, n_frames, 135, 240)
+    ball = np.stack([opre.preprocess_stack(frames[i - 1:i + 2], res[0], res[1]) for i in range(1, n_frames - 1)])[None]
+    table = np.stack([opre.preprocess_stack([f], res[0], res[1]) for f in frames])[None]
+    traj = synthetic_trajectories(rng, 1)
+    return ball.astype(np.float32), table.astype(np.float32), traj
+
+
+def gen_process_trajectory(w):
+    """inference/utils.py:36-67 (ball-variant decode, chunks of 4), :105-134 (table variant, chunks of 8, threshold 0.1) and
+    :235-265 through the reference's own load_model functions (inference_balldetection.py:40-61, inference_tabledetection.py:40-57,
+    inference_uplifting.py:33-58)."""
+    write_checkpoints(w)
+    from inference import utils as iu
+    from inference.inference_balldetection import load_model as load_ball
+    from inference.inference_tabledetection import load_model as load_table
+    from inference.inference_uplifting import load_model as load_up
+    ball, table, (tb, tt, tm, tti) = process_trajectory_inputs()
+    bm, _ = load_ball(os.path.join(w, 'inference_balldetection', 'wasb', 'model.pt'))
+    tmod, _ = load_table(os.path.join(w, 'inference_tabledetection', 'hrnet', 'model.pt'))
+    um, _, mode = load_up(os.path.join(w, 'inference_uplifting', 'ours', 'model.pt'))
+    bpos = iu.process_trajectory_ball(bm, torch.from_numpy(ball))
+    tpos = iu.process_trajectory_table(tmod, torch.from_numpy(table))
+    spin, pos3d = iu.process_trajectory_uplifting(um, torch.from_numpy(tb), torch.from_numpy(tt), torch.from_numpy(tti), torch.from_numpy(tm), mode)
+    np.savez_compressed(os.path.join(GOLDEN, 'process_trajectory.npz'), seed=700, ball_pos=bpos, table_pos=tpos, spin=spin, pos3d=pos3d,
+                        transform_mode=np.array(mode))
+
+
 def write_vitpose_checkpoints(w, res=(160, 96)):
     """Reference-format ViTPose checkpoints (ball: 9 -> 1 channels, table: 3 -> 13) with oracle weights."""
     from oracle import vitpose as ov
@@ -389,7 +422,9 @@ def gen_interface_vitpose(w):
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     w = setup_reference()
-    sys.path.insert(0, ROOT)
+    sys.path.insert(1, ROOT)       # after the reference: this repository's `inference` shim package must not shadow the reference's
+    if sys.path[0] != REF:
+        raise RuntimeError('the reference must come first on sys.path')
     torch.set_num_threads(os.cpu_count())
     only = set(sys.argv[1:])
     for fn in (gen_preprocess, gen_hrnet, gen_decode, gen_uplift, gen_tails, gen_filters, gen_calibration):
@@ -406,6 +441,9 @@ def main():
     if not only or 'gen_interface' in only:
         gen_interface(w)
         print('wrote gen_interface')
+    if not only or 'gen_process_trajectory' in only:
+        gen_process_trajectory(w)
+        print('wrote gen_process_trajectory')
 
 
 if __name__ == '__main__':

@@ -137,3 +137,42 @@ def test_full_pipeline_runs(weights, golden):
     Mext[2, 3] = 5.0
     Mint = np.array([[2000.0, 0, 960, 0], [0, 2000.0, 540, 0], [0, 0, 1, 0]])
     np.testing.assert_allclose(pipe.reproject(pos3d, Mint, Mext), otl.reproject(pos3d, Mint, Mext), rtol=1e-12)
+
+
+def test_process_trajectory_seams(weights, golden):
+    """inference/utils.py:36-67, 105-134, 235-265 and the load_model functions under the reference's module paths, against the
+    reference's own outputs (tests/golden/process_trajectory.npz, oracle/gen_golden.py:gen_process_trajectory).
+    process_trajectory_ball is the one caller of the BALL-variant decode."""
+    from inference import utils as iu
+    from inference.inference_balldetection import load_model as load_ball
+    from inference.inference_tabledetection import load_model as load_table
+    from inference.inference_uplifting import load_model as load_up
+    from oracle.gen_golden import process_trajectory_inputs
+    g = golden('process_trajectory')
+    ball, table, (tb, tt, tm, tti) = process_trajectory_inputs(int(g['seed']))
+    bm, btf = load_ball(os.path.join(weights, 'inference_balldetection', 'wasb', 'model.pt'))
+    tmod, _ = load_table(os.path.join(weights, 'inference_tabledetection', 'hrnet', 'model.pt'))
+    um, _, mode = load_up(os.path.join(weights, 'inference_uplifting', 'ours', 'model.pt'))
+    assert mode == str(g['transform_mode']) and callable(btf)
+    bm.compute_dtype = tmod.compute_dtype = 'fp32'            # strict parity path for the 1e-3 px comparison
+    bpos = iu.process_trajectory_ball(bm, torch.from_numpy(ball))
+    assert bpos.shape == g['ball_pos'].shape and bpos.dtype == np.float64 and np.all(bpos[:, 2] == 1.0)
+    np.testing.assert_allclose(bpos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=2e-3)
+    tpos = iu.process_trajectory_table(tmod, torch.from_numpy(table))
+    assert tpos.shape == g['table_pos'].shape == (8, 13, 3)
+    err = np.abs(tpos[..., :2] - g['table_pos'][..., :2]).max(axis=-1)
+    assert np.mean(err < 2e-3) >= 0.95, err
+    spin, pos3d = iu.process_trajectory_uplifting(um, *(torch.from_numpy(a) for a in (tb, tt, tti, tm)), mode)
+    assert isinstance(spin, np.ndarray) and spin.shape == (3,) and pos3d.shape == g['pos3d'].shape
+    np.testing.assert_allclose(pos3d, g['pos3d'], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(spin, g['spin'], rtol=1e-3, atol=1e-3)
+    # the ball variant differs from the table variant the interface classes use (different sigma bounds): both are live
+    hm, _ = bm(torch.from_numpy(ball[0, :2]).cuda())
+    a, b = iu.extract_position_ball(hm, 1920, 1080), iu.extract_position_table(hm, 1920, 1080)[:, 0]
+    assert a.shape == b.shape == (2, 3)
+    with pytest.raises(ValueError):
+        iu.extract_position_table(hm[:, 0], 1920, 1080)
+    # default arithmetic class (TF32) through the same seam
+    bm.compute_dtype = 'tf32'
+    bpos_tf = iu.process_trajectory_ball(bm, torch.from_numpy(ball))
+    assert bpos_tf.shape == bpos.shape and np.isfinite(bpos_tf).all()      # output parity of this path: tests/test_gpu_output_parity.py

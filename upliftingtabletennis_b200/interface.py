@@ -266,10 +266,10 @@ class _Detector:
 
     @staticmethod
     def _frame_key(im):
-        """Identity of a host frame: its memory (address, shape, strides), for numpy arrays and torch CPU tensors alike."""
+        """Identity of a host frame: its memory (address, shape, strides, element type), for numpy arrays and torch CPU tensors alike."""
         if isinstance(im, torch.Tensor):
-            return (im.data_ptr(), tuple(im.shape), tuple(im.stride()))
-        return (im.__array_interface__['data'][0], tuple(im.shape), tuple(im.strides))
+            return (im.data_ptr(), tuple(im.shape), tuple(im.stride()), str(im.dtype))
+        return (im.__array_interface__['data'][0], tuple(im.shape), tuple(im.strides), im.dtype.str)
 
     @staticmethod
     def _pass_plan(n_stacks, chunk, streaming, ramp=(4, 12)):
@@ -283,10 +283,15 @@ class _Detector:
             s0 += ns
         return bounds
 
+    stage_slots = 12               # pinned staging ring for numpy frames: 12 x 6.2 MB at 1080p, whatever the clip length
+
     def _upload(self, images, dev):
-        """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames are staged through a cached
-        pinned buffer; torch CPU tensors (e.g. already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA
-        tensor, per input image its row in it, and [(frame index, event)] marking how far the copy has got."""
+        """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames (pageable memory, what cv2 delivers) go
+        through a small ring of pinned staging slots: host threads copy frame i into slot i % stage_slots (numpy releases the GIL for
+        it) as soon as the transfer that last used the slot has finished (one event per slot -- no stream-wide synchronisation), and
+        the slot is sent as soon as it is staged, so the host memcpy pipelines with the PCIe transfer.  torch CPU tensors (e.g.
+        already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA tensor, per input image its row in it, and
+        [(frame index, event)] marking how far the copy has got."""
         slots, order, uniq = {}, [], []
         for im in images:
             # frames are recognised by their memory, not by the Python object: clip[i] creates a new view object on every indexing,
@@ -296,41 +301,56 @@ class _Detector:
                 slots[k] = len(uniq)
                 uniq.append(im)
             order.append(slots[k])
-        shape = (len(uniq),) + tuple(uniq[0].shape)
-        out = torch.empty(shape, dtype=torch.uint8, device=dev)
+        fshape = tuple(uniq[0].shape)
+        for u in uniq:
+            if tuple(u.shape) != fshape or len(fshape) != 3 or fshape[2] != 3 or (u.dtype != torch.uint8 if isinstance(u, torch.Tensor) else u.dtype != np.uint8):
+                raise ValueError('frames must be uint8 arrays of one common shape (H, W, 3); got %s %s (first frame %s)' % (tuple(u.shape), u.dtype, fshape))
+        n = len(uniq)
+        out = torch.empty((n,) + fshape, dtype=torch.uint8, device=dev)
         all_torch = all(isinstance(u, torch.Tensor) for u in uniq)
-        view = None
-        if not all_torch:
-            stage = getattr(self, '_stage', None)
-            if stage is None or stage.shape[1:] != shape[1:] or stage.shape[0] < shape[0]:
-                stage = self._stage = torch.empty(shape, dtype=torch.uint8).pin_memory()
-            view = stage.numpy()
         copy_stream = getattr(self, '_copy_stream', None)
         if copy_stream is None:
             copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
-        staged = None
-        if not all_torch:
-            # numpy frames (what cv2 delivers): the copies into the pinned staging buffer run on a few host threads (numpy releases the
-            # GIL for them) and frame i is sent as soon as it is staged, so the host memcpy pipelines with the PCIe transfer
-            copy_stream.synchronize()           # an earlier call's transfers have left the staging buffer
-
-            def stage_one(i):
-                u = uniq[i]
-                view[i] = u.numpy() if isinstance(u, torch.Tensor) else u
-            staged = [_staging_pool().submit(stage_one, i) for i in range(len(uniq))]
         copy_stream.wait_stream(torch.cuda.current_stream())
         ready = []
-        with torch.cuda.stream(copy_stream):
-            for i, u in enumerate(uniq):
-                if all_torch:
+
+        def mark(i):
+            if i % 2 == 1 or i == n - 1:      # an event every other frame: the first pass (4 stacks) starts after 6 frames
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                ready.append((i, ev))
+
+        if all_torch:
+            with torch.cuda.stream(copy_stream):
+                for i, u in enumerate(uniq):
                     out[i].copy_(u, non_blocking=True)
-                else:
-                    staged[i].result()
-                    out[i].copy_(self._stage[i], non_blocking=True)
-                if i % 2 == 1 or i == len(uniq) - 1:      # an event every other frame: the first pass (4 stacks) starts after 6 frames
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    ready.append((i, ev))
+                    mark(i)
+            return out, order, ready
+        ns = self.stage_slots
+        stage = getattr(self, '_stage', None)
+        if stage is None or tuple(stage.shape[1:]) != fshape:
+            stage = self._stage = torch.empty((ns,) + fshape, dtype=torch.uint8).pin_memory()
+            self._stage_ev = [None] * ns
+        view, slot_ev = stage.numpy(), self._stage_ev
+
+        def stage_one(i, ev):
+            if ev is not None:
+                ev.synchronize()            # the transfer that last read this slot (possibly of an earlier call) has finished
+            u = uniq[i]
+            view[i % ns] = u.numpy() if isinstance(u, torch.Tensor) else u
+
+        pool = _staging_pool()
+        staged = {i: pool.submit(stage_one, i, slot_ev[i % ns]) for i in range(min(ns, n))}
+        with torch.cuda.stream(copy_stream):
+            for i in range(n):
+                staged.pop(i).result()
+                out[i].copy_(stage[i % ns], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                slot_ev[i % ns] = ev
+                if i + ns < n:
+                    staged[i + ns] = pool.submit(stage_one, i + ns, ev)
+                mark(i)
         return out, order, ready
 
 

@@ -151,6 +151,51 @@ __global__ void __launch_bounds__(128) mma_kernel(const uint32_t* A, const uint3
   if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
+// ---- part 4: like the convolution's issue loop: every MMA reads a DIFFERENT A slab (start address moved by whole pixel rows), rows of
+// ROWB bytes (32 / 64 / 128-byte swizzle), B = N weight rows of the same width ----
+template <int TF32>
+__global__ void __launch_bounds__(128) mma_shift_kernel(int N, int rowb, int reps, int distinct, long long* clk) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  uint8_t* sA = smem;                    // 1400 pixel rows
+  uint8_t* sB = smem + 180 * 1024;       // N rows
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (180 * 1024 + 32 * 1024) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f800000u, 0x3f800000u, 0x3f800000u, 0x3f800000u);
+  if (tid == 0) mbar_init(&bar, 1);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (tid < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, N, TF32 ? 2 : 1);
+    const uint32_t layout = rowb == 32 ? 6u : rowb == 64 ? 4u : 2u;
+    const int ksteps = rowb / 32;
+    const long long t0 = clock64();
+    int n = 0;
+    for (int rep = 0; rep < reps; ++rep)
+      for (int j = 0; j < 16; ++j)
+        for (int k = 0; k < ksteps; ++k, ++n) {
+          const uint32_t arow = smem_u32(sA) + (distinct ? (j * 65 + (rep & 3)) * rowb : 0) + k * 32;
+          umma<TF32>(tmem, make_desc(arow, 8 * rowb, layout), make_desc(smem_u32(sB) + k * 32, 8 * rowb, layout), idesc, n ? 1u : 0u);
+        }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    mbar_wait(&bar, 0);
+    clk[0] = clock64() - t0;
+    clk[1] = n;
+  }
+  __syncthreads();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
@@ -259,6 +304,22 @@ int main() {
         CK(cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost));
         printf("mma %s M128 N=%-3d K=%d: %.1f clk per MMA (%d MMAs back to back)\n", tf ? "tf32" : "bf16", n, tf ? 8 : 16, (double)c / (reps * 4), reps * 4);
       }
+    // ---- part 4 ----
+    CK(cudaFuncSetAttribute(mma_shift_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024));
+    CK(cudaFuncSetAttribute(mma_shift_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 214 * 1024));
+    long long* dclk2;
+    CK(cudaMalloc(&dclk2, 16));
+    for (int tf = 1; tf >= 0; --tf)
+      for (int rowb : {32, 64, 128})
+        for (int distinct = 0; distinct < 2; ++distinct)
+          for (int n : {16, 48, 96, 144, 192, 256}) {
+            if (tf) mma_shift_kernel<1><<<1, 128, 214 * 1024>>>(n, rowb, 200, distinct, dclk2);
+            else mma_shift_kernel<0><<<1, 128, 214 * 1024>>>(n, rowb, 200, distinct, dclk2);
+            CK(cudaDeviceSynchronize());
+            long long c[2];
+            CK(cudaMemcpy(c, dclk2, 16, cudaMemcpyDeviceToHost));
+            printf("issue loop %s rows of %3d B, %s A slabs, N=%-3d: %.1f clk per MMA\n", tf ? "tf32" : "bf16", rowb, distinct ? "distinct" : "one    ", n, (double)c[0] / c[1]);
+          }
   }
   return 0;
 }

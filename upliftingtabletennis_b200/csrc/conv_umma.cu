@@ -89,6 +89,9 @@ struct Cfg {
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static constexpr int GCOLS = ACC_COLS < (ESZ == 2 ? 64 : 32) ? ACC_COLS : (ESZ == 2 ? 64 : 32);     // accumulator columns fetched per TMEM wait
+  // software-pipelined epilogue (see the kernel); not with TMA-staged residual tiles, whose shared-memory reads have no latency to hide
+  // (the full-resolution 16 -> 16 layers ran at 6.5 TB/s without it, 5.7 TB/s with it)
+  static constexpr bool PIPE = ESZ == 4 && S == 1 && !RB && ACC_COLS / GCOLS >= 2;
   static_assert(ESZ == 2 || ESZ == 4, "bf16 or tf32-in-fp32 elements");
   static_assert(ACC_COLS % GCOLS == 0, "the epilogue drains whole groups of accumulator columns");
   static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "a K-chunk is one 32/64/128-byte swizzled row");
@@ -200,24 +203,33 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t wbase = smem_u32(sW);
-      auto issue = [](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc) {      // every MMA accumulates (the epilogue zeroes what it drains)
-        if (ESZ == 2) mma(d, da, db, idesc, 1u);
-        else mma_tf32(d, da, db, idesc, 1u);
+    // The WHOLE warp walks the loops with warp-uniform values and one elected lane issues: addresses, descriptors and the TMEM
+    // column then live in uniform registers and consecutive tcgen05.mma are 1-3 instructions apart.  With `if (lane == 0)` around
+    // the loops the compiler treated every operand as divergent and wrapped each MMA in an ELECT / R2UR.BROADCAST loop (16
+    // instructions, ~80 clk per MMA against the tensor pipe's 45 clk for a thin one -- the thin layers were issue bound).
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const bool leader = elect_one();
+      const uint32_t wbase = smem_u32(sW) >> 4;
+      auto issue = [leader](uint32_t d, uint64_t da, uint64_t db, uint32_t idesc) {      // every MMA accumulates (the epilogue zeroes what it drains)
+        if (leader) {
+          if (ESZ == 2) mma(d, da, db, idesc, 1u);
+          else mma_tf32(d, da, db, idesc, 1u);
+        }
       };
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph);      // accumulators drained and zeroed by the epilogue
         fence_after();
-        const uint32_t d_acc = tmem + acc * C::ACC_COLS;
+        const uint32_t d_acc = tmem_u + acc * C::ACC_COLS;
         for (int u = 0; u < C::UNITS; ++u, ++it) {
           const int kc = u / C::NPY, py = u % C::NPY;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           fence_after();
-          const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES);
+          const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES) >> 4;      // 16-byte units from here on (make_desc16)
+          constexpr uint32_t RB16 = C::ROWB / 16;
           if (C::FUSE) {
             // input (halo) row hr = yi + 1 feeds output rows yo = yi + 1 - ky; row yo lives in column block R-1-yo
 #pragma unroll 1
@@ -229,11 +241,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
               const uint32_t d_tmem = d_acc + (R - 2 - yi + k0) * COUT;
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
-                const uint32_t arow = abase + (hr * C::TW + kx) * C::ROWB;
-                const uint32_t brow = wbase + (((kc * 3 + kx) * 3 + k0) * COUT) * C::ROWB;
+                const uint32_t arow = abase + (hr * C::TW + kx) * RB16;
+                const uint32_t brow = wbase + (((kc * 3 + kx) * 3 + k0) * COUT) * RB16;
 #pragma unroll
                 for (int ks = 0; ks < C::KSTEPS; ++ks)
-                  issue(d_tmem, make_desc(arow + ks * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + ks * 32, 8 * C::ROWB, C::LAYOUT), idesc);
+                  issue(d_tmem, make_desc16<8 * C::ROWB, C::LAYOUT>(arow + ks * 2), make_desc16<8 * C::ROWB, C::LAYOUT>(brow + ks * 2), idesc);
               }
             }
           } else {
@@ -246,22 +258,23 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
                 const int ky = tap / KS, kx = tap % KS;
                 uint32_t arow;
                 if (S == 1) {
-                  arow = abase + ((r + ky) * C::TW + kx) * C::ROWB;
+                  arow = abase + ((r + ky) * C::TW + kx) * RB16;
                 } else {
                   if ((ky != 1 ? 1 : 0) != py) continue;     // this unit holds the other row parity
                   const int px = kx != 1 ? 1 : 0;
-                  arow = abase + px * C::BOX_AL + ((r + (ky == 2 ? 1 : 0)) * C::TW + (kx == 2 ? 1 : 0)) * C::ROWB;
+                  arow = abase + px * (C::BOX_AL / 16) + ((r + (ky == 2 ? 1 : 0)) * C::TW + (kx == 2 ? 1 : 0)) * RB16;
                 }
-                const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * C::ROWB;
+                const uint32_t brow = wbase + ((tap * C::NKC + kc) * COUT) * RB16;
 #pragma unroll
                 for (int ks = 0; ks < C::KSTEPS; ++ks)
-                  issue(d_tmem, make_desc(arow + ks * 32, 8 * C::ROWB, C::LAYOUT), make_desc(brow + ks * 32, 8 * C::ROWB, C::LAYOUT), idesc);
+                  issue(d_tmem, make_desc16<8 * C::ROWB, C::LAYOUT>(arow + ks * 2), make_desc16<8 * C::ROWB, C::LAYOUT>(brow + ks * 2), idesc);
               }
             }
           }
-          commit(bar_empty + 8 * s);          // smem stage reusable once these MMAs have read it
+          if (leader) commit(bar_empty + 8 * s);          // smem stage reusable once these MMAs have read it
         }
-        commit(bar_tfull + 8 * acc);          // accumulators complete
+        if (leader) commit(bar_tfull + 8 * acc);          // accumulators complete
+        __syncwarp();
       }
     }
   } else {
@@ -302,6 +315,73 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
       if (res_tma) mbar_wait(bar_rfull + 8 * acc, aph);
       mbar_wait(bar_tfull + 8 * acc, aph);
       fence_after();
+      if constexpr (C::PIPE) {
+        // Software-pipelined drain (TF32 stride-1 layers, at most one residual): the TMEM load and the residual loads of column
+        // group g + 1 are in flight while group g is added up and stored, so neither latency is exposed per group (stem conv1 ran at
+        // 59 % of the HBM rate waiting for one tcgen05.ld at a time; residuals read from global memory cost ~1 us per group).
+        constexpr int G = C::ACC_COLS / GCOLS;
+        uint32_t v[2][NSUB][16], rv[2][NSUB][RW];
+        const int nres = a.nres;
+        const uint32_t tbase = lane_base + acc * C::ACC_COLS;
+        auto fetch = [&](int g, uint32_t (&vv)[NSUB][16], uint32_t (&rr)[NSUB][RW]) {
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb) tmem_ld16(tbase + g * GCOLS + sb * 16, vv[sb]);
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb) {
+            const int col = g * GCOLS + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
+            const int oy = ty * R + r;
+#pragma unroll
+            for (int j = 0; j < RW; ++j) rr[sb][j] = 0;
+            if (nres > 0) {
+              if (res_tma) {
+                const uint32_t row = smem_u32(sR + (acc * C::NRB + c0 / C::CB) * C::RBOX_BYTES) + (r * BW + m) * C::RROWB;
+                const uint32_t swz = ((row >> 7) & C::RSWZ) << 4;
+#pragma unroll
+                for (int i = 0; i < RW / 4; ++i) lds128((row + (c0 % C::CB) * ESZ + 16 * i) ^ swz, &rr[sb][4 * i]);
+              } else if (ox < a.w_img && oy < a.h) {
+                const int sh = a.rsh[0];
+                const char* rp = (const char*)a.res[0] +
+                                 ((((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off + c0) * ESZ;
+#pragma unroll
+                for (int i = 0; i < RW / 8; ++i) ldg256(rp + 32 * i, &rr[sb][8 * i]);
+              }
+            }
+          }
+        };
+        fetch(0, v[0], rv[0]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) tmem_zero16(tbase + sb * 16);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (g + 1 < G) fetch(g + 1, v[(g + 1) & 1], rv[(g + 1) & 1]);
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb) {
+            const int col = g * GCOLS + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
+            const int oy = ty * R + r;
+            if (!(ox < a.w_img && oy < a.h)) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[g & 1][sb][j]) + sBias[c0 + j];
+            if (nres > 0) add_words(f, rv[g & 1][sb]);
+            if (a.relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            char* op = (char*)a.out + ((((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0) * ESZ;
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(f[j]);
+            stg256(op, o);
+            stg256(op + 32, o + 8);
+          }
+          if (g + 1 < G) {
+            tmem_wait_ld();
+#pragma unroll
+            for (int sb = 0; sb < NSUB; ++sb) tmem_zero16(tbase + (g + 1) * GCOLS + sb * 16);     // leave the columns zeroed for the next tile
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int g0 = 0; g0 < C::ACC_COLS; g0 += GCOLS) {
         uint32_t v[NSUB][16];
@@ -386,6 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           }
         }
       }
+      }
       tmem_wait_st();
       fence_before();
       __syncwarp();
@@ -415,6 +496,7 @@ int kc_of(const TtkConv& cv, int esz) {
     if (cv.k == 3 && cv.stride == 2 && cv.cin_p >= 64) return 32;
     return cv.cin_p < 64 ? cv.cin_p : 64;
   }
+  if (cv.k == 3 && cv.stride == 1 && cv.cin_p == 128 && cv.cout_p == 16) return 16;      // transition1.0: 64-byte rows fill faster than 32-byte ones
   if (cv.k == 3 && cv.cin_p >= 64) return 8;
   if (cv.k == 3 && cv.stride == 2 && cv.cin_p == 32 && cv.cout_p == 128) return 8;
   if (cv.k == 3) return 16;
@@ -671,9 +753,9 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   TTK_UMMA32(3, 1, 64, 64, 4, 3, 0, 8)       // stem conv2, quarter-resolution branch: 147 KB of weights + three 25 KB boxes
   if (k == 3 && s == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0, 16, 4>(cv, a, st);
   TTK_UMMA32(3, 1, 32, 32, 4, 3, 0, 16)      // half-resolution branch (residual read from global memory: no room for staged tiles)
-  if (k == 3 && s == 1 && ci == 16 && co == 16 && a.nres == 0) return launch<3, 1, 16, 16, 8, 2, 0, 16, 4>(cv, a, st);
+  if (k == 3 && s == 1 && ci == 16 && co == 16 && a.nres == 0) return launch<3, 1, 16, 16, 8, 2, 0, 16, 4>(cv, a, st);     // taller tile (R = 4 with four stages: 0.77 vs 0.66 ms)
   TTK_UMMA32(3, 1, 16, 16, 4, 3, 1, 16)      // full-resolution branch, residual tiles staged by TMA
-  TTK_UMMA32(3, 1, 128, 16, 8, 3, 0, 8)      // transition1.0
+  TTK_UMMA32(3, 1, 128, 16, 4, 3, 0, 16)     // transition1.0: 8-channel chunks (32-byte rows, R = 8) were bound by TMA's fill rate: 2.75 ms per 16 images
   TTK_UMMA32(3, 1, 128, 32, 4, 3, 0, 8)      // eighth-resolution branch (128 -> 128 as four 32-channel output slices)
   // 3x3 stride 2
   TTK_UMMA32(3, 2, 128, 32, 2, 3, 0, 8)

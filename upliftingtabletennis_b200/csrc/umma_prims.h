@@ -68,6 +68,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes,
   d |= (uint64_t)(layout & 7) << 61;
   return d;
 }
+// The same descriptor from the start address in 16-byte units (shared-memory addresses are below 256 KB, so the 14-bit field cannot
+// overflow): one add per descriptor in an issue loop that steps through a staged tile.
+template <uint32_t SBO_BYTES, uint32_t LAYOUT>
+__device__ __forceinline__ uint64_t make_desc16(uint32_t addr16) {
+  constexpr uint32_t hi = ((SBO_BYTES >> 4) & 0x3FFF) | (1u << 14) | ((LAYOUT & 7) << 29);
+  return ((uint64_t)hi << 32) | (uint64_t)(addr16 + 0x10000u);
+}
 // kind::f16 instruction descriptor: D f32, A/B bf16, K-major unless the transpose bit is set (bit 15: A, bit 16: B MN-major)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major = 0) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -90,6 +97,12 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (the same one on every call): the issuer of tcgen05.mma / commit
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

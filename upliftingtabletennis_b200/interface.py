@@ -188,6 +188,20 @@ def _uplifting_transform(ball_coords, table_coords, times):
     return b, t, ti, m
 
 
+class _nvtx:
+    """NVTX range around a stage of the path (visible in Nsight Systems / ncu --nvtx): `with _nvtx('ttk:decode'): ...`."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
 _POOL = None
 
 
@@ -195,7 +209,7 @@ def _staging_pool():
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix='ttk-stage')
+        _POOL = ThreadPoolExecutor(max_workers=max(4, min(8, (os.cpu_count() or 8) // 2)), thread_name_prefix='ttk-stage')
     return _POOL
 
 
@@ -226,11 +240,15 @@ class _Detector:
                 main.wait_event(ready[waited][1])
                 waited += 1
             if getattr(self.model, 'input_layout', 'nhwc16') == 'nchw':       # ViTPose: the reference's NCHW float32 tensor
-                x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nchw')
-                hm = self.model.heatmaps(x)
+                with _nvtx('ttk:preprocess'):
+                    x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nchw')
+                with _nvtx('ttk:heatmap_network'):
+                    hm = self.model.heatmaps(x)
             else:
-                x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
-                hm = self.model.heatmaps_from_nhwc16(x, prec)
+                with _nvtx('ttk:preprocess'):
+                    x = ops.preprocess_stacks(frames_u8[f0:f_hi + 1], self.frames_per_stack, stack_stride, ns, w, h, layout='nhwc16', dtype=dt)
+                with _nvtx('ttk:heatmap_network'):
+                    hm = self.model.heatmaps_from_nhwc16(x, prec)
             # interface.py:116,169 decode with the TABLE variant of extract_position_torch_gaussian.  It runs on a second stream:
             # the per-map fit is a latency-bound kernel of one warp per map (~0.3 ms whatever the number of maps) that fits beside the
             # persistent convolution CTAs, so the decode of pass i hides under the network of pass i + 1.
@@ -239,7 +257,7 @@ class _Detector:
                 side = self._decode_stream = torch.cuda.Stream(device=hm.device)
             done = torch.cuda.Event()
             done.record(main)
-            with torch.cuda.stream(side):
+            with torch.cuda.stream(side), _nvtx('ttk:decode'):
                 side.wait_event(done)
                 p = ops.decode_heatmaps(hm, self.resolution[0], self.resolution[1], 'table')
             hm.record_stream(side)
@@ -283,7 +301,7 @@ class _Detector:
             s0 += ns
         return bounds
 
-    stage_slots = 12               # pinned staging ring for numpy frames: 12 x 6.2 MB at 1080p, whatever the clip length
+    stage_slots = 16               # pinned staging ring for numpy frames: 16 x 6.2 MB at 1080p, whatever the clip length
 
     def _upload(self, images, dev):
         """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames (pageable memory, what cv2 delivers) go
@@ -292,6 +310,13 @@ class _Detector:
         the slot is sent as soon as it is staged, so the host memcpy pipelines with the PCIe transfer.  torch CPU tensors (e.g.
         already pinned) are copied directly.  Returns the (n, H, W, 3) uint8 CUDA tensor, per input image its row in it, and
         [(frame index, event)] marking how far the copy has got."""
+        torch.cuda.nvtx.range_push('ttk:upload')
+        try:
+            return self._upload_frames(images, dev)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _upload_frames(self, images, dev):
         slots, order, uniq = {}, [], []
         for im in images:
             # frames are recognised by their memory, not by the Python object: clip[i] creates a new view object on every indexing,
@@ -503,10 +528,12 @@ class TableTennisPipeline:
             ball_xy, _, times_ball, offsets = ops.filter_ball(ball_positions, ball_positions_aux, float(fps))
             table_keypoints = self.table_detector._run(frames, 1, n, False, None)[0]
             table_keypoints_aux = self.table_detector_aux._run(frames, 1, n, False, None)[0]
-        filtered_table_keypoints = ops.filter_table(table_keypoints, table_keypoints_aux)
-        ball_coords, table_coords, times, mask = ops.trajectory_pack(ball_xy, times_ball, offsets, filtered_table_keypoints[None],
-                                                                    SEQ_LEN, WIDTH, HEIGHT)
-        return self.uplifting_model.predict_without_normalization(ball_coords, table_coords, mask, times)
+        with _nvtx('ttk:filters_pack'):
+            filtered_table_keypoints = ops.filter_table(table_keypoints, table_keypoints_aux)
+            ball_coords, table_coords, times, mask = ops.trajectory_pack(ball_xy, times_ball, offsets, filtered_table_keypoints[None],
+                                                                        SEQ_LEN, WIDTH, HEIGHT)
+        with _nvtx('ttk:uplift'):
+            return self.uplifting_model.predict_without_normalization(ball_coords, table_coords, mask, times)
 
     def calibrate_camera(self, keypoints):
         return calibrate_camera(keypoints)

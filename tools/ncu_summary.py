@@ -7,7 +7,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-rep, tag = sys.argv[1], sys.argv[2]
+rep, tag = sys.argv[1], sys.argv[2]                        # report file, output tag
+prec = sys.argv[3] if len(sys.argv) > 3 else 'bf16'          # key prefix in ncu_traffic.json: bench.py looks up '<dtype>/<conv name>'
+images = int(sys.argv[4]) if len(sys.argv) > 4 else 4        # images per launch of the profiled pass
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -27,11 +29,12 @@ with open(out, 'w') as f:
 names = ['model.conv1', 'model.conv2', 'model.layer1.0.conv1', 'model.layer1.0.conv2', 'model.layer1.0.conv3', 'model.transition1.0.0',
          'model.transition1.1.0.0']
 scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
-traffic = {}
+tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
 ir, iw, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
 for n, d in zip(names, data):
-    traffic[n] = {'dram_bytes_per_launch': float(d[ir]) * scale[units[ir]] + float(d[iw]) * scale[units[iw]],
-                  'duration_us_under_ncu': float(d[it]), 'kernel': d[hdr.index('Kernel Name')][:90], 'images_per_launch': 4}
-json.dump(traffic, open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'), 'w'), indent=1)
+    traffic['%s/%s' % (prec, n)] = {'dram_bytes_per_launch': float(d[ir]) * scale[units[ir]] + float(d[iw]) * scale[units[iw]],
+                  'duration_us_under_ncu': float(d[it]), 'kernel': d[hdr.index('Kernel Name')][:90], 'images_per_launch': images}
+json.dump(traffic, open(tpath, 'w'), indent=1)
 print(open(out).read()[:3000])
 print(json.dumps(traffic, indent=1))

@@ -24,8 +24,11 @@
 #include <cuda.h>
 
 #include "uplift.h"
+#include "umma_prims.h"
 
 namespace {
+
+using namespace umma;      // mbarriers, TMA loads, descriptors, tcgen05 wrappers shared by all tensor-core kernels
 
 constexpr int D = 128, HEADS = 4, HD = 32, NF = 16, NTAB = 13;
 constexpr int NG = 4;                                // warp groups: warps 4g .. 4g+3 cover the four TMEM lane quarters
@@ -39,62 +42,12 @@ constexpr int LAYER_ROWS = 768;                    // qkv 384 | proj 128 | fc1 1
 
 enum { MODE_POS = 0, MODE_TEMPORAL = 1, MODE_SECOND = 2 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x4000;\n\t"
-      "@p bra LAB_DONE;\n\t"
-      "bra LAB_WAIT;\n\t"
-      "LAB_DONE:\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-               "l"(map), "r"(bar), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;      // 8 rows x 128 B between core-matrix groups
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;       // 8 rows x 64 B
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                // SWIZZLE_64B
-  return d;
-}
-constexpr uint32_t IDESC_128x32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-constexpr uint32_t IDESC_128x128 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc = IDESC_128x128) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t addr) { return make_desc(addr, 1024, 2); }     // 8 rows x 128 B between core-matrix groups
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t addr) { return make_desc(addr, 512, 4); }       // 8 rows x 64 B
+constexpr uint32_t IDESC_128x32 = make_idesc(128, 32), IDESC_128x128 = make_idesc(128, 128);
+__device__ __forceinline__ void tc_fence_before() { fence_before(); }
+__device__ __forceinline__ void tc_fence_after() { fence_after(); }
+__device__ __forceinline__ void proxy_fence() { fence_async_smem(); }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t* u = reinterpret_cast<uint32_t*>(v);
@@ -234,6 +187,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  // MMA issue: warp 0 walks the issue code with warp-uniform operands (TMEM base broadcast, addresses from shared-memory symbols) and
+  // its elected lane executes tcgen05.mma / commit / the TMA loads.  Under `if (tid == 0)` the compiler wrapped every MMA in an
+  // ELECT / R2UR loop (16 instructions each) -- issue latency that sat on each of the nine MMA round trips of a layer.
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const bool issuer = elect_one() && warp == 0;
+  auto issue_mma = [&](uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
+    if (issuer) mma(tmem_d, da, db, idesc, accumulate);
+  };
   const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
   constexpr uint32_t COL_X = 384, COL_S = 0, COL_O = 128, COL_PROJ = 256, COL_FC1 = 0, COL_FC2 = 128;
   const int k_lo = g_row * SSTRIDE, k_hi = k_lo + S;        // this row's key block
@@ -259,8 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   // fc2 of the last table-token layer (the layer before layer_first); ring slot and mbarrier parity follow gchunk + 3.
   constexpr bool TAIL = MODE == MODE_TEMPORAL, HEADLESS_LAST = MODE == MODE_POS;
   const int total_chunks = p.n_layers * 6;
-  auto issue_load = [&](int gchunk) {           // thread 0 only
-    if (gchunk >= total_chunks) return;
+  auto issue_load = [&](int gchunk) {           // warp 0; the elected lane issues
+    if (gchunk >= total_chunks || !issuer) return;
     const int slot = (gchunk + 3) % 3;
     const int wrow = gchunk >= 0 ? (p.layer_first + gchunk / 6) * LAYER_ROWS + (gchunk % 6) * 128 : (p.layer_first - 1) * LAYER_ROWS + (6 + gchunk) * 128;
     mbar_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
@@ -268,7 +229,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     tma_load_2d(dst, &wmap, bar_full + 8 * slot, 0, wrow);
     tma_load_2d(dst + 16384, &wmap, bar_full + 8 * slot, 64, wrow);
   };
-  auto gemm = [&](int gchunk, uint32_t a_base, uint32_t col) {   // thread 0 only: D[128 x 128] at TMEM column `col`
+  auto gemm = [&](int gchunk, uint32_t a_base, uint32_t col) {   // warp 0: D[128 x 128] at TMEM column `col`
     const int slot = (gchunk + 3) % 3;
     mbar_wait(bar_full + 8 * slot, ((gchunk + (TAIL ? 3 : 0)) / 3) & 1);
     tc_fence_after();
@@ -277,8 +238,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     for (int kh = 0; kh < 2; ++kh)
 #pragma unroll
       for (int k16 = 0; k16 < 4; ++k16)
-        umma(tmem + col, make_desc_sw128(a_base + kh * 16384 + k16 * 32), make_desc_sw128(b_base + kh * 16384 + k16 * 32),
-             (kh | k16) != 0 ? 1u : 0u);
+        issue_mma(tmem_u + col, make_desc_sw128(a_base + kh * 16384 + k16 * 32), make_desc_sw128(b_base + kh * 16384 + k16 * 32),
+                  (kh | k16) != 0 ? 1u : 0u, IDESC_128x128);
   };
   uint32_t mma_phase = 0;
   auto mma_sync = [&]() {                       // all threads: wait for the committed MMAs
@@ -376,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     if (q_live && key < k_hi && sMask[key] == 0.f) key_bits |= 1u << j;
   }
 
-  if (tid == 0) {
+  if (warp == 0) {
     issue_load(TAIL ? -3 : 0);
     issue_load(TAIL ? -2 : 1);
     issue_load(TAIL ? -1 : 2);
@@ -422,35 +383,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       proxy_fence();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         gemm(-3, smem_u32(sA), COL_PROJ);
-        umma_commit(bar_mma);
+        if (issuer) commit(bar_mma);
       }
       mma_sync();
-      if (tid == 0) issue_load(0);
+      if (warp == 0) issue_load(0);
       residual_ln(true, COL_PROJ, nullptr, tw.ln2w, tw.ln2b, true, nullptr);
       proxy_fence();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         gemm(-2, smem_u32(sA), COL_FC1);
-        umma_commit(bar_mma);
+        if (issuer) commit(bar_mma);
       }
       mma_sync();
-      if (tid == 0) issue_load(1);
+      if (warp == 0) issue_load(1);
       relu_fc1(tw.fc1b);
       proxy_fence();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         gemm(-1, smem_u32(sQh), COL_FC2);
-        umma_commit(bar_mma);
+        if (issuer) commit(bar_mma);
       }
       mma_sync();
-      if (tid == 0) issue_load(2);
+      if (warp == 0) issue_load(2);
       residual_ln(true, COL_FC2, tw.fc2b, p.layers[0].ln1w, p.layers[0].ln1b, true, nullptr);
     }
   }
@@ -463,16 +424,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       gemm(g0 + 0, smem_u32(sA), 0);
       gemm(g0 + 1, smem_u32(sA), 128);
       gemm(g0 + 2, smem_u32(sA), 256);
-      umma_commit(bar_mma);
+      if (issuer) commit(bar_mma);
     }
     mma_sync();
     const bool headless = HEADLESS_LAST && l + 1 == p.n_layers;     // last table-token layer: stops after the attention (see TcParams)
-    if (tid == 0 && !headless) {                  // proj, fc1; ring slot 2 stays empty (scratch) until the attention is done
+    if (warp == 0 && !headless) {                  // proj, fc1; ring slot 2 stays empty (scratch) until the attention is done
       issue_load(g0 + 3);
       issue_load(g0 + 4);
     }
@@ -511,18 +472,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       }
     }
     // ---- attention per head on the tensor cores ---------------------------------------------------
-    auto issue_scores = [&](int hh) {             // thread 0 only: S = Q_h K_h^T (K = 32 = two K16 steps)
+    auto issue_scores = [&](int hh) {             // warp 0: S = Q_h K_h^T (K = 32 = two K16 steps)
       const uint32_t qa = smem_u32(sQh + hh * 8192), ka = smem_u32(sKh + hh * 8192);
-      umma(tmem + COL_S, make_desc_sw64(qa), make_desc_sw64(ka), 0u);
-      umma(tmem + COL_S, make_desc_sw64(qa + 32), make_desc_sw64(ka + 32), 1u);
+      issue_mma(tmem_u + COL_S, make_desc_sw64(qa), make_desc_sw64(ka), 0u, IDESC_128x128);
+      issue_mma(tmem_u + COL_S, make_desc_sw64(qa + 32), make_desc_sw64(ka + 32), 1u, IDESC_128x128);
     };
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_scores(0);
-      umma_commit(bar_mma);
+      if (issuer) commit(bar_mma);
     }
 #pragma unroll 1
     for (int hh = 0; hh < HEADS; ++hh) {
@@ -587,15 +548,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
       proxy_fence();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {
         tc_fence_after();
         const uint32_t pa = smem_u32(sA), va = smem_u32(sVt + hh * 8192);
 #pragma unroll
         for (int k16 = 0; k16 < 8; ++k16)
-          umma(tmem + COL_O + hh * HD, make_desc_sw128(pa + (k16 >> 2) * 16384 + (k16 & 3) * 32),
-               make_desc_sw128(va + (k16 >> 2) * 4096 + (k16 & 3) * 32), k16 != 0 ? 1u : 0u, IDESC_128x32);
+          issue_mma(tmem_u + COL_O + hh * HD, make_desc_sw128(pa + (k16 >> 2) * 16384 + (k16 & 3) * 32),
+                    make_desc_sw128(va + (k16 >> 2) * 4096 + (k16 & 3) * 32), k16 != 0 ? 1u : 0u, IDESC_128x32);
         if (hh + 1 < HEADS) issue_scores(hh + 1);  // every thread has drained S_hh; one round trip per head
-        umma_commit(bar_mma);
+        if (issuer) commit(bar_mma);
       }
     }
     mma_sync();         // O of the last head is complete
@@ -635,40 +596,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       issue_load(g0 + 5);                         // fc2 weights into ring slot 2: the softmax scratch in it is dead now
       gemm(g0 + 3, smem_u32(sA), COL_PROJ);
-      umma_commit(bar_mma);
+      if (issuer) commit(bar_mma);
     }
     mma_sync();
-    if (tid == 0) issue_load(g0 + 6);
+    if (warp == 0) issue_load(g0 + 6);
     // ---- x += proj ; LayerNorm 2 -> sA ---------------------------------------------------
     residual_ln(true, COL_PROJ, nullptr, lw.ln2w, lw.ln2b, true, nullptr);
     // ---- fc1 GEMM ---------------------------------------------------------------------------
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       gemm(g0 + 4, smem_u32(sA), COL_FC1);
-      umma_commit(bar_mma);
+      if (issuer) commit(bar_mma);
     }
     mma_sync();
-    if (tid == 0) issue_load(g0 + 7);
+    if (warp == 0) issue_load(g0 + 7);
     // ---- ReLU(fc1 + b) -> bf16 A operand (in the q buffer); 32 columns per warp group ----------
     relu_fc1(lw.fc1b);
     // ---- fc2 GEMM ---------------------------------------------------------------------------
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
       gemm(g0 + 5, smem_u32(sQh), COL_FC2);
-      umma_commit(bar_mma);
+      if (issuer) commit(bar_mma);
     }
     mma_sync();
-    if (tid == 0) issue_load(g0 + 8);
+    if (warp == 0) issue_load(g0 + 8);
     // ---- x += fc2 + b ; next layer's LayerNorm 1 -> sA, or the stage's output rows ---------------------
     {
       const bool last = l + 1 == p.n_layers;
@@ -689,22 +650,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) uplift_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
-}
-
-typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn get_encode() {
-  static EncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    cudaDriverEntryPointQueryResult q;
-    void* ptr = nullptr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeFn)ptr;
-  }
-  return fn;
 }
 
 __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n) {

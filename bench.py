@@ -459,29 +459,36 @@ def main():
             return rot, pos
 
         up_res = {}
-        for key in ('bf16', 'fp32'):
-            ms_a = timed(lambda: up_chunks(ua_d, key), sub_steps, 2)
+        for key in ('tf32x3', 'bf16', 'fp32'):
+            ms_a = timed(lambda: up_chunks(ua_d, key), sub_steps if key != 'fp32' else 1, 2 if key != 'fp32' else 1)
             n_launch = (up.engine.last_launches() + 1) * ((nloc + UPLIFT_CHUNK - 1) // UPLIFT_CHUNK)
 
             def e2e_fn():
                 rot, pos = up_chunks([a.to(dev, non_blocking=True) for a in ua_p], key)
                 return rot.cpu(), pos.cpu()
-            ms_b = timed(e2e_fn, sub_steps, 2)
-            up_res[key] = (UPLIFT_TOTAL * sub_steps / (ms_a * 1e-3), UPLIFT_TOTAL * sub_steps / (ms_b * 1e-3), ms_a / sub_steps, n_launch)
+            n_a = sub_steps if key != 'fp32' else 1
+            ms_b = timed(e2e_fn, n_a, 1)
+            up_res[key] = (UPLIFT_TOTAL * n_a / (ms_a * 1e-3), UPLIFT_TOTAL * n_a / (ms_b * 1e-3), ms_a / n_a, n_launch)
         with torch.no_grad():
             sl = [a[:4096] for a in ua_d]
             r32, p32u = up.engine.forward(*sl, 'fp32')
             r16, p16u = up.engine.forward(*sl, 'bf16')
+            r3, p3u = up.engine.forward(*sl, 'tf32x3')
             vm = sl[2].bool()
             bf16_rel = float(((p16u - p32u)[vm].norm() / p32u[vm].norm()).item())
-        up_line = {'value': up_res['fp32'][0], 'unit': 'trajectories/s', 'dtype': 'fp32', 'scaling': 'strong',
+            x3_abs = float((p3u - p32u)[vm].abs().max().item())
+        up_line = {'value': up_res['tf32x3'][0], 'unit': 'trajectories/s', 'dtype': 'tf32x3', 'api_default_dtype': up.compute_dtype, 'scaling': 'strong',
                    'workload': 'configs[3]: %d synthetic trajectories (T = 50, 13 table keypoints) sharded over %d rank(s) by index range, chunks of %d, '
                                'spin rotated to local axes; at N > 1 one NCCL all_gather of the 612-byte result records per pass' % (UPLIFT_TOTAL, world, UPLIFT_CHUNK),
-                   'ms_per_pass': up_res['fp32'][2], 'gpu_launches_per_pass': up_res['fp32'][3],
-                   'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['fp32'][0] / 1e3,
-                   'e2e': {'value': up_res['fp32'][1], 'unit': 'trajectories/s', 'h2d_bytes_per_pass': int(sum(a.numel() * 4 for a in ua)) * world,
+                   'ms_per_pass': up_res['tf32x3'][2], 'gpu_launches_per_pass': up_res['tf32x3'][3],
+                   'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['tf32x3'][0] / 1e3,
+                   'e2e': {'value': up_res['tf32x3'][1], 'unit': 'trajectories/s', 'h2d_bytes_per_pass': int(sum(a.numel() * 4 for a in ua)) * world,
                            'd2h_bytes_per_pass': UPLIFT_TOTAL * 153 * 4},
-                   'note': "fp32 is the reference's arithmetic for these Linear layers on a GPU (torch keeps TF32 off for matmul) and the API default",
+                   'max_abs_pos_diff_vs_fp32_simt': x3_abs,
+                   'note': "tf32x3: every Linear layer as three TF32 tensor-core products of split operands (fp32-level results; the reference's Linear layers are "
+                           "fp32 on a GPU, torch keeps TF32 off for matmul); the API default",
+                   'fp32_simt': {'value': up_res['fp32'][0], 'e2e': up_res['fp32'][1], 'ms_per_pass': up_res['fp32'][2], 'gpu_launches_per_pass': up_res['fp32'][3],
+                                 'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['fp32'][0] / 1e3, 'note': 'fused SIMT stacks, the strict parity path'},
                    'bf16': {'value': up_res['bf16'][0], 'e2e': up_res['bf16'][1], 'ms_per_pass': up_res['bf16'][2], 'gpu_launches_per_pass': up_res['bf16'][3],
                             'tflops': UPLIFT_GFLOP_PER_TRAJ * up_res['bf16'][0] / 1e3,
                             'tensor_frac': UPLIFT_GFLOP_PER_TRAJ * up_res['bf16'][0] / 1e3 / world / peaks()['bf16_tflops_sustained'],
@@ -686,7 +693,8 @@ def main():
             o_ms = roofline_other['all_convs']['ms'] / roofline_other['all_convs']['share_of_detector_time']
             eager['speedup_wasb_network'][roofline_other['dtype'] + '_vs_torch_bf16_channels_last'] = BATCH / (o_ms * 1e-3) / eager['wasb_forward']['bf16_channels_last']
         if up_line is not None:
-            eager['speedup_uplift'] = {'fp32_vs_torch_fp32_sdpa': up_line['value'] / world / eager['uplift_forward']['fp32_sdpa_b4096']}
+            eager['speedup_uplift'] = {'tf32x3_vs_torch_fp32_sdpa': up_line['value'] / world / eager['uplift_forward']['fp32_sdpa_b4096'],
+                                       'fp32_simt_vs_torch_fp32_sdpa': up_line['fp32_simt']['value'] / world / eager['uplift_forward']['fp32_sdpa_b4096']}
     cpu = None
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())

@@ -213,11 +213,14 @@ def test_decode_profile_hook(dev):
 UPLIFT_ATOL, UPLIFT_RTOL = 1e-4, 1e-4
 
 
+# both fp32-level paths meet the same bar: 'tf32x3' (default: tcgen05 tensor cores, three TF32 products per term) and 'fp32' (fused SIMT stacks)
+@pytest.mark.parametrize('prec', ['tf32x3', 'fp32'])
 @pytest.mark.parametrize('name', ['connectstage', 'multistage'])
-def test_uplift_golden(dev, golden, name):
+def test_uplift_golden(dev, golden, name, prec):
     from upliftingtabletennis_b200.uplift import get_model
     g = golden('uplift')
-    m = get_model(name, 'large', 'dynamic', 'new').to(dev).eval()
+    m = get_model(name, 'large', 'dynamic', 'new', dtype=prec).to(dev).eval()
+    assert m.compute_dtype == prec and get_model(name, 'large', 'dynamic', 'new').compute_dtype == 'tf32x3'
     m.load_state_dict(oup.random_state_dict(int(g[name + '_seed'])))
     args = [torch.from_numpy(g[name + '_' + k]).to(dev) for k in ('ball', 'table', 'mask', 'times')]
     rot, pos = m(*args)
@@ -225,10 +228,11 @@ def test_uplift_golden(dev, golden, name):
     np.testing.assert_allclose(rot.cpu().numpy(), g[name + '_rot'], rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
 
 
-def test_uplift_t60_and_batch(dev, golden):
+@pytest.mark.parametrize('prec', ['tf32x3', 'fp32'])
+def test_uplift_t60_and_batch(dev, golden, prec):
     from upliftingtabletennis_b200.uplift import get_model
     g = golden('uplift')
-    m = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+    m = get_model('connectstage', 'large', 'dynamic', 'new', dtype=prec).to(dev).eval()
     sd = oup.random_state_dict(int(g['connectstage_seed']))
     m.load_state_dict(sd)
     args = [torch.from_numpy(g['t60_' + k]).to(dev) for k in ('ball', 'table', 'mask', 'times')]
@@ -244,6 +248,10 @@ def test_uplift_t60_and_batch(dev, golden):
     np.testing.assert_allclose(rot.cpu().numpy(), r_ref.numpy(), rtol=UPLIFT_RTOL, atol=UPLIFT_ATOL)
     r1, p1 = m(*(torch.from_numpy(a[5:6]).to(dev) for a in (ball, table, mask, times)))
     assert torch.equal(r1[0], rot[5]) and torch.equal(p1[0], pos[5])
+    if prec == 'tf32x3':       # how close the split-operand tensor-core products are to fp32: report, and hold a tighter bar than the 1e-4 above
+        err = float((pos.cpu() - p_ref).abs().max())
+        print('tf32x3 max |pos - oracle| = %.2e' % err)
+        assert err < 3e-5
 
 
 def test_uplift_mask_errors(dev):

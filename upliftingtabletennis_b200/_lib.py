@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libttk.so')
 
-F32, BF16, TF32 = 0, 1, 2
+F32, BF16, TF32, TF32X3 = 0, 1, 2, 3
 DECODE_TABLE, DECODE_BALL = 0, 1
 LAYOUT_NCHW_F32, LAYOUT_NHWC16 = 0, 1
 

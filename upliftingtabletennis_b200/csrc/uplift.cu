@@ -508,6 +508,8 @@ extern "C" void ttk_uplift_destroy(ttk_uplift* h) {
   if (!h) return;
   for (UpliftParam& p : h->params) cudaFree(p.dev);
   cudaFree(h->wmat_dev);
+  cudaFree(h->w3_hi);
+  cudaFree(h->w3_lo);
   cudaFree(h->layers_dev);
   delete h;
 }
@@ -530,22 +532,29 @@ extern "C" int ttk_uplift_set_param(ttk_uplift* h, int i, const float* data_host
   p.set = true;
   h->layers_ready = false;
   h->wmat_ready = false;
+  h->w3_ready = false;
   return TTK_OK;
 }
 
-extern "C" size_t ttk_uplift_workspace_bytes(const ttk_uplift* h, int batch, int seq_len, int dtype) {
-  (void)dtype;
-  if (!h || batch <= 0 || seq_len <= 0) return 0;
-  // X [B*T][128] + table_emb [B*13][128] (+ embed(pos) [B*T][128] without skip connection) + bf16 attention rows [B*T][128]
+namespace {
+// X [B*T][128] + table_emb [B*13][128] (+ embed(pos) [B*T][128] without skip connection) + bf16 attention rows [B*T][128]
+size_t base_workspace_bytes(const ttk_uplift* h, int batch, int seq_len) {
   size_t tokens = (size_t)batch * seq_len * (h->skip ? 1 : 2) + (size_t)batch * NTAB;
-  return tokens * D * sizeof(float) + (size_t)batch * seq_len * D * 2 + 1024;
+  return (tokens * D * sizeof(float) + (size_t)batch * seq_len * D * 2 + 1024 + 1023) & ~(size_t)1023;
+}
+}  // namespace
+
+extern "C" size_t ttk_uplift_workspace_bytes(const ttk_uplift* h, int batch, int seq_len, int dtype) {
+  if (!h || batch <= 0 || seq_len <= 0) return 0;
+  // the tf32x3 path keeps a layer's activations in HBM between its kernels (uplift3.cu)
+  return base_workspace_bytes(h, batch, seq_len) + (dtype == TTK_TF32X3 ? ttk_uplift3_workspace_bytes(h, batch, seq_len) : 0);
 }
 
 extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const float* table_dev, const float* mask_dev,
                                   const float* times_dev, int batch, int seq_len, int dtype, float* rot_out_dev,
                                   float* pos_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_uplift_forward: null handle");
-  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16, "ttk_uplift_forward: bad dtype %d", dtype);
+  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32X3, "ttk_uplift_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0 && seq_len >= 2 && seq_len + 1 <= MT, "ttk_uplift_forward: seq_len must be in [2, %d] (got %d)", MT - 1, seq_len);
   for (const UpliftParam& p : h->params)
     if (!p.set) {
@@ -588,6 +597,48 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
       h->dev("firststage.table_embed.fc2.weight"), h->dev("firststage.table_embed.fc2.bias"), table_emb);
   TTK_LAUNCH_CHECK();
   h->launches += 2;
+
+  if (dtype == TTK_TF32X3) {
+    // fp32-class tensor-core path: every Linear layer as three TF32 products of split operands (gemm3_umma.cu, uplift3.cu); heads stay SIMT
+    if (!h->w3_ready) {
+      int rc = ttk_uplift3_prepare(h);
+      if (rc) return rc;
+    }
+    UpliftIO io;
+    io.ball = ball_dev;
+    io.table = table_dev;
+    io.mask = mask_dev;
+    io.times = times_dev;
+    io.batch = batch;
+    io.T = T;
+    io.rot_out = rot_out_dev;
+    io.pos_out = pos_out_dev;
+    io.X = X;
+    io.table_emb = table_emb;
+    io.second_emb = second_emb;
+    io.attn_rows = nullptr;
+    void* ws3 = (char*)workspace_dev + base_workspace_bytes(h, batch, seq_len);
+    int rc = ttk_uplift3_stage(h, MODE_POS, io, ws3, st);
+    if (rc) return rc;
+    rc = ttk_uplift3_stage(h, MODE_TEMPORAL, io, ws3, st);
+    if (rc) return rc;
+    head_kernel<<<ttk_cdiv(ntok, MT), THREADS, HEAD_SMEM_BYTES, st>>>(X, ntok, head_ptrs(h, "firststage.position_head"), pos_out_dev);
+    TTK_LAUNCH_CHECK();
+    h->launches += 1;
+    if (!h->skip) {
+      embed_kernel<<<ttk_cdiv(ntok, MT), THREADS, SMEM_BYTES, st>>>(pos_out_dev, 3, 3, ntok, h->dev("embed.fc1.weight"),
+                                                                   h->dev("embed.fc1.bias"), h->dev("embed.fc2.weight"),
+                                                                   h->dev("embed.fc2.bias"), second_emb);
+      TTK_LAUNCH_CHECK();
+      h->launches += 1;
+    }
+    rc = ttk_uplift3_stage(h, MODE_SECOND, io, ws3, st);
+    if (rc) return rc;
+    head_kernel<<<ttk_cdiv(batch, MT), THREADS, HEAD_SMEM_BYTES, st>>>(table_emb, batch, head_ptrs(h, "rotation_head"), rot_out_dev);
+    TTK_LAUNCH_CHECK();
+    h->launches += 1;
+    return TTK_OK;
+  }
 
   if (dtype == TTK_BF16) {
     // tensor-core path: tcgen05 GEMMs, residual stream in TMEM (uplift_tc.cu); heads stay fp32

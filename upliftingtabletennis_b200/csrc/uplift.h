@@ -29,6 +29,9 @@ struct ttk_uplift {
   // bf16 tensor-core path: every layer's [qkv(384) | proj(128) | fc1(128) | fc2(128)] x 128 weight rows, K-major
   __nv_bfloat16* wmat_dev = nullptr;
   bool wmat_ready = false;
+  // fp32-class tensor-core path (3xTF32): hi / lo halves of every layer's [qkv | proj | fc1 | fc2] weight rows, fp32 [layers*768][128] each
+  float *w3_hi = nullptr, *w3_lo = nullptr;
+  bool w3_ready = false;
   int find(const std::string& n) const {
     for (size_t i = 0; i < params.size(); ++i)
       if (params[i].name == n) return (int)i;
@@ -44,6 +47,25 @@ struct UpliftIO {
   float *X, *table_emb, *second_emb;     // workspace slices
   void* attn_rows;                       // bf16 [batch*T][128]: attention output of the ball tokens in the last table-token layer
 };
+
+// gemm3_umma.cu: C = act(A' W^T + bias) (+ R) with K = 128, fp32 in / out, three TF32 tensor-core products per term (fp32-level results).
+struct Gemm3Args {
+  const float* A;          // [M][128]
+  const float *W_hi, *W_lo; // [N][128]: W = W_hi + W_lo, W_hi = tf32(W) (split on the host, ttk_uplift3_prepare)
+  const float* bias;       // [N] or null
+  const float* R;          // [M][N] residual or null (may alias C)
+  float* C;                // [M][N]
+  int M, N;                // N a multiple of 128
+  int relu;
+  const float* ln_stats;   // [M][2] (mean, rstd) of A's rows: A' = LayerNorm(A) with ln_gamma / ln_beta [128]; null: A' = A
+  const float *ln_gamma, *ln_beta;
+  float* out_stats;        // [M][2] mean / rstd (eps 1e-5) of the rows of C, for the next LayerNorm (N = 128 only); null: not needed
+};
+int ttk_gemm3(const Gemm3Args& g, cudaStream_t st);
+// uplift3.cu: the transformer on ttk_gemm3 + fp32 attention ("tf32x3" arithmetic class)
+size_t ttk_uplift3_workspace_bytes(const ttk_uplift* h, int batch, int T);
+int ttk_uplift3_prepare(ttk_uplift* h);
+int ttk_uplift3_stage(ttk_uplift* h, int mode, const UpliftIO& io, void* ws, cudaStream_t st);
 
 // uplift_tc.cu
 int ttk_uplift_tc_prepare(ttk_uplift* h);

@@ -11,7 +11,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
 from .detector import _attach
-from .precision import PrecisionMixin, lib_enum
+from .precision import BF16, FP32, TF32X3, PrecisionMixin, lib_enum
 
 SIZES = {'small': (32, 8, 4), 'base': (64, 12, 4), 'large': (128, 16, 4), 'huge': (192, 16, 8)}   # uplifting/model.py:574-603
 PARAM_SHAPES = {'cls_token': lambda d: (1, 1, d)}
@@ -44,11 +44,17 @@ class UpliftEngine:
             check(lib.ttk_uplift_set_param(self.h, i, ptr(t), numel))
         self.loaded = True
 
+    TF32X3_CHUNK = 4096          # trajectories per library call on the tf32x3 path: its activations live in HBM (7.3 GB per 4096)
+
     def forward(self, ball, table, mask, times, dtype=torch.float32):
         assert self.loaded
         B, T, _ = ball.shape
         dev = ball.device
         dt = lib_enum(dtype)
+        if dt == _lib.TF32X3 and B > self.TF32X3_CHUNK:
+            parts = [self.forward(ball[i:i + self.TF32X3_CHUNK], table[i:i + self.TF32X3_CHUNK], mask[i:i + self.TF32X3_CHUNK],
+                                  times[i:i + self.TF32X3_CHUNK], dtype) for i in range(0, B, self.TF32X3_CHUNK)]
+            return torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
         args = [a.to(torch.float32).contiguous() for a in (ball, table, mask, times)]
         need = lib.ttk_uplift_workspace_bytes(self.h, B, T, dt)
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -81,8 +87,11 @@ def _shape_of(name, numel, dim):
 
 class MultiStageModel(PrecisionMixin, nn.Module):
     """Drop-in for uplifting/model.py:MultiStageModel (tabletoken_mode 'dynamic', time_rotation 'new').
-    ``compute_dtype`` (constructor argument ``dtype``): 'fp32' (default: the reference's Linear layers are fp32 on a GPU too) or
-    'bf16' (tcgen05 tensor cores)."""
+    ``compute_dtype`` (constructor argument ``dtype``): 'tf32x3' (default: tcgen05 tensor cores with split operands, fp32-level
+    results like the reference's fp32 Linear layers on a GPU), 'fp32' (fused SIMT stacks, the strict parity path) or 'bf16'
+    (fused tcgen05 stacks, bf16 operands)."""
+    default_precision = TF32X3
+    supported_precisions = (TF32X3, FP32, BF16)
 
     def __init__(self, dim, depth, num_heads, mode='dynamic', time_rotation='new', use_skipconnection=False, dtype=None):
         super().__init__()

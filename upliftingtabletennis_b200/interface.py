@@ -209,7 +209,9 @@ def _staging_pool():
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max_workers=max(4, min(8, (os.cpu_count() or 8) // 2)), thread_name_prefix='ttk-stage')
+        # host threads that copy numpy frames into the pinned staging ring: up to 8, sharing the cores with the other ranks of the node
+        ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 8) // ranks)), thread_name_prefix='ttk-stage')
     return _POOL
 
 

@@ -90,7 +90,9 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
 // registers.  (The first version, one warp per (row, head) with lanes over keys like uplift.cu's fused stack, was a chain of dependent
 // FMAs and shuffles with 14 of 32 lanes busy: 4.9 ms per table-token layer against 1 ms of HBM time.)
 // SMAX: compile-time bound of the sequence length (score registers); G: sequences per CTA; SLOTS: thread slots per head (>= G S rows).
-template <int MODE, int SMAX, int G, int SLOTS>
+// FIRST_ONLY: only token 0 of every sequence is a query and o has one row per SEQUENCE (last table-token layer: only the ball token is
+// used afterwards, model.py:375-378).
+template <int MODE, int SMAX, int G, int SLOTS, bool FIRST_ONLY = false>
 __global__ void __launch_bounds__(4 * SLOTS, SLOTS == 32 ? 4 : 2) attention3_kernel(const float* __restrict__ qkv, float* __restrict__ o, const float* __restrict__ table,
                                                                      const float* __restrict__ mask, const float* __restrict__ times,
                                                                      const float* __restrict__ invf, int batch, int T) {
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(4 * SLOTS, SLOTS == 32 ? 4 : 2) attention3_ker
   const float scale = 0.17677669529663687f;             // 1 / sqrt(32), SDPA default
   const int hh = tid / SLOTS, r = tid % SLOTS;          // SLOTS thread slots per head; a warp works on one head
   if (r >= M) return;
+  if (FIRST_ONLY && r % S != 0) return;
   const int k0 = (r / S) * S;
   float q[HD];
 #pragma unroll
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(4 * SLOTS, SLOTS == 32 ? 4 : 2) attention3_ker
       }
     }
   }
-  float4* op = reinterpret_cast<float4*>(o + (row0 + r) * D + hh * HD);      // 128 contiguous bytes per thread
+  float4* op = reinterpret_cast<float4*>(o + (FIRST_ONLY ? seq0 + r / S : row0 + r) * D + hh * HD);      // 128 contiguous bytes per thread
 #pragma unroll
   for (int d = 0; d < HD; d += 4) op[d / 4] = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
 }
@@ -272,6 +275,7 @@ int ttk_uplift3_stage(ttk_uplift* h, int mode, const UpliftIO& io, void* ws, cud
   static bool attr = false;
   if (!attr) {
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_POS, NTAB + 1, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(32)));
+    TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_POS, NTAB + 1, 2, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(32)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_TEMPORAL, 52, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_TEMPORAL, 64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_SECOND, 52, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
@@ -311,6 +315,29 @@ int ttk_uplift3_stage(ttk_uplift* h, int mode, const UpliftIO& io, void* ws, cud
     int rc = ttk_gemm3(g, st);
     if (rc) return rc;
     const float* invf = h->dev(lname(mode, i, "attn.rotary_emb.inv_freq"));
+    // Last table-token layer: only the ball token (row 0 of every sequence) is used afterwards, so its attention has one query per
+    // sequence and projection + MLP run on those rows alone (1/14 of the rows), straight on io.X.
+    const bool ball_only = mode == MODE_POS && i + 1 == n_layers;
+    if (ball_only) {
+      attention3_kernel<MODE_POS, NTAB + 1, 2, 32, true><<<ttk_cdiv(n_seq, 2), 128, att_smem(32), st>>>(qkv, oa, io.table, io.mask, io.times, invf, batch, T);
+      TTK_LAUNCH_CHECK();
+      gather_rows_kernel<<<ttk_cdiv(ntok, 8), 256, 0, st>>>(x, io.X, ntok, NTAB + 1);
+      TTK_LAUNCH_CHECK();
+      float* bstats = qkv;                              // q | k | v are dead once the attention has run
+      float* ba = oa + (size_t)ntok * D;
+      g = Gemm3Args{oa, whi + 384 * D, wlo + 384 * D, nullptr, io.X, io.X, (int)ntok, D, 0, nullptr, nullptr, nullptr, bstats};
+      rc = ttk_gemm3(g, st);
+      if (rc) return rc;
+      g = Gemm3Args{io.X, whi + 512 * D, wlo + 512 * D, h->dev(lname(mode, i, "mlp1.fc1.bias")), nullptr, ba, (int)ntok, D, 1, bstats,
+                    h->dev(lname(mode, i, "norm2.weight")), h->dev(lname(mode, i, "norm2.bias")), nullptr};
+      rc = ttk_gemm3(g, st);
+      if (rc) return rc;
+      g = Gemm3Args{ba, whi + 640 * D, wlo + 640 * D, h->dev(lname(mode, i, "mlp1.fc2.bias")), io.X, io.X, (int)ntok, D, 0, nullptr, nullptr, nullptr, nullptr};
+      rc = ttk_gemm3(g, st);
+      if (rc) return rc;
+      h->launches += 6;
+      return TTK_OK;
+    }
     if (mode == MODE_POS)
       attention3_kernel<MODE_POS, NTAB + 1, 2, 32><<<ttk_cdiv(n_seq, 2), 128, att_smem(32), st>>>(qkv, oa, io.table, io.mask, io.times, invf, batch, T);
     else if (mode == MODE_TEMPORAL && S <= 52)

@@ -45,7 +45,8 @@ namespace {
 using namespace umma;
 
 constexpr int BW = 128;          // output pixels per tile row = MMA M
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;         // TMA warp, MMA warp, 4 epilogue warps
+constexpr int THREADS_HF = 320;      // horizontal tap fusion: 8 epilogue warps (two per TMEM lane quarter, alternating output rows)
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
@@ -54,7 +55,7 @@ constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 // (blockIdx.y selects the slice when the layer has more); R: output rows per tile; STAGES: smem ring depth;
 // RB: reserve shared memory for TMA-staged residual tiles (double buffered with the accumulators);
 // KCO: channels per K-chunk when not the default (a narrower chunk buys a taller tile for the same shared memory).
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2, int HF = 0>
 struct Cfg {
   static constexpr int KCMAX = 128 / ESZ;                           // a swizzled smem row holds at most 128 bytes
   static constexpr int KC = KCO ? KCO : (CIN < KCMAX ? CIN : KCMAX);      // channels per K-chunk = one swizzled smem row
@@ -65,7 +66,8 @@ struct Cfg {
   static constexpr bool FUSE = KS == 3 && S == 1 && 3 * COUT <= 256;   // vertical tap fusion
   static constexpr int NPY = S == 2 ? 2 : 1;            // row-parity units per K-chunk
   static constexpr int NBOX = S == 2 ? 2 : 1;           // TMA boxes per unit (column parities)
-  static constexpr int TW = S == 2 ? BW + 1 : BW + 2 * PAD;
+  static constexpr int TW = S == 2 ? BW + 1 : (HF ? BW : BW + 2 * PAD);
+  static constexpr int OUTW = HF ? BW - 2 : BW;          // output pixels per tile row (horizontal tap fusion: the edge lanes are halo only)
   static constexpr int TR = S == 2 ? R + 1 : R + 2 * PAD;
   static constexpr int BOX_BYTES = TR * TW * ROWB;
   static constexpr int BOX_AL = al1024(BOX_BYTES);
@@ -74,7 +76,7 @@ struct Cfg {
   static constexpr int TAPS = KS * KS;
   static constexpr int W_BYTES = TAPS * NKC * COUT * ROWB;
   static constexpr int W_BYTES_AL = al1024(W_BYTES);
-  static constexpr int ACC_COLS = R * COUT;
+  static constexpr int ACC_COLS = (HF ? 3 : 1) * R * COUT;      // HF: three accumulator sets (one per horizontal tap) per output row
   static constexpr int TMEM_COLS = pow2_cols(2 * ACC_COLS);
   // residual staging: boxes of CB channels (<= 128 swizzled bytes per pixel) x 128 px x R rows
   static constexpr int CB = COUT < KCMAX ? COUT : KCMAX;
@@ -83,15 +85,17 @@ struct Cfg {
   static constexpr int RBOX_BYTES = R * BW * RROWB;     // multiple of 1024
   static constexpr int RES_BYTES = RB ? 2 * NRB * RBOX_BYTES : 0;
   static constexpr uint32_t RSWZ = RROWB == 32 ? 1u : RROWB == 64 ? 3u : 7u;
-  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + RES_BYTES + COUT * 4 + 256;
+  static constexpr int XCH_BYTES = HF ? 4 * 2 * R * COUT * 4 : 0;      // HF: edge-lane exchange between the four epilogue warps
+  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + RES_BYTES + COUT * 4 + XCH_BYTES + 256;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : ROWB == 64 ? 4u : 2u;     // SWIZZLE_32B / 64B / 128B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
+  static_assert(!HF || (KS == 3 && S == 1 && 9 * COUT <= 256 && COUT == 16 && !RB), "horizontal tap fusion: 3x3 stride 1, 16 output channels, no staged residual");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
   static constexpr int GCOLS = ACC_COLS < (ESZ == 2 ? 64 : 32) ? ACC_COLS : (ESZ == 2 ? 64 : 32);     // accumulator columns fetched per TMEM wait
   // software-pipelined epilogue (see the kernel); not with TMA-staged residual tiles, whose shared-memory reads have no latency to hide
   // (the full-resolution 16 -> 16 layers ran at 6.5 TB/s without it, 5.7 TB/s with it)
-  static constexpr bool PIPE = ESZ == 4 && S == 1 && !RB && ACC_COLS / GCOLS >= 2;
+  static constexpr bool PIPE = ESZ == 4 && S == 1 && !RB && !HF && ACC_COLS / GCOLS >= 2;
   static_assert(ESZ == 2 || ESZ == 4, "bf16 or tf32-in-fp32 elements");
   static_assert(ACC_COLS % GCOLS == 0, "the epilogue drains whole groups of accumulator columns");
   static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "a K-chunk is one 32/64/128-byte swizzled row");
@@ -118,16 +122,18 @@ struct KArgs {
   int tiles_x, tiles_y, total;
 };
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
-__global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>;
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2, int HF = 0>
+__global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel(const __grid_constant__ KMaps maps, const KArgs a) {
+  constexpr int NTHR = HF ? THREADS_HF : THREADS;
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ, HF>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sA = smem + C::W_BYTES_AL;
   uint8_t* sR = sA + STAGES * C::STAGE_BYTES;           // [acc][box][row][px][CB] swizzled (1024-aligned)
   float* sBias = reinterpret_cast<float*>(sR + C::RES_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + COUT);
+  float* sXch = sBias + COUT;                           // HF: [warp][set 0 of lane 31 | set 2 of lane 0][R][COUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + C::XCH_BYTES / 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
                  bar_tempty = bar_tfull + 16, bar_rfull = bar_tempty + 16;
@@ -140,12 +146,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     const uint4* wsrc = reinterpret_cast<const uint4*>(a.w) + (size_t)blockIdx.y * (C::W_BYTES / 16);
     const uint32_t wbase = smem_u32(sW);
     constexpr int CPR = C::ROWB / 16;
-    for (int i = tid; i < C::W_BYTES / 16; i += THREADS) {
+    for (int i = tid; i < C::W_BYTES / 16; i += NTHR) {
       uint32_t addr = wbase + (i / CPR) * C::ROWB + (i % CPR) * 16;
       addr ^= ((addr >> 7) & C::SWZ) << 4;
       *reinterpret_cast<uint4*>(sW + (addr - wbase)) = __ldg(wsrc + i);
     }
-    for (int i = tid; i < COUT; i += THREADS) sBias[i] = a.bias[n_off + i];
+    for (int i = tid; i < COUT; i += NTHR) sBias[i] = a.bias[n_off + i];
   }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_tfull + 8 * i, 1);
-      mbar_init(bar_tempty + 8 * i, 4);
+      mbar_init(bar_tempty + 8 * i, HF ? 8 : 4);
       mbar_init(bar_rfull + 8 * i, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
             if (KS == 1 && a.dual)     // channels beyond the first tensor are zero filled
               tma_load_4d(dst, &maps.m[kc < a.dual ? 0 : 1], bar_full + 8 * s, (kc < a.dual ? kc : kc - a.dual) * C::KC, tx * BW, ty * R, img);
             else
-              tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * BW - C::PAD, ty * R - C::PAD, img);
+              tma_load_4d(dst, &maps.m[0], bar_full + 8 * s, kc * C::KC, tx * C::OUTW - C::PAD, ty * R - C::PAD, img);
           } else {
 #pragma unroll
             for (int px = 0; px < 2; ++px)
@@ -230,7 +236,24 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
           fence_after();
           const uint32_t abase = smem_u32(sA + s * C::STAGE_BYTES) >> 4;      // 16-byte units from here on (make_desc16)
           constexpr uint32_t RB16 = C::ROWB / 16;
-          if (C::FUSE) {
+          if (HF) {
+            // horizontal + vertical tap fusion: input row hr (lane = input pixel, no shift) times [W(ky, kx) for all kx, ky in k0..k1]:
+            // N = 3 (k1 - k0 + 1) Cout lands in the accumulator sets [row block][kx][Cout]; the epilogue adds the three sets of a row
+            // with a lane shift of kx - 1
+#pragma unroll 1
+            for (int hr = 0; hr < R + 2; ++hr) {
+              const int yi = hr - 1;
+              const int k0 = yi + 2 - R > 0 ? yi + 2 - R : 0;
+              const int k1 = yi + 1 < 2 ? yi + 1 : 2;
+              const uint32_t idesc = ESZ == 2 ? make_idesc(128, (k1 - k0 + 1) * 3 * COUT) : make_idesc_tf32(128, (k1 - k0 + 1) * 3 * COUT);
+              const uint32_t d_tmem = d_acc + (R - 2 - yi + k0) * 3 * COUT;
+              const uint32_t arow = abase + hr * C::TW * RB16;
+              const uint32_t brow = wbase + ((kc * 3 + k0) * 3 * COUT) * RB16;
+#pragma unroll
+              for (int ks = 0; ks < C::KSTEPS; ++ks)
+                issue(d_tmem, make_desc16<8 * C::ROWB, C::LAYOUT>(arow + ks * 2), make_desc16<8 * C::ROWB, C::LAYOUT>(brow + ks * 2), idesc);
+            }
+          } else if (C::FUSE) {
             // input (halo) row hr = yi + 1 feeds output rows yo = yi + 1 - ky; row yo lives in column block R-1-yo
 #pragma unroll 1
             for (int hr = 0; hr < R + 2; ++hr) {
@@ -285,8 +308,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     constexpr int NSUB = GCOLS / 16;
     constexpr int RW = 4 * ESZ;                    // 32-bit words of the 16 channels of a pixel: 8 (bf16, one sector) or 16 (fp32, two)
     const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+    const int eg = (warp - 2) >> 2;                // HF: epilogue group 0 / 1 takes the even / odd output rows of a tile
     // zero both accumulator buffers, then open them for the MMA warp
-    for (int c = 0; c < 2 * C::ACC_COLS; c += 16) tmem_zero16(lane_base + c);
+    if (eg == 0)
+      for (int c = 0; c < 2 * C::ACC_COLS; c += 16) tmem_zero16(lane_base + c);
     tmem_wait_st();
     fence_before();
     __syncwarp();
@@ -311,11 +336,90 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < a.total; tile += gridDim.x, ++tcount) {
       const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, img = tile / (a.tiles_x * a.tiles_y);
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
-      const int ox = tx * BW + m;
+      const int ox = HF ? tx * C::OUTW + m - 1 : tx * BW + m;      // HF: lane m is input pixel tx OUTW - 1 + m and output pixel of the same index
       if (res_tma) mbar_wait(bar_rfull + 8 * acc, aph);
       mbar_wait(bar_tfull + 8 * acc, aph);
       fence_after();
-      if constexpr (C::PIPE) {
+      if constexpr (HF != 0) {
+        // ---- horizontal tap fusion: out[r][x] = set0[r][x - 1] + set1[r][x] + set2[r][x + 1]; lanes 0 and 127 are halo only ----
+        const uint32_t tbase = lane_base + acc * C::ACC_COLS;
+        float* xme = sXch + (q * 2) * R * COUT;
+        // pass 1: the edge lanes publish what their neighbours in the adjacent warps need
+#pragma unroll 1
+        for (int r = eg; r < R; r += 2) {
+          uint32_t e0[16], e2[16];
+          tmem_ld16(tbase + (R - 1 - r) * 3 * COUT, e0);
+          tmem_ld16(tbase + (R - 1 - r) * 3 * COUT + 2 * COUT, e2);
+          tmem_wait_ld();
+          if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xme[r * COUT + j] = __uint_as_float(e0[j]);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xme[R * COUT + r * COUT + j] = __uint_as_float(e2[j]);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float* xprev = sXch + ((q > 0 ? q - 1 : 0) * 2) * R * COUT;              // set 0 of the previous warp's lane 31
+        const float* xnext = sXch + ((q < 3 ? q + 1 : 3) * 2 + 1) * R * COUT;          // set 2 of the next warp's lane 0
+#pragma unroll 1
+        for (int r = eg; r < R; r += 2) {
+          uint32_t v0[16], v1[16], v2[16];
+          const uint32_t ta = tbase + (R - 1 - r) * 3 * COUT;
+          tmem_ld16(ta, v0);
+          tmem_ld16(ta + COUT, v1);
+          tmem_ld16(ta + 2 * COUT, v2);
+          tmem_wait_ld();
+          tmem_zero16(ta);
+          tmem_zero16(ta + COUT);
+          tmem_zero16(ta + 2 * COUT);
+          const int oy = ty * R + r;
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float left = __shfl_up_sync(0xffffffffu, __uint_as_float(v0[j]), 1);
+            float right = __shfl_down_sync(0xffffffffu, __uint_as_float(v2[j]), 1);
+            if (lane == 0) left = xprev[r * COUT + j];
+            if (lane == 31) right = xnext[r * COUT + j];
+            f[j] = (left + __uint_as_float(v1[j])) + right + sBias[j];
+          }
+          const bool live = m >= 1 && m <= C::OUTW && ox < a.w_img && oy < a.h;
+          for (int rr = 0; rr < a.nres; ++rr) {            // (the layer this path serves has no residual; kept for the one-conv test hook)
+            if (!live) break;
+            const int sh = a.rsh[rr];
+            const char* rp = (const char*)a.res[rr] +
+                             ((((size_t)img * (a.h >> sh) + (oy >> sh)) * (a.w_img >> sh) + (ox >> sh)) * a.cout_total + n_off) * ESZ;
+            uint32_t rw[RW];
+#pragma unroll
+            for (int i = 0; i < RW / 8; ++i) ldg256(rp + 32 * i, &rw[8 * i]);
+            add_words(f, rw);
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (live) {
+            char* op = (char*)a.out + ((((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off) * ESZ;
+            if (ESZ == 2) {
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                o[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              stg256(op, o);
+            } else {
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(f[j]);
+              stg256(op, o);
+              stg256(op + 32, o + 8);
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");        // the exchange buffer is free for the next tile
+      } else if constexpr (C::PIPE) {
         // Software-pipelined drain (TF32 stride-1 layers, at most one residual): the TMEM load and the residual loads of column
         // group g + 1 are in flight while group g is added up and stored, so neither latency is exposed per group (stem conv1 ran at
         // 59 % of the HBM rate waiting for one tcgen05.ld at a time; residuals read from global memory cost ~1 us per group).
@@ -484,6 +588,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_umma_kernel(const __grid_cons
 // output channels one CTA handles: 128-wide 3x3 layers with 64+ input channels are split so the weights fit in shared memory
 int cout_tile(const TtkConv& cv, int esz) { return (cv.k == 3 && cv.cout_p == 128 && cv.cin_p >= 64) ? (esz == 2 ? 64 : 32) : cv.cout_p; }
 bool fused_ky(const TtkConv& cv, int esz) { return cv.k == 3 && cv.stride == 1 && 3 * cout_tile(cv, esz) <= 256; }
+// horizontal + vertical tap fusion (one MMA per input row and K step, N = 9 Cout): the thin layer that is bound by its MMA count
+// -- TF32 only: with K = 8 per instruction it has twice the MMAs of the bf16 kernel (4.48 -> 3.50 ms per 32 stacks); in bf16 the extra
+// epilogue work (three accumulator sets, two shuffles per value, edge-lane exchange) outweighs the saved MMAs (1.74 -> 3.00 ms)
+bool fused_h(const TtkConv& cv, int esz) { return esz == 4 && cv.k == 3 && cv.stride == 1 && cv.cin_p == 128 && cv.cout_p == 16; }
 // channels per K-chunk (one swizzled shared-memory row).  The stride-1 3x3 layers with 64+ input channels are bound by their MMA
 // count (a 128-pixel x 32-byte MMA holds the tensor pipe 45.5 clk at N <= 48 and N / 2 clk from N = 96 on, tools/tf32_probe.cu) and
 // the halo rows of a tile are pure overhead: 3 (R + 2) / R MMAs per K step and output row.  Narrow chunks shrink the staging boxes so
@@ -516,10 +624,10 @@ float round_tf32(float v) {      // nearest-even on the 13 dropped mantissa bits
   return v;
 }
 
-template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2>
+template <int KS, int S, int CIN, int COUT, int R, int STAGES, int RB, int KCO = 0, int ESZ = 2, int HF = 0>
 int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
-  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>;
-  if (C::KC != kc_of(cv, ESZ) || COUT != cout_tile(cv, ESZ)) {
+  using C = Cfg<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ, HF>;
+  if (C::KC != kc_of(cv, ESZ) || COUT != cout_tile(cv, ESZ) || (HF != 0) != fused_h(cv, ESZ)) {
     ttk_set_error("conv %s: kernel K-chunk %d / output slice %d differ from the packed weights' %d / %d", cv.name.c_str(), C::KC, COUT,
                   kc_of(cv, ESZ), cout_tile(cv, ESZ));
     return TTK_ERR_STATE;
@@ -531,7 +639,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
     attr = true;
   }
@@ -584,7 +692,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   k.w_img = a.wout;
   k.cout_total = a.cout;
   k.relu = a.relu;
-  k.tiles_x = ttk_cdiv(a.wout, BW);
+  k.tiles_x = ttk_cdiv(a.wout, C::OUTW);
   k.tiles_y = ttk_cdiv(a.hout, R);
   k.total = k.tiles_x * k.tiles_y * a.n;
   const int nsplit = a.cout / COUT;
@@ -593,7 +701,7 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
   occ = std::max(1, std::min(occ, 2));
   const int gx = std::max(1, std::min(k.total, ttk_num_sms() * occ / nsplit));
   dim3 grid(gx, nsplit);
-  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, k);
+  conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ, HF><<<grid, HF ? THREADS_HF : THREADS, C::SMEM_BYTES, st>>>(maps, k);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
@@ -675,6 +783,7 @@ void ttk_conv_umma_pack_dual(const float* w3, const float* wd, int esz, std::vec
 
 // Weights for the tensor-core path: rows of KC input channels (K-major), zero padded, per output-channel slice:
 //   fused 3x3 stride 1 : [slice][k-chunk][kx][ky][cout_tile][KC]   (B = the three vertical taps side by side)
+//   transition1.0      : [k-chunk][ky][kx][cout][KC]               (B = all nine taps: horizontal + vertical fusion)
 //   otherwise          : [slice][tap][k-chunk][cout_tile][KC]
 // bf16 (w_umma) and TF32-rounded fp32 (w_umma32) images are both kept; they differ in KC and in the slice width of the 128-wide layers.
 int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
@@ -691,7 +800,10 @@ int ttk_conv_umma_pack(TtkConv& cv, const float* w_host) {
         for (int t = 0; t < kk; ++t) {
           const int kc = ci / KC, c = ci % KC, sl = co / ct, cl = co % ct;
           size_t row;
-          if (fused) {
+          if (fused_h(cv, esz)) {
+            const int ky = t / 3, kx = t % 3;
+            row = (((size_t)sl * nkc + kc) * 3 + ky) * 3 + kx;      // [k-chunk][ky][kx][cout]: B of one input row = all nine taps
+          } else if (fused) {
             const int ky = t / 3, kx = t % 3;
             row = (((size_t)sl * nkc + kc) * 3 + kx) * 3 + ky;
           } else {
@@ -755,7 +867,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   TTK_UMMA32(3, 1, 32, 32, 4, 3, 0, 16)      // half-resolution branch (residual read from global memory: no room for staged tiles)
   if (k == 3 && s == 1 && ci == 16 && co == 16 && a.nres == 0) return launch<3, 1, 16, 16, 8, 2, 0, 16, 4>(cv, a, st);     // taller tile (R = 4 with four stages: 0.77 vs 0.66 ms)
   TTK_UMMA32(3, 1, 16, 16, 4, 3, 1, 16)      // full-resolution branch, residual tiles staged by TMA
-  TTK_UMMA32(3, 1, 128, 16, 4, 3, 0, 16)     // transition1.0: 8-channel chunks (32-byte rows, R = 8) were bound by TMA's fill rate: 2.75 ms per 16 images
+  if (k == 3 && s == 1 && ci == 128 && co == 16) return launch<3, 1, 128, 16, 4, 3, 0, 16, 4, 1>(cv, a, st);     // transition1.0: nine taps per MMA
   TTK_UMMA32(3, 1, 128, 32, 4, 3, 0, 8)      // eighth-resolution branch (128 -> 128 as four 32-channel output slices)
   // 3x3 stride 2
   TTK_UMMA32(3, 2, 128, 32, 2, 3, 0, 8)

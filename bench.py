@@ -654,6 +654,8 @@ def main():
     roofline = roofline_of(args.dtype, args.dump_profile or None)
     stages = roofline.pop('stages')
     roofline['whole_step_tflops'] = WASB_GFLOP_PER_STACK * BATCH * args.steps / (head['ms_dev'] * 1e-3) / 1e3
+    roofline['whole_step_tflops_note'] = ('against the 344.07 GFLOP per stack of the reference graph; the plan skips the thirteen stage-4 fuse convolutions whose outputs '
+                                          'nothing reads (the reference computes and drops them), all_convs counts the executed work')
     roofline_other = None
     if 'bf16' in legs:
         o = 'bf16' if args.dtype != 'bf16' else 'tf32'

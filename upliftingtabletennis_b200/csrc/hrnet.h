@@ -57,6 +57,7 @@ struct ttk_hrnet {
   std::vector<TtkTensor> tensors;
   std::vector<TtkOp> ops;
   int input_tensor = -1;
+  int dead_ops = 0;             // ops of the reference's graph whose outputs nothing reads (removed from the plan)
   int subbatch = 16;
   int launches = 0;
   int force_simt = 0;           // bf16 storage through the SIMT kernels (debug / cross-check of the tcgen05 path)

@@ -142,9 +142,34 @@ def test_network_block_fusion_on_off(net):
         y_off, _ = m(x)
         n_off = m.engine.last_launches()
     finally:
-        lib.ttk_hrnet_set_block_fusion(m.engine.h, 0)          # the default (see hrnet.h)
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)          # the default (see hrnet.h)
         m.compute_dtype = torch.float32
     assert n_off - n_on == 12           # twelve BasicBlocks of the 16- and 32-channel branches run as one launch each
     ref = ohr.wasb_forward(sd, x.cpu()).numpy()
     assert np.linalg.norm(y_on.cpu().numpy() - ref) / np.linalg.norm(ref) < 3e-2
     assert np.linalg.norm((y_on - y_off).cpu().numpy()) / np.linalg.norm(ref) < 2e-2
+
+
+def test_network_block_fusion_tf32(net):
+    """TF32 path: the six BasicBlocks of the 16-channel full-resolution branch as fused kernels against the conv-by-conv plan.  The fused
+    kernel rounds the intermediate with cvt.rna (TMA rounds to even) and takes the residual from the TF32-rounded staged tile, so the two
+    plans agree to TF32 resolution, not bit for bit."""
+    from upliftingtabletennis_b200._lib import lib
+    m, sd = net
+    x = torch.from_numpy(np.random.default_rng(3).standard_normal((2, 9, 72, 264)).astype(np.float32)).cuda()
+    m.compute_dtype = 'tf32'
+    try:
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 2)          # 2 = also the TF32 blocks (off by default: slower than conv by conv, hrnet.cu)
+        y_on, _ = m(x)
+        n_on = m.engine.last_launches()
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 0)
+        y_off, _ = m(x)
+        n_off = m.engine.last_launches()
+    finally:
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)
+        m.compute_dtype = torch.float32
+    assert n_off - n_on == 6
+    ref = ohr.wasb_forward(sd, x.cpu()).numpy()
+    scale = np.abs(ref).max()
+    assert np.abs(y_on.cpu().numpy() - ref).max() <= 1e-2 * scale          # the path's stated bound
+    assert np.abs((y_on - y_off).cpu().numpy()).max() <= 4e-3 * scale

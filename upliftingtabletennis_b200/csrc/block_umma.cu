@@ -1,4 +1,5 @@
-// Fused BasicBlock of the HRNet branches on tcgen05 (bf16, 16- and 32-channel branches):
+// Fused BasicBlock of the HRNet branches on tcgen05 (bf16: 16- and 32-channel branches; TF32 on fp32 activations: the 16-channel
+// full-resolution branch, whose two convolutions are HBM bound on their own -- 320 bytes per pixel conv by conv, 128 fused):
 //   y = relu(conv2(relu(conv1(x) + b1)) + b2 + x)              balldetection/models/wasb.py:35-64 (BasicBlock.forward, BN folded)
 // The two 3x3 convolutions of a block run in ONE kernel: the intermediate tensor never leaves the SM and the residual is taken
 // from the staged input tile, so a block reads x once and writes y once (conv by conv it is read x, write t, read t, read x,
@@ -27,9 +28,9 @@ constexpr int BW = 128, WO = 126, TW = 130, THREADS = 320;      // TMA warp, MMA
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
 
-template <int C, int R, int SLOTS>
+template <int C, int R, int SLOTS, int ESZ = 2>
 struct BCfg {
-  static constexpr int ROWB = 2 * C;                   // bytes per pixel row of a tile (32 or 64)
+  static constexpr int ROWB = ESZ * C;                 // bytes per pixel row of a tile (32 or 64)
   static constexpr int R1 = R + 2, RX = R + 4;         // intermediate rows, input rows
   static constexpr int NX = SLOTS + 1;                 // input tile ring: one tile per slot in flight plus one being loaded
   static constexpr int X_BYTES = RX * TW * ROWB, X_AL = al1024(X_BYTES);
@@ -40,37 +41,43 @@ struct BCfg {
   static constexpr int SMEM_BYTES = 1024 + 2 * W_AL + NX * X_AL + SLOTS * T_AL + 2 * C * 4 + 256;
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : 4u;     // SWIZZLE_32B / 64B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : 3u;
-  static_assert(C == 16 || C == 32, "channel counts of the fused block");
+  static_assert((C == 16 || C == 32) && (ROWB == 32 || ROWB == 64), "channel counts of the fused block");
   static_assert(SLOTS * ACC <= 512, "accumulators exceed TMEM");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct BlockArgs {
-  const __nv_bfloat16 *w1, *w2;      // packed like ttk_conv_umma_pack (fused 3x3: [kx][ky][cout][cin])
+  const void *w1, *w2;               // packed like ttk_conv_umma_pack (fused 3x3: [kx][ky][cout][cin])
   const float *b1, *b2;
-  __nv_bfloat16* out;
+  void* out;
   int n, h, w;
   int tiles_x, tiles_y, total;
 };
 
-// RR output rows from RR + 2 staged rows at `abase`, weights at `wbase`, accumulators at `d_acc` (row yo in column block RR-1-yo)
-template <int C, int RR, uint32_t LAYOUT>
-__device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint32_t d_acc) {
-  constexpr int ROWB = 2 * C;
+// RR output rows from RR + 2 staged rows at `abase`, weights at `wbase`, accumulators at `d_acc` (row yo in column block RR-1-yo).
+// Called by the whole MMA warp with warp-uniform arguments; the elected lane issues (see conv_umma.cu).
+template <int C, int RR, uint32_t LAYOUT, int ESZ>
+__device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint32_t d_acc, bool leader) {
+  constexpr int ROWB = ESZ * C;
+  constexpr uint32_t RB16 = ROWB / 16;
+  const uint32_t a16 = abase >> 4, w16 = wbase >> 4;
 #pragma unroll 1
   for (int hr = 0; hr < RR + 2; ++hr) {
     const int yi = hr - 1;
     const int k0 = yi + 2 - RR > 0 ? yi + 2 - RR : 0;
     const int k1 = yi + 1 < 2 ? yi + 1 : 2;
-    const uint32_t idesc = make_idesc(128, (k1 - k0 + 1) * C);
+    const uint32_t idesc = ESZ == 2 ? make_idesc(128, (k1 - k0 + 1) * C) : make_idesc_tf32(128, (k1 - k0 + 1) * C);
     const uint32_t d = d_acc + (RR - 2 - yi + k0) * C;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const uint32_t arow = abase + (hr * TW + kx) * ROWB;
-      const uint32_t brow = wbase + ((kx * 3 + k0) * C) * ROWB;
+      const uint32_t arow = a16 + (hr * TW + kx) * RB16;
+      const uint32_t brow = w16 + ((kx * 3 + k0) * C) * RB16;
 #pragma unroll
-      for (int k16 = 0; k16 < C / 16; ++k16)
-        mma(d, make_desc(arow + k16 * 32, 8 * ROWB, LAYOUT), make_desc(brow + k16 * 32, 8 * ROWB, LAYOUT), idesc, 1u);
+      for (int ks = 0; ks < ROWB / 32; ++ks)
+        if (leader) {
+          if (ESZ == 2) mma(d, make_desc16<8 * ROWB, LAYOUT>(arow + ks * 2), make_desc16<8 * ROWB, LAYOUT>(brow + ks * 2), idesc, 1u);
+          else mma_tf32(d, make_desc16<8 * ROWB, LAYOUT>(arow + ks * 2), make_desc16<8 * ROWB, LAYOUT>(brow + ks * 2), idesc, 1u);
+        }
     }
   }
 }
@@ -78,9 +85,9 @@ __device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint3
 // Tiles of a CTA are numbered t = 0, 1, 2, ... in the order it takes them; tile t lives in input buffer t % NX and in slot t % SLOTS
 // (slot = its own accumulators and intermediate tile, served by its own group of four epilogue warps), so with two slots the MMAs of
 // one tile run under the epilogues of the other.
-template <int C, int R, int SLOTS>
+template <int C, int R, int SLOTS, int ESZ = 2>
 __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_constant__ CUtensorMap xmap, const BlockArgs a) {
-  using K = BCfg<C, R, SLOTS>;
+  using K = BCfg<C, R, SLOTS, ESZ>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW1 = smem;
@@ -144,7 +151,9 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       mbar_wait(bar_init, 0);                          // accumulators zeroed
       fence_after();
       // per slot: next tile number and whether its conv1 has been issued; a slot advances whenever its barrier has flipped
@@ -155,19 +164,21 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
         for (int k = 0; k < SLOTS; ++k) {
           const int t = nxt[k];
           if (t >= my_tiles) continue;
-          const uint32_t acc1 = tmem + k * K::ACC, acc2 = acc1 + K::ACC1;
+          const uint32_t acc1 = tmem_u + k * K::ACC, acc2 = acc1 + K::ACC1;
           if (stage[k] == 0) {
             const uint32_t s = t % K::NX;
             if (!mbar_test(bar_xfull + 8 * s, (t / K::NX) & 1)) continue;
             fence_after();
-            issue_conv<C, K::R1, K::LAYOUT>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1);
-            commit(bar_m1 + 8 * k);
+            issue_conv<C, K::R1, K::LAYOUT, ESZ>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1, leader);
+            if (leader) commit(bar_m1 + 8 * k);
+            __syncwarp();
             stage[k] = 1;
           } else {
             if (!mbar_test(bar_st + 8 * k, (t / SLOTS) & 1)) continue;       // intermediate tile written (and acc1 zeroed again)
             fence_after();
-            issue_conv<C, R, K::LAYOUT>(smem_u32(sT + k * K::T_AL), smem_u32(sW2), acc2);
-            commit(bar_m2 + 8 * k);
+            issue_conv<C, R, K::LAYOUT, ESZ>(smem_u32(sT + k * K::T_AL), smem_u32(sW2), acc2, leader);
+            if (leader) commit(bar_m2 + 8 * k);
+            __syncwarp();
             stage[k] = 0;
             nxt[k] = t + SLOTS;
             if (nxt[k] >= my_tiles) --live;
@@ -221,13 +232,22 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
           if (ri < K::R1) {
             const int iy = y0 - 1 + ri;
             const bool inside = col_in && iy >= 0 && iy < a.h;
-            uint32_t pk[C / 2];
+            uint32_t pk[C * ESZ / 4];
+            if (ESZ == 2) {
 #pragma unroll
-            for (int j = 0; j < C / 2; ++j) {
-              const float f0 = inside ? fmaxf(__uint_as_float(v[g][2 * j]) + sB1[2 * j], 0.f) : 0.f;
-              const float f1 = inside ? fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB1[2 * j + 1], 0.f) : 0.f;
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
-              pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+              for (int j = 0; j < C / 2; ++j) {
+                const float f0 = inside ? fmaxf(__uint_as_float(v[g][2 * j]) + sB1[2 * j], 0.f) : 0.f;
+                const float f1 = inside ? fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB1[2 * j + 1], 0.f) : 0.f;
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+                pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+            } else {
+              // the intermediate is an operand of kind::tf32, which truncates: round it here like TMA rounds the tensors it loads
+#pragma unroll
+              for (int j = 0; j < C; ++j) {
+                const float f0 = inside ? fmaxf(__uint_as_float(v[g][j]) + sB1[j], 0.f) : 0.f;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[j]) : "f"(f0));
+              }
             }
             const uint32_t row_ad = st_base + (ri * TW + m) * K::ROWB;
 #pragma unroll
@@ -252,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       const uint32_t sx_base = smem_u32(sX + s * K::X_AL);
 #pragma unroll 1
       for (int r0 = 0; r0 < R; r0 += G) {
-        uint32_t v[G][C], rv[G][C / 2];
+        uint32_t v[G][C], rv[G][C * ESZ / 4];
 #pragma unroll
         for (int g = 0; g < G; ++g)
           if (r0 + g < R) {
@@ -278,15 +298,21 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
           const int r = r0 + g;
           const int oy = y0 + r;
           if (r < R && col_ok && oy < a.h) {
-            uint32_t o[C / 2];
+            uint32_t o[C * ESZ / 4];
+            if (ESZ == 2) {
 #pragma unroll
-            for (int j = 0; j < C / 2; ++j) {
-              const float f0 = fmaxf(__uint_as_float(v[g][2 * j]) + sB2[2 * j] + __uint_as_float(rv[g][j] << 16), 0.f);
-              const float f1 = fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB2[2 * j + 1] + __uint_as_float(rv[g][j] & 0xffff0000u), 0.f);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
-              o[j] = *reinterpret_cast<uint32_t*>(&b2);
+              for (int j = 0; j < C / 2; ++j) {
+                const float f0 = fmaxf(__uint_as_float(v[g][2 * j]) + sB2[2 * j] + __uint_as_float(rv[g][j] << 16), 0.f);
+                const float f1 = fmaxf(__uint_as_float(v[g][2 * j + 1]) + sB2[2 * j + 1] + __uint_as_float(rv[g][j] & 0xffff0000u), 0.f);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+                o[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+            } else {
+              // the residual is the staged input tile, i.e. x as TMA rounded it to TF32 (2^-12 relative: inside the path's class)
+#pragma unroll
+              for (int j = 0; j < C; ++j) o[j] = __float_as_uint(fmaxf(__uint_as_float(v[g][j]) + sB2[j] + __uint_as_float(rv[g][j]), 0.f));
             }
-            uint4* op = reinterpret_cast<uint4*>(a.out + (((size_t)img * a.h + oy) * a.w + ox) * C);
+            uint4* op = reinterpret_cast<uint4*>((char*)a.out + (((size_t)img * a.h + oy) * a.w + ox) * C * ESZ);
 #pragma unroll
             for (int u = 0; u < K::ROWB / 16; ++u) op[u] = make_uint4(o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
           }
@@ -303,9 +329,9 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
-template <int C, int R, int SLOTS>
+template <int C, int R, int SLOTS, int ESZ = 2>
 int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
-  using K = BCfg<C, R, SLOTS>;
+  using K = BCfg<C, R, SLOTS, ESZ>;
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -313,37 +339,40 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
   }
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
     attr = true;
   }
   CUtensorMap map;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)w * C * 2, (cuuint64_t)h * w * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * ESZ, (cuuint64_t)w * C * ESZ, (cuuint64_t)h * w * C * ESZ};
   cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TW, (cuuint32_t)K::RX, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (encode(&map, ESZ == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              K::ROWB == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     ttk_set_error("cuTensorMapEncodeTiled failed for the fused block %s", c1.name.c_str());
     return TTK_ERR_CUDA;
   }
   BlockArgs a;
-  a.w1 = c1.w_umma, a.w2 = c2.w_umma, a.b1 = c1.bias, a.b2 = c2.bias, a.out = (__nv_bfloat16*)y;
+  a.w1 = ESZ == 2 ? (const void*)c1.w_umma : (const void*)c1.w_umma32, a.w2 = ESZ == 2 ? (const void*)c2.w_umma : (const void*)c2.w_umma32;
+  a.b1 = c1.bias, a.b2 = c2.bias, a.out = y;
   a.n = n, a.h = h, a.w = w;
   a.tiles_x = ttk_cdiv(w, WO), a.tiles_y = ttk_cdiv(h, R);
   a.total = a.tiles_x * a.tiles_y * n;
   const int grid = std::max(1, std::min(a.total, ttk_num_sms()));
-  block_umma_kernel<C, R, SLOTS><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
+  block_umma_kernel<C, R, SLOTS, ESZ><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
 }  // namespace
 
-// y = relu(conv2(relu(conv1(x))) + x) for two 3x3 stride-1 convolutions with cin = cout = 16 or 32 (padded), NHWC bf16.
-int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
+// y = relu(conv2(relu(conv1(x))) + x) for two 3x3 stride-1 convolutions with cin = cout = 16 or 32 (padded), NHWC bf16 (esz 2) or, for 16
+// channels, NHWC fp32 multiplied as TF32 (esz 4).
+int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st, int esz) {
   if (c1.k != 3 || c2.k != 3 || c1.stride != 1 || c2.stride != 1 || c1.cin_p != c1.cout_p || c2.cin_p != c1.cin_p || c2.cout_p != c1.cin_p)
     return TTK_ERR_UNSUPPORTED;
+  if (esz == 4) return c1.cin_p == 16 ? launch<16, 4, 1, 4>(c1, c2, x, y, n, h, w, st) : TTK_ERR_UNSUPPORTED;      // 64-byte rows, one slot
   if (c1.cin_p == 16) return launch<16, 6, 2>(c1, c2, x, y, n, h, w, st);      // two tiles in flight (2 x 224 TMEM columns)
   if (c1.cin_p == 32) return launch<32, 4, 1>(c1, c2, x, y, n, h, w, st);      // 320 TMEM columns per tile: one slot
   return TTK_ERR_UNSUPPORTED;

@@ -618,7 +618,10 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
   bool dual_skipped = false;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const TtkOp& op = h->ops[oi];
-    if (umma && sizeof(T) == 2 && h->use_block_fusion && is_basic_block(h, oi)) {
+    // TF32: the fused kernel exists (16 channels, one tile in flight: 227 KB do not hold a second slot of fp32 tiles) and is parity-green,
+    // but M1 -> E1 -> M2 -> E2 of a single tile run back to back: 2.19 ms per block against 1.50 ms for the two HBM-bound convolutions, so
+    // it is used only when asked for (use_block_fusion == 2)
+    if (umma && is_basic_block(h, oi) && ((esz == 2 && h->use_block_fusion) || (esz == 4 && h->use_block_fusion == 2 && h->convs[op.conv].cin_p == 16))) {
       const TtkOp& op2 = h->ops[oi + 1];
       const TtkTensor& ti = h->tensors[op.in];
       auto p2 = [&](int t) -> void* { return t == h->input_tensor ? const_cast<void*>(x) : (void*)(ws + h->tensors[t].offset); };
@@ -632,7 +635,7 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
         r.flops += 2.0 * opix * c2.cin * c2.cout * 9;
         r.bytes = 2.0 * opix * ti.c * sizeof(T) + 2.0 * 9 * ti.c * ti.c * sizeof(T);
       }
-      const int rc = ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st);
+      const int rc = ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st, esz);
       if (rc == TTK_OK) {
         h->launches++;
         ++oi;                                      // conv2 is done as well
@@ -970,12 +973,12 @@ extern "C" int ttk_hrnet_debug_block(ttk_hrnet* h, int conv_index, const void* i
   TTK_CHECK_ARG(h && conv_index >= 0 && conv_index + 1 < (int)h->convs.size() - 1, "ttk_hrnet_debug_block: bad conv index %d", conv_index);
   const TtkConv &c1 = h->convs[conv_index], &c2 = h->convs[conv_index + 1];
   TTK_CHECK_ARG(c1.set && c2.set, "ttk_hrnet_debug_block: weights not set");
-  return ttk_block_umma_launch(c1, c2, in_dev, out_dev, n, hin, win, (cudaStream_t)stream);
+  return ttk_block_umma_launch(c1, c2, in_dev, out_dev, n, hin, win, (cudaStream_t)stream, 2);
 }
 
 extern "C" int ttk_hrnet_set_block_fusion(ttk_hrnet* h, int enable) {
   TTK_CHECK_ARG(h, "ttk_hrnet_set_block_fusion: null handle");
-  h->use_block_fusion = enable ? 1 : 0;
+  h->use_block_fusion = enable;          // 0 off, 1 bf16 blocks (default), 2 also the TF32 16-channel blocks
   return TTK_OK;
 }
 

@@ -72,10 +72,9 @@ struct ttk_hrnet {
   bool dual_ready = false;
   int use_dual = 1;
   int cur_esz = 0;              // element size of the tensor-core path the running forward uses (0: SIMT), for the profile records
-  int use_block_fusion = 0;     // BasicBlocks of the 16- and 32-channel branches as one kernel (block_umma.cu).  Off: measured
-                                // break-even (31.8 vs 31.2-32.0 ms per 32 stacks); the thin-channel MMAs cost ~79 clk each on the
-                                // tensor pipe whatever N <= 48 is, and the fused tile needs 9 of them per output row (halo rows of
-                                // the intermediate) against 7.5 for the two separate kernels, see DESIGN.md section 4.2
+  int use_block_fusion = 1;     // BasicBlocks as one kernel (block_umma.cu): the 16- and 32-channel branches in bf16, the 16-channel branch
+                                // in TF32.  Round 1 measured break-even in bf16 because the thin MMAs were issue bound (16 instructions per
+                                // tcgen05.mma); with the warp-uniform issue loop the fused blocks win
   // optional per-launch timing (ttk_hrnet_set_profile): events bracket every launch on the caller's stream
   int profile = 0;
   std::vector<cudaEvent_t> events;     // pool, events[i] precedes launch i
@@ -93,4 +92,4 @@ int ttk_conv_umma_launch_dual(const void* w_dual, const float* bias_dual, const 
 void ttk_conv_umma_pack_dual(const float* w3, const float* wd, int esz, std::vector<uint8_t>& out);
 
 // block_umma.cu: y = relu(conv2(relu(conv1(x))) + x) for the 3x3 stride-1 pairs of a BasicBlock with 16 or 32 (padded) channels.
-int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st);
+int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st, int esz = 2);

@@ -169,6 +169,9 @@ def test_network_block_fusion_tf32(net):
         lib.ttk_hrnet_set_block_fusion(m.engine.h, 1)
         m.compute_dtype = torch.float32
     assert n_off - n_on == 6
+    # the pruned plan: 72 convolutions of the reference graph - 13 whose outputs nothing reads - the projection shortcut folded into
+    # conv3's GEMM, + 3 fuse sums + the final layer (tests/test_abi.py::test_hrnet_plan_drops_unread_outputs)
+    assert n_off == 72 - 13 - 1 - 1 + 3 + 1, n_off
     ref = ohr.wasb_forward(sd, x.cpu()).numpy()
     scale = np.abs(ref).max()
     assert np.abs(y_on.cpu().numpy() - ref).max() <= 1e-2 * scale          # the path's stated bound

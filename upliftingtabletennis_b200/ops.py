@@ -80,9 +80,9 @@ def trajectory_pack(ball_xy, times, offsets, table, seq_len=50, img_w=1920.0, im
     table_o = torch.empty((n, 13, 3), dtype=torch.float32, device=dev)
     times_o = torch.empty((n, seq_len), dtype=torch.float32, device=dev)
     mask_o = torch.empty((n, seq_len), dtype=torch.float32, device=dev)
-    check(lib.ttk_trajectory_pack(ptr(ball_xy.contiguous()), ptr(times.contiguous()), ptr(offsets.contiguous()),
-                                  ptr(table.contiguous()), n, seq_len, float(img_w), float(img_h), ptr(ball_o), ptr(table_o),
-                                  ptr(times_o), ptr(mask_o), stream_ptr()))
+    ball_xy, times, offsets, table = ball_xy.contiguous(), times.contiguous(), offsets.contiguous(), table.contiguous()     # held until the call returns
+    check(lib.ttk_trajectory_pack(ptr(ball_xy), ptr(times), ptr(offsets), ptr(table), n, seq_len, float(img_w), float(img_h), ptr(ball_o),
+                                  ptr(table_o), ptr(times_o), ptr(mask_o), stream_ptr()))
     return ball_o, table_o, times_o, mask_o
 
 

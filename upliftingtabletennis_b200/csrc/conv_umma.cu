@@ -92,10 +92,12 @@ struct Cfg {
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
   static_assert(!HF || (KS == 3 && S == 1 && 9 * COUT <= 256 && COUT == 16 && !RB), "horizontal tap fusion: 3x3 stride 1, 16 output channels, no staged residual");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
-  static constexpr int GCOLS = ACC_COLS < (ESZ == 2 ? 64 : 32) ? ACC_COLS : (ESZ == 2 ? 64 : 32);     // accumulator columns fetched per TMEM wait
-  // software-pipelined epilogue (see the kernel); not with TMA-staged residual tiles, whose shared-memory reads have no latency to hide
-  // (the full-resolution 16 -> 16 layers ran at 6.5 TB/s without it, 5.7 TB/s with it)
-  static constexpr bool PIPE = ESZ == 4 && S == 1 && !RB && !HF && ACC_COLS / GCOLS >= 2;
+  // software-pipelined epilogue (see the kernel): stride-1 layers without TMA-staged residual tiles, whose shared-memory reads have no
+  // latency to hide (the full-resolution 16 -> 16 layers ran at 6.5 TB/s without it, 5.7 TB/s with it).  TF32: all of them; bf16: the
+  // wide layers (64+ output channels per CTA), whose epilogue -- one warp per scheduler -- is what bounds them
+  static constexpr bool PIPE = S == 1 && !RB && !HF && ACC_COLS >= 64 && (ESZ == 4 || COUT >= 64);
+  static constexpr int GMAX = (ESZ == 2 && !PIPE) ? 64 : 32;
+  static constexpr int GCOLS = ACC_COLS < GMAX ? ACC_COLS : GMAX;     // accumulator columns fetched per TMEM wait
   static_assert(ESZ == 2 || ESZ == 4, "bf16 or tf32-in-fp32 elements");
   static_assert(ACC_COLS % GCOLS == 0, "the epilogue drains whole groups of accumulator columns");
   static_assert(ROWB == 32 || ROWB == 64 || ROWB == 128, "a K-chunk is one 32/64/128-byte swizzled row");
@@ -420,7 +422,7 @@ __global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");        // the exchange buffer is free for the next tile
       } else if constexpr (C::PIPE) {
-        // Software-pipelined drain (TF32 stride-1 layers, at most one residual): the TMEM load and the residual loads of column
+        // Software-pipelined drain (stride-1 layers without staged residual tiles, at most one residual): the TMEM load and the residual loads of column
         // group g + 1 are in flight while group g is added up and stored, so neither latency is exposed per group (stem conv1 ran at
         // 59 % of the HBM rate waiting for one tcgen05.ld at a time; residuals read from global memory cost ~1 us per group).
         constexpr int G = C::ACC_COLS / GCOLS;
@@ -473,11 +475,21 @@ __global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel
               for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
             char* op = (char*)a.out + ((((size_t)img * a.h + oy) * a.w_img + ox) * a.cout_total + n_off + c0) * ESZ;
-            uint32_t o[16];
+            if (ESZ == 2) {
+              uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(f[j]);
-            stg256(op, o);
-            stg256(op + 32, o + 8);
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                o[j] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              stg256(op, o);
+            } else {
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(f[j]);
+              stg256(op, o);
+              stg256(op + 32, o + 8);
+            }
           }
           if (g + 1 < G) {
             tmem_wait_ld();

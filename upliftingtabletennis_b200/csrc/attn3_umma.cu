@@ -1,0 +1,323 @@
+// Multi-head self-attention of the ViTPose backbone with fp32-level results on the tensor cores (3xTF32), the reference-precision
+// sibling of attn_umma.cu (same flash-attention schedule, same roles):
+//   out = softmax((q * 32^-0.5) k^T) v per (image, head)      vit_pose/vit_models/backbone/vit.py:160-176 (Attention.forward)
+// Every operand is a split float32 pair x = hi + lo (hi = tf32(x), lo = tf32(x - hi)); every product is three kind::tf32 MMAs
+// (lo*hi + hi*lo + hi*hi, float32 accumulation in TMEM), which leaves ~2^-21 relative error per product -- float32 class.
+// qkv [2][images * tokens][3 * 384] float32 planes as the x3 qkv GEMM wrote them; out [2][T][384] planes (the proj GEMM's A operand).
+//
+// One CTA = one (image, head, 128-query tile); it walks the key tiles (64 keys) once:
+//   S   = Q K_j^T           3 x 4 tcgen05.mma 128 x 64 x 8; Q / K_j hi | lo tiles staged by TMA (128-byte rows = 32 floats), S in TMEM
+//   P_j = exp2(S*c - m)     two threads per query row (32 keys each): scores to registers, S is then free for the next Q K^T; running
+//                           maximum in registers, P_j split and written as float32 hi / lo K-major A operands (128-byte swizzle)
+//   O  += P_j V_j           3 x 8 tcgen05.mma 128 x 48 x 8; V staged TRANSPOSED ([dim][key] hi / lo planes from a small transpose
+//                           kernel) with a row of ones appended, so the row sums of P come out of the same MMAs.  Each key tile's
+//                           P_j V_j is a FRESH TMEM accumulation that the softmax threads add to register accumulators
+//                           (rescaled by 2^(m_old - m_new), round-to-nearest): the tensor core's float32 accumulate truncates, and
+//                           a chain over all 45 key tiles (1080 MMAs) measured 1.8e-5 relative error -- per tile it is 24 MMAs.
+// 128 x 64 tiles because the float32 P pair alone takes 64 KB of shared memory; 216 KB in all, one CTA per SM.  The tensor pipe
+// bounds it: thin MMAs (N = 64 / 48) take their ~45 clk floor each, 36 of them per tile against 512 clk of exponentials.
+#include "umma_prims.h"
+#include "vit.h"
+
+namespace {
+
+using namespace umma;
+
+constexpr int HD = 32, BQ = 128, BKEY = 64, NST = 3, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
+constexpr int Q_PLANE = BQ * 128, Q_BYTES = 2 * Q_PLANE;                 // hi | lo, 128-byte rows
+constexpr int K_PLANE = BKEY * 128, K_BYTES = 2 * K_PLANE;
+constexpr int VR = 48;                                 // rows of the staged V^T tile: 32 dims, a row of ones, 15 rows of zeros (N % 16 == 0)
+constexpr int V_CHUNK = VR * 128;                      // one 32-key chunk [48 rows][128 B]
+constexpr int V_PLANE = 2 * V_CHUNK, V_BYTES = 2 * V_PLANE;
+constexpr int KV_BYTES = K_BYTES + V_BYTES;            // 40 KB
+constexpr int P_CHUNK = BQ * 128;                      // one 32-key chunk [128 rows][128 B]
+constexpr int P_PLANE = 2 * P_CHUNK, P_BYTES = 2 * P_PLANE;      // 64 KB
+constexpr int X_BYTES = 4 * BQ * 4;                    // row maxima (2 parities x 2 halves) exchanged between partner warps
+constexpr int SMEM_BYTES = Q_BYTES + NST * KV_BYTES + P_BYTES + X_BYTES + 256;
+constexpr int TMEM_COLS = 128;                         // S: 64 columns, O: 48
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct Attn3Maps {
+  CUtensorMap qkv;     // [2][images][tokens][3*dim] float32, box {32, rows, 1, 2}: one for Q (128 rows) ...
+  CUtensorMap kk;      // ... one for K (64 rows)
+  CUtensorMap vt;      // [2][images][heads*48][tok_pad] float32, box {32, 48, 1, 2}
+};
+
+// V^T planes with the extra rows: vt[p][img][head*48 + d][token] = v_p[img][token][head*32 + d] for d < 32; ones row (hi plane only) at
+// d == 32 for existing tokens; 0 elsewhere
+__global__ void __launch_bounds__(256) v_transpose3_kernel(const float* __restrict__ qkv, size_t qkv_plane, int tokens, int tok_pad, int dim,
+                                                           float* __restrict__ vt, size_t vt_plane) {
+  __shared__ float tile[2][64][HD + 1];
+  const int t0 = blockIdx.x * 64, head = blockIdx.y, img = blockIdx.z;
+  const int heads = dim / HD;
+  for (int i = threadIdx.x; i < 2 * 64 * HD; i += 256) {
+    const int p = i / (64 * HD), t = (i / HD) % 64, d = i % HD;
+    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const char*>(qkv) + p * qkv_plane);
+    tile[p][t][d] = t0 + t < tokens ? src[((size_t)img * tokens + t0 + t) * 3 * dim + 2 * dim + head * HD + d] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 64 * VR; i += 256) {
+    const int p = i / (64 * VR), d = (i / 64) % VR, t = i % 64;
+    float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(vt) + p * vt_plane) + ((size_t)img * heads + head) * VR * tok_pad;
+    if (t0 + t < tok_pad) base[(size_t)d * tok_pad + t0 + t] = d < HD ? tile[p][t][d] : (d == HD && p == 0 && t0 + t < tokens ? 1.f : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __grid_constant__ Attn3Maps maps, float* __restrict__ out,
+                                                                     size_t out_plane, int tokens, int dim) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Q_BYTES;
+  uint8_t* sP = sKV + NST * KV_BYTES;
+  uint8_t* sX = sP + P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sX + X_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
+  const uint32_t bar_kv_full = smem_u32(bars), bar_kv_empty = bar_kv_full + 8 * NST, bar_q = bar_kv_empty + 8 * NST, bar_s_full = bar_q + 8,
+                 bar_s_empty = bar_s_full + 8, bar_p_full = bar_s_empty + 8, bar_o_full = bar_p_full + 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
+  const int nk = (tokens + BKEY - 1) / BKEY;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();          // the swizzled tiles need 1024-byte alignment
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bar_kv_full + 8 * s, 1);
+      mbar_init(bar_kv_empty + 8 * s, 1);
+    }
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s_full, 1);
+    mbar_init(bar_s_empty, 8);
+    mbar_init(bar_p_full, 8);
+    mbar_init(bar_o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // TMA + MMA warp: all lanes walk the loop with warp-uniform values, one elected lane issues (see conv_umma.cu)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t tS = tmem_u, tO = tmem_u + BKEY;
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKEY), idesc_o = make_idesc_tf32(BQ, VR);
+    auto load_kv = [&](int j) {
+      const uint32_t s = j % NST;
+      if (leader) {
+        mbar_expect_tx(bar_kv_full + 8 * s, KV_BYTES);
+        const uint32_t dst = smem_u32(sKV + s * KV_BYTES);
+        tma_load_4d(dst, &maps.kk, bar_kv_full + 8 * s, dim + head * HD, j * BKEY, img, 0);
+        // V^T chunks: [plane][chunk][48 rows][128 B]; a box brings one 32-key chunk of both planes -> strided destination, so
+        // one box per (plane, chunk) would need 4 loads; instead the planes are interleaved per chunk: [chunk][plane] (see issue_o)
+        tma_load_4d(dst + K_BYTES, &maps.vt, bar_kv_full + 8 * s, j * BKEY, head * VR, img, 0);
+        tma_load_4d(dst + K_BYTES + 2 * V_CHUNK, &maps.vt, bar_kv_full + 8 * s, j * BKEY + 32, head * VR, img, 0);
+      }
+    };
+    auto issue_s = [&](int j) {
+      const uint32_t s = j % NST;
+      mbar_wait(bar_kv_full + 8 * s, (j / NST) & 1);
+      fence_after();
+      const uint32_t a0 = smem_u32(sQ) >> 4, b0 = smem_u32(sKV + s * KV_BYTES) >> 4;
+#pragma unroll
+      for (int k8 = 0; k8 < HD / 8; ++k8) {
+        const uint64_t ah = make_desc16<1024, 2>(a0 + k8 * 2), al = make_desc16<1024, 2>(a0 + Q_PLANE / 16 + k8 * 2);
+        const uint64_t bh = make_desc16<1024, 2>(b0 + k8 * 2), bl = make_desc16<1024, 2>(b0 + K_PLANE / 16 + k8 * 2);
+        if (leader) {
+          mma_tf32(tS, al, bh, idesc_s, k8 ? 1u : 0u);
+          mma_tf32(tS, ah, bl, idesc_s, 1u);
+          mma_tf32(tS, ah, bh, idesc_s, 1u);
+        }
+      }
+      if (leader) commit(bar_s_full);
+    };
+    if (leader) {
+      mbar_expect_tx(bar_q, Q_BYTES);
+      tma_load_4d(smem_u32(sQ), &maps.qkv, bar_q, head * HD, q0, img, 0);
+    }
+    for (int j = 0; j < NST && j < nk; ++j) load_kv(j);
+    mbar_wait(bar_q, 0);
+    issue_s(0);
+    for (int j = 0; j < nk; ++j) {
+      if (j + 1 < nk) {
+        mbar_wait(bar_s_empty, j & 1);           // softmax has read S_j out of TMEM
+        fence_after();
+        issue_s(j + 1);
+      }
+      mbar_wait(bar_p_full, j & 1);              // P_j is in shared memory (and O_{j-1} has been consumed)
+      fence_after();
+      const uint32_t s = j % NST;
+      const uint32_t p0 = smem_u32(sP) >> 4, v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES) >> 4;
+#pragma unroll
+      for (int k8 = 0; k8 < BKEY / 8; ++k8) {
+        // P: [plane][chunk][128 rows][128 B]; V^T: [chunk][plane][48 rows][128 B]
+        const uint32_t pc = (k8 >> 2) * (P_CHUNK / 16) + (k8 & 3) * 2, vc = (k8 >> 2) * (2 * V_CHUNK / 16) + (k8 & 3) * 2;
+        const uint64_t ph = make_desc16<1024, 2>(p0 + pc), pl = make_desc16<1024, 2>(p0 + P_PLANE / 16 + pc);
+        const uint64_t vh = make_desc16<1024, 2>(v0 + vc), vl = make_desc16<1024, 2>(v0 + V_CHUNK / 16 + vc);
+        if (leader) {
+          mma_tf32(tO, pl, vh, idesc_o, k8 ? 1u : 0u);             // this tile's P V (and row sums); the softmax threads accumulate over tiles
+          mma_tf32(tO, ph, vl, idesc_o, 1u);
+          mma_tf32(tO, ph, vh, idesc_o, 1u);
+        }
+      }
+      if (leader) {
+        commit(bar_kv_empty + 8 * s);
+        commit(bar_o_full);
+      }
+      if (j + NST < nk) {                          // refill this stage once P_j V_j has read it
+        mbar_wait(bar_kv_empty + 8 * s, (j / NST) & 1);
+        load_kv(j + NST);
+      }
+      __syncwarp();
+    }
+  } else {
+    // softmax warps 0..7: warp w and w+4 share TMEM lanes 32 (w % 4) .., i.e. the same 32 query rows; `half` picks the 32 key
+    // columns (= one swizzled P chunk) and the 16 output dimensions a thread owns
+    const uint32_t tS = tmem, tO = tmem + BKEY;
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;                  // query row of this thread = TMEM lane
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float sl2 = 0.17677669529663687f * 1.4426950408889634f;      // 32^-0.5 * log2(e)
+    float m_run = -INFINITY, l_acc = 0.f, o_acc[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o_acc[d] = 0.f;
+    constexpr int HK = BKEY / 2;
+    const uint32_t p_row = smem_u32(sP) + half * P_CHUNK + row * 128;
+    float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima
+    auto take_o = [&](float scale) {                // (accumulators + the finished tile's P V) * scale
+      uint32_t v[16], w;
+      tmem_ld16(tO + lane_base + half * 16, v);
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(w) : "r"(tO + lane_base + HD));      // column 32: sum_k P[row][k]
+      tmem_wait_ld();
+#pragma unroll
+      for (int d = 0; d < 16; ++d) o_acc[d] = (o_acc[d] + __uint_as_float(v[d])) * scale;
+      l_acc = (l_acc + __uint_as_float(w)) * scale;
+    };
+    for (int j = 0; j < nk; ++j) {
+      const int valid = min(BKEY, tokens - j * BKEY) - half * HK;        // keys of this thread's half that exist (may be <= 0)
+      mbar_wait(bar_s_full, j & 1);
+      fence_after();
+      uint32_t sv[HK];
+      tmem_ld32(tS + lane_base + half * HK, sv);
+      tmem_wait_ld();
+      fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_s_empty);
+      if (valid < HK) {                                                  // last key tile only (warp-uniform)
+#pragma unroll
+        for (int i = 0; i < HK; ++i)
+          if (i >= valid) sv[i] = 0xff800000u;                           // -inf
+      }
+      float mx4[4] = {__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]), __uint_as_float(sv[3])};
+#pragma unroll
+      for (int i = 4; i < HK; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mx4[k] = fmaxf(mx4[k], __uint_as_float(sv[i + k]));
+      }
+      float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      xch[((j & 1) * 2 + half) * BQ + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BQ + row]);
+      const float m_new = fmaxf(m_run, mx * sl2);   // finite: every key tile has at least one existing key
+      const float alpha = ex2(m_run - m_new);       // (0 for j == 0, unused there)
+      m_run = m_new;
+      // exponentials: they need neither O nor the P buffer, so they overlap the P_{j-1} V_{j-1} MMAs
+      float p[HK];
+#pragma unroll
+      for (int i = 0; i < HK; ++i) p[i] = ex2(fmaf(__uint_as_float(sv[i]), sl2, -m_run));
+      if (j > 0) {                                   // P_{j-1} V_{j-1} has landed: into the register accumulators, on to this tile's scale
+        mbar_wait(bar_o_full, (j - 1) & 1);
+        fence_after();
+        take_o(alpha);
+      }
+      // P_j -> shared memory as hi / lo float32 planes (128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
+#pragma unroll
+      for (int u = 0; u < HK / 4; ++u) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(p[4 * u + e], h[e], l[e]);
+        const uint32_t a = p_row + (((uint32_t)u ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + P_PLANE), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+      }
+      fence_before();                                // the reads of O_{j-1} are ordered before the MMAs that overwrite it
+      fence_async_smem();                            // P_j visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_full);
+    }
+    mbar_wait(bar_o_full, (nk - 1) & 1);
+    fence_after();
+    take_o(1.f);
+    if (q0 + row < tokens) {
+      const float inv = 1.f / l_acc;
+      float* op = out + ((size_t)img * tokens + q0 + row) * dim + head * HD + half * 16;
+      float* ol = reinterpret_cast<float*>(reinterpret_cast<char*>(op) + out_plane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split_tf32(o_acc[4 * i + e] * inv, h[e], l[e]);
+        reinterpret_cast<float4*>(op)[i] = make_float4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<float4*>(ol)[i] = make_float4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+}  // namespace
+
+size_t ttk_attention3_scratch_bytes(int images, int tokens, int heads, int head_dim) {
+  const size_t tok_pad = (size_t)(tokens + 7) / 8 * 8;
+  (void)head_dim;
+  return 2 * (size_t)images * heads * VR * tok_pad * 4;
+}
+
+int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_plane, void* vt_scratch, int images, int tokens, int heads,
+                   int head_dim, cudaStream_t st) {
+  if (head_dim != HD || images <= 0 || tokens <= 0 || images > 65535 || qkv_plane % 16 || out_plane % 16) {
+    ttk_set_error("ttk_attention3: unsupported shape (head_dim %d, tokens %d, images %d)", head_dim, tokens, images);
+    return TTK_ERR_UNSUPPORTED;
+  }
+  const int dim = heads * HD, tok_pad = (tokens + 7) / 8 * 8;
+  static bool attr = false;
+  if (!attr) {
+    TTK_CUDA(cudaFuncSetAttribute(attention3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  float* vt = (float*)vt_scratch;
+  const size_t vt_plane = (size_t)images * heads * VR * tok_pad * 4;
+  v_transpose3_kernel<<<dim3(ttk_cdiv(tok_pad, 64), heads, images), 256, 0, st>>>(qkv, qkv_plane, tokens, tok_pad, dim, vt, vt_plane);
+  TTK_LAUNCH_CHECK();
+  Attn3Maps maps;
+  bool ok = true;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)3 * dim, (cuuint64_t)tokens, (cuuint64_t)images, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)3 * dim * 4, (cuuint64_t)tokens * 3 * dim * 4, (cuuint64_t)qkv_plane};
+    cuuint32_t box_q[4] = {HD, BQ, 1, 2}, box_k[4] = {HD, BKEY, 1, 2};
+    ok = ok && encode_f32(&maps.qkv, qkv, 4, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
+    ok = ok && encode_f32(&maps.kk, qkv, 4, dims, strides, box_k, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)tokens, (cuuint64_t)heads * VR, (cuuint64_t)images, 2};
+    cuuint64_t strides[3] = {(cuuint64_t)tok_pad * 4, (cuuint64_t)heads * VR * tok_pad * 4, (cuuint64_t)vt_plane};
+    cuuint32_t box[4] = {32, VR, 1, 2};
+    ok = ok && encode_f32(&maps.vt, vt, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (!ok) {
+    ttk_set_error("ttk_attention3: cuTensorMapEncodeTiled failed");
+    return TTK_ERR_CUDA;
+  }
+  attention3_umma_kernel<<<dim3(ttk_cdiv(tokens, BQ), heads, images), THREADS, SMEM_BYTES, st>>>(maps, out, out_plane, tokens, dim);
+  TTK_LAUNCH_CHECK();
+  return TTK_OK;
+}

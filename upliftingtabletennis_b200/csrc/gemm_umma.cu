@@ -15,7 +15,7 @@ namespace {
 
 using namespace umma;
 
-constexpr int BM = 128, BK = 64, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
+constexpr int BM = 128, THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps
 constexpr int STG_ROW = 80;         // bytes per staged output row piece (64 + 16 padding: conflict-free 16-byte accesses)
 
 
@@ -29,12 +29,18 @@ struct GemmMaps {
 // WRES: the whole BN x K weight tile (K = 384 = 6 k-blocks) stays in shared memory and the CTA walks M tiles of one N tile, so only
 // A streams through the ring.  L2 -> SM operand traffic, not the tensor pipe, bounds the streaming variant (~42 B/clk per SM
 // against 40 KB per 384 clk of MMA); with the weights resident it drops from 40 KB to 16 KB per k-block.
+// X3 (3xTF32, fp32-level results): operands are split float32 plane pairs (hi | lo, vit.h), a k-block is 32 floats (the same 128-byte
+// rows), a stage holds A_hi | A_lo | W_hi | W_lo (one TMA box with a plane dimension per operand) and every k8 step issues three
+// kind::tf32 MMAs: lo*hi, hi*lo, hi*hi.  64 KB per stage against 12 x 64 clk of MMA: the L2 -> SM operand stream bounds it.
 constexpr int KB_RES = 6;
-template <int BN, bool WRES>
+template <int BN, bool WRES, bool X3 = false>
 struct GCfg {
-  static constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+  static_assert(!X3 || !WRES, "the split weights of an N tile do not fit in shared memory");
+  static constexpr int BK = X3 ? 32 : 64;            // elements per k-block
+  static constexpr int A_PLANE = BM * 128, W_PLANE = BN * 128;
+  static constexpr int A_BYTES = (X3 ? 2 : 1) * A_PLANE, W_BYTES = (X3 ? 2 : 1) * W_PLANE;
   static constexpr int STAGE_BYTES = WRES ? A_BYTES : A_BYTES + W_BYTES;
-  static constexpr int STAGES = WRES ? (BN == 192 ? 3 : 6) : (BN == 128 ? 6 : BN == 192 ? 5 : 4);
+  static constexpr int STAGES = X3 ? 3 : WRES ? (BN == 192 ? 3 : 6) : (BN == 128 ? 6 : BN == 192 ? 5 : 4);
   static constexpr int WRES_BYTES = WRES ? KB_RES * W_BYTES : 0;
   static constexpr int RING_BYTES = WRES_BYTES + STAGES * STAGE_BYTES;
   static constexpr int TMEM_COLS = BN == 128 ? 256 : 512;
@@ -79,9 +85,10 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
 
-template <int BN, bool WRES, int ACT>
+template <int BN, bool WRES, int ACT, bool X3>
 __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_constant__ GemmMaps maps, const GemmArgs g, int tiles_m, int tiles_n) {
-  using C = GCfg<BN, WRES>;
+  using C = GCfg<BN, WRES, X3>;
+  constexpr int BK = C::BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem + C::WRES_BYTES;             // [resident W k-blocks][A (+ W) stages]
@@ -132,35 +139,56 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
             const int ptx = (g.up_w + PW - 1) / PW, pty = (g.up_h + PH - 1) / PH;
             const int px0 = (tm % ptx) * PW, py0 = ((tm / ptx) % pty) * PH, img = tm / (ptx * pty);
             const int dy = (tap >> 1) == 0 ? 0 : (g.py ? 1 : -1), dx = (tap & 1) == 0 ? 0 : (g.px ? 1 : -1);
-            tma_load_4d(dst, &maps.a, bar_full + 8 * s, kc * BK, px0 + dx, py0 + dy, img);
+            if (X3) tma_load_5d(dst, &maps.a, bar_full + 8 * s, kc * BK, px0 + dx, py0 + dy, img, 0);
+            else tma_load_4d(dst, &maps.a, bar_full + 8 * s, kc * BK, px0 + dx, py0 + dy, img);
+          } else if (X3) {
+            tma_load_3d(dst, &maps.a, bar_full + 8 * s, kb * BK, tm * BM, 0);
           } else {
             tma_load_2d(dst, &maps.a, bar_full + 8 * s, kb * BK, tm * BM);
           }
-          if (!WRES) tma_load_2d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN);
+          if (X3) tma_load_3d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN, 0);
+          else if (!WRES) tma_load_2d(dst + C::A_BYTES, &maps.w, bar_full + 8 * s, kb * BK, tn * BN);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    // the whole warp walks the loops with warp-uniform values, one elected lane issues (conv_umma.cu explains why)
+    {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const bool leader = elect_one();
+      constexpr uint32_t idesc = X3 ? make_idesc_tf32(BM, BN) : make_idesc(BM, BN);
       uint32_t it = 0, tcount = 0;
       if (WRES && walk.first < walk.limit) mbar_wait(bar_w, 0);
       for (int tile = walk.first; tile < walk.limit; tile += walk.step, ++tcount) {
         const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);        // accumulator drained by the epilogue (passes at once the first two times)
         fence_after();
-        const uint32_t d = tmem + acc * BN;
+        const uint32_t d = tmem_u + acc * BN;
         for (int kb = 0; kb < kblocks; ++kb, ++it) {
           const uint32_t s = it % C::STAGES, ph = (it / C::STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
           fence_after();
-          const uint32_t a0 = smem_u32(ring + s * C::STAGE_BYTES), b0 = WRES ? smem_u32(smem + kb * C::W_BYTES) : a0 + C::A_BYTES;
+          const uint32_t a0 = smem_u32(ring + s * C::STAGE_BYTES) >> 4, b0 = WRES ? smem_u32(smem + kb * C::W_BYTES) >> 4 : a0 + C::A_BYTES / 16;
+          if (X3) {
 #pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16)
-            mma(d, make_desc(a0 + k16 * 32, 1024, 2), make_desc(b0 + k16 * 32, 1024, 2), idesc, (kb | k16) ? 1u : 0u);
-          commit(bar_empty + 8 * s);
+            for (int k8 = 0; k8 < 4; ++k8) {
+              const uint64_t ah = make_desc16<1024, 2>(a0 + k8 * 2), al = make_desc16<1024, 2>(a0 + C::A_PLANE / 16 + k8 * 2);
+              const uint64_t bh = make_desc16<1024, 2>(b0 + k8 * 2), bl = make_desc16<1024, 2>(b0 + C::W_PLANE / 16 + k8 * 2);
+              if (leader) {
+                mma_tf32(d, al, bh, idesc, (kb | k8) ? 1u : 0u);
+                mma_tf32(d, ah, bl, idesc, 1u);
+                mma_tf32(d, ah, bh, idesc, 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              if (leader) mma(d, make_desc16<1024, 2>(a0 + k16 * 2), make_desc16<1024, 2>(b0 + k16 * 2), idesc, (kb | k16) ? 1u : 0u);
+          }
+          if (leader) commit(bar_empty + 8 * s);
         }
-        commit(bar_tfull + 8 * acc);
+        if (leader) commit(bar_tfull + 8 * acc);
+        __syncwarp();
       }
     }
   } else {
@@ -176,6 +204,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     const bool implicit = g.implicit_c > 0;
     const int gM = g.M, gN = g.N, dbg = g.act >> 8, r_mod = g.r_mod, up_w = g.up_w, up_h = g.up_h, upy = g.py, upx = g.px;
     const bool c_bf16 = g.c_bf16 != 0;
+    const bool c_split = X3 && g.c_split != 0;
+    const long long c_plane = (long long)g.c_plane;
     const float* __restrict__ gR = g.R;
     const float* __restrict__ gBias = g.bias;
     uint8_t* const gC = (uint8_t*)g.C;
@@ -256,7 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
         // stage 64-byte row pieces of the warp's 32 x 32 block in shared memory, then write them out row-contiguous (4 lanes per row,
         // full 32-byte sectors): bf16 = one piece of 32 columns, float32 = two pieces of 16 columns
         const uint32_t my = stg_u32 + lane * STG_ROW;
-        const int pieces = c_bf16 ? 1 : 2;
+        const int pieces = c_bf16 ? 1 : c_split ? 4 : 2;      // split: two float32 pieces of the hi plane, then of the lo plane
 #pragma unroll 1
         for (int pc = 0; pc < pieces; ++pc) {
           if (c_bf16) {
@@ -274,8 +304,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               // f[16 * pc + 4 * j ..]: select without dynamic register indexing
-              const float a0 = pc ? f[16 + 4 * j] : f[4 * j], a1 = pc ? f[17 + 4 * j] : f[4 * j + 1], a2 = pc ? f[18 + 4 * j] : f[4 * j + 2],
-                          a3 = pc ? f[19 + 4 * j] : f[4 * j + 3];
+              float a0 = (pc & 1) ? f[16 + 4 * j] : f[4 * j], a1 = (pc & 1) ? f[17 + 4 * j] : f[4 * j + 1],
+                    a2 = (pc & 1) ? f[18 + 4 * j] : f[4 * j + 2], a3 = (pc & 1) ? f[19 + 4 * j] : f[4 * j + 3];
+              if (c_split) {
+                float h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(a0, h0, l0), split_tf32(a1, h1, l1), split_tf32(a2, h2, l2), split_tf32(a3, h3, l3);
+                const bool lo = pc >= 2;
+                a0 = lo ? l0 : h0, a1 = lo ? l1 : h1, a2 = lo ? l2 : h2, a3 = lo ? l3 : h3;
+              }
               asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(my + 16 * j), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
             }
           }
@@ -285,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
           for (int i = 0; i < 4; ++i)
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(val[i].x), "=r"(val[i].y), "=r"(val[i].z), "=r"(val[i].w)
                          : "r"(stg_u32 + (8 * i + rsel) * STG_ROW + usel * 16));
-          const long long coff = (long long)(n + pc * 16) * esz;
+          const long long coff = (long long)(n + (pc & 1) * 16) * esz + (pc >= 2 ? c_plane : 0);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             if (obase[i] >= 0 && !(dbg & 2)) *reinterpret_cast<uint4*>(gC + obase[i] + coff) = val[i];
@@ -302,18 +338,39 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
   if (warp == 2) tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
-template <int BN, bool WRES, int ACT>
+template <int BN, bool WRES, int ACT, bool X3>
 int launch_act(const GemmArgs& g, cudaStream_t st) {
-  using C = GCfg<BN, WRES>;
+  using C = GCfg<BN, WRES, X3>;
+  constexpr int BK = C::BK;
   static bool attr = false;
   if (!attr) {
-    TTK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, WRES, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, WRES, ACT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr = true;
   }
   GemmMaps maps;
-  bool ok_a;
+  bool ok_a, ok_w;
   int tiles_m = ttk_cdiv(g.M, BM);
-  if (g.implicit_c) {
+  if (X3) {
+    // split float32 operands: the plane pair is the outermost map dimension (box 2), so one TMA brings hi and lo of a tile
+    const cuuint64_t K4 = (cuuint64_t)g.K * 4;
+    if (g.implicit_c) {
+      const int c = g.implicit_c, n_img = g.M / (g.up_h * g.up_w);
+      cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)g.up_w, (cuuint64_t)g.up_h, (cuuint64_t)n_img, 2};
+      cuuint64_t strides[4] = {(cuuint64_t)c * 4, (cuuint64_t)g.up_w * c * 4, (cuuint64_t)g.up_h * g.up_w * c * 4, (cuuint64_t)g.a_plane};
+      cuuint32_t box[5] = {BK, PW, PH, 1, 2};
+      ok_a = encode_f32(&maps.a, g.A, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      tiles_m = n_img * ttk_cdiv(g.up_w, PW) * ttk_cdiv(g.up_h, PH);
+    } else {
+      cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, 2};
+      cuuint64_t strides[2] = {K4, (cuuint64_t)g.a_plane};
+      cuuint32_t box[3] = {BK, BM, 2};
+      ok_a = encode_f32(&maps.a, g.A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, 2};
+    cuuint64_t strides[2] = {K4, (cuuint64_t)g.w_plane};
+    cuuint32_t box[3] = {BK, BN, 2};
+    ok_w = encode_f32(&maps.w, g.W, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else if (g.implicit_c) {
     EncodeFn enc = get_encode();
     const int c = g.implicit_c, n_img = g.M / (g.up_h * g.up_w);
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)g.up_w, (cuuint64_t)g.up_h, (cuuint64_t)n_img};
@@ -325,34 +382,38 @@ int launch_act(const GemmArgs& g, cudaStream_t st) {
   } else {
     ok_a = encode_2d(&maps.a, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.K, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   }
-  if (!ok_a || !encode_2d(&maps.w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B)) {
+  if (!X3) ok_w = encode_2d(&maps.w, g.W, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.K, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok_a || !ok_w) {
     ttk_set_error("ttk_gemm_umma: cuTensorMapEncodeTiled failed (M %d N %d K %d)", g.M, g.N, g.K);
     return TTK_ERR_CUDA;
   }
   const int tiles_n = g.N / BN;
   const int grid = std::max(1, std::min(tiles_m * tiles_n, ttk_num_sms()));
-  gemm_umma_kernel<BN, WRES, ACT><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, g, tiles_m, tiles_n);
+  gemm_umma_kernel<BN, WRES, ACT, X3><<<grid, THREADS, C::SMEM_BYTES, st>>>(maps, g, tiles_m, tiles_n);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
 
-template <int BN, bool WRES>
+template <int BN, bool WRES, bool X3 = false>
 int launch(const GemmArgs& g, cudaStream_t st) {      // the activation is a compile-time parameter of the epilogue
   switch (g.act & 0xff) {
-    case VIT_ACT_GELU: return launch_act<BN, WRES, VIT_ACT_GELU>(g, st);
-    case VIT_ACT_RELU: return launch_act<BN, WRES, VIT_ACT_RELU>(g, st);
-    default: return launch_act<BN, WRES, VIT_ACT_NONE>(g, st);
+    case VIT_ACT_GELU: return launch_act<BN, WRES, VIT_ACT_GELU, X3>(g, st);
+    case VIT_ACT_RELU: return launch_act<BN, WRES, VIT_ACT_RELU, X3>(g, st);
+    default: return launch_act<BN, WRES, VIT_ACT_NONE, X3>(g, st);
   }
 }
 
 }  // namespace
 
 int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st) {
-  if (g.M <= 0 || g.K % BK != 0 || g.N % 128 != 0 || (g.R && g.c_bf16) ||
+  const int BK = g.x3 ? 32 : 64;
+  if (g.M <= 0 || g.K % BK != 0 || g.N % 128 != 0 || (g.R && g.c_bf16) || (g.x3 && g.c_bf16) || (g.c_split && !g.x3) ||
+      (g.x3 && (g.a_plane % 16 || g.w_plane % 16 || g.c_plane % 16)) ||
       (g.implicit_c && (g.implicit_c % BK != 0 || g.K != 4 * g.implicit_c || g.up_w <= 0 || g.R))) {
     ttk_set_error("ttk_gemm_umma: unsupported shape M %d N %d K %d", g.M, g.N, g.K);
     return TTK_ERR_UNSUPPORTED;
   }
+  if (g.x3) return launch<128, false, true>(g, st);
   // K = 384 (qkv, proj, fc1) with enough M tiles per CTA to amortise the weight load: weights resident in shared memory
   if (g.K == KB_RES * BK && g.M >= 16 * BM) return g.N >= 1152 && g.N % 192 == 0 ? launch<192, true>(g, st) : launch<128, true>(g, st);
   if (g.N % 192 == 0) return launch<192, false>(g, st);

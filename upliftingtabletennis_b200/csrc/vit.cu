@@ -7,7 +7,10 @@
 //   GEMM fc2 (+X)] -> LN -> 2 x [4 parity gathers -> 4 GEMMs (BN folded, ReLU) scattered to the 2x grid] -> 1x1 conv.
 // Every Linear / conv / transposed conv is one GEMM C = act(A W^T + b) (+ R).  dtype TTK_F32 runs the float32 SIMT kernels
 // of this file (parity with the CPU reference); TTK_BF16 runs the same plan with bf16 operands on tcgen05 tensor cores
-// (gemm_umma.cu, attn_umma.cu), float32 accumulation, float32 residual stream.
+// (gemm_umma.cu, attn_umma.cu), float32 accumulation, float32 residual stream.  TTK_TF32X3 is the reference-precision tensor-core
+// path: every GEMM / attention operand is a split float32 pair (hi = tf32(x), lo = tf32(x - hi), written by the producing kernel's
+// epilogue) and every product three kind::tf32 MMAs (gemm_umma.cu X3 mode, attn3_umma.cu) -- float32-class results at ~1/3 of the
+// TF32 tensor rate instead of the SIMT rate.
 #include "vit.h"
 
 #include <math.h>
@@ -20,8 +23,28 @@ namespace {
 constexpr int DIM = 384, DEPTH = 12, HEADS = 12, HD = 32, MLP = 1536, PATCH = 16, PAD = 2, DEC = 256;
 
 // ---- im2col of the patch embedding: A[t][c*256 + ky*16 + kx] = x[b][c][ty*16 - 2 + ky][tx*16 - 2 + kx] ----------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+  lo = __uint_as_float(l);
+}
+// store four float32 values, or (lo_plane != 0) their tf32 hi / lo split into two planes lo_plane bytes apart
+__device__ __forceinline__ void store4(float* o, size_t lo_plane, float a, float b, float c, float d) {
+  if (lo_plane == 0) {
+    *reinterpret_cast<float4*>(o) = make_float4(a, b, c, d);
+    return;
+  }
+  float h[4], l[4];
+  split_tf32(a, h[0], l[0]), split_tf32(b, h[1], l[1]), split_tf32(c, h[2], l[2]), split_tf32(d, h[3], l[3]);
+  *reinterpret_cast<float4*>(o) = make_float4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<float4*>(reinterpret_cast<char*>(o) + lo_plane) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
 template <typename T>
-__global__ void patch_im2col_kernel(const float* __restrict__ x, int images, int C, int H, int W, int hp, int wp, T* __restrict__ A) {
+__global__ void patch_im2col_kernel(const float* __restrict__ x, int images, int C, int H, int W, int hp, int wp, T* __restrict__ A,
+                                    size_t lo_plane = 0) {
   // one warp per (token, channel): lane = (ky, half row) reads 8 consecutive pixels and writes 8 consecutive elements, so a warp
   // reads 16 segments of 64 bytes and writes one contiguous run of 256 elements
   const int lane = threadIdx.x & 31, ky = lane >> 1, hx = (lane & 1) * 8;
@@ -38,8 +61,8 @@ __global__ void patch_im2col_kernel(const float* __restrict__ x, int images, int
     for (int k = 0; k < 8; ++k) v[k] = (row_ok && x0 + k >= 0 && x0 + k < W) ? __ldg(row + x0 + k) : 0.f;
     T* o = A + (size_t)t * (C * PATCH * PATCH) + (size_t)c * PATCH * PATCH + ky * PATCH + hx;
     if constexpr (sizeof(T) == 4) {
-      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
-      reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      store4(o, lo_plane, v[0], v[1], v[2], v[3]);
+      store4(o + 4, lo_plane, v[4], v[5], v[6], v[7]);
     } else {
       uint32_t pk[4];
 #pragma unroll
@@ -55,7 +78,7 @@ __global__ void patch_im2col_kernel(const float* __restrict__ x, int images, int
 // ---- LayerNorm(eps 1e-6) over 384 channels, one warp per token ------------------------------------------------------------
 template <typename T>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows,
-                                 T* __restrict__ out) {
+                                 T* __restrict__ out, size_t lo_plane = 0) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float4* p = reinterpret_cast<const float4*>(x + (size_t)row * DIM);
@@ -85,7 +108,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     const float o0 = v[i].x * rstd * ww.x + bb.x, o1 = v[i].y * rstd * ww.y + bb.y, o2 = v[i].z * rstd * ww.z + bb.z,
                 o3 = v[i].w * rstd * ww.w + bb.w;
     if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (size_t)row * DIM + c) = make_float4(o0, o1, o2, o3);
+      store4(reinterpret_cast<float*>(out) + (size_t)row * DIM + c, lo_plane, o0, o1, o2, o3);
     } else {
       __nv_bfloat162 a = __floats2bfloat162_rn(o0, o1), d = __floats2bfloat162_rn(o2, o3);
       uint2 pk;
@@ -267,6 +290,10 @@ __global__ void final_conv_kernel(const T* __restrict__ in, const float* __restr
   }
 }
 
+__global__ void split_pool_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) split_tf32(in[i], hi[i], lo[i]);
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __float2bfloat16(in[i]);
 }
@@ -288,7 +315,7 @@ void add_param(ttk_vit* h, const std::string& name, std::vector<int> shape) {
 
 int launch_gemm(ttk_vit* h, const GemmArgs& g, int dtype, cudaStream_t st) {
   ++h->launches;
-  if (dtype == TTK_BF16) return ttk_gemm_umma(g, st);
+  if (dtype == TTK_BF16 || dtype == TTK_TF32X3) return ttk_gemm_umma(g, st);
   gemm_f32_kernel<<<dim3(g.N / 64, ttk_cdiv(g.M, 64)), 256, 0, st>>>(g);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
@@ -300,11 +327,13 @@ struct Workspace {              // slices for one sub-batch of `n` images
   float* X;                     // [T][384] float32 residual stream
   char *A, *QKV, *ATT, *HID;    // operand buffers in the path's dtype
   char *D1, *D2;                // deconv outputs NHWC
+  size_t pA, pQKV, pATT, pHID, pD1;      // TTK_TF32X3: byte distance between the hi and the lo plane of each operand buffer
   size_t total;
 };
 
 Workspace carve(const ttk_vit* h, char* base, int n, int dtype) {
-  const size_t es = dtype == TTK_BF16 ? 2 : 4;
+  const bool x3 = dtype == TTK_TF32X3;
+  const size_t es = dtype == TTK_BF16 ? 2 : 4, planes = x3 ? 2 : 1;
   const size_t T = (size_t)n * h->tokens;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -316,11 +345,12 @@ Workspace carve(const ttk_vit* h, char* base, int n, int dtype) {
   w.X = (float*)take(T * DIM * 4);
   // A: LN output [T][384], patch im2col [T][in_ch*256], deconv gathers [T][4*384] and [4T][4*256]
   size_t a_elems = T * (size_t)std::max(std::max(DIM, h->in_ch * PATCH * PATCH), std::max(4 * DIM, 4 * 4 * DEC));
-  w.A = take(a_elems * es);
-  w.QKV = take(T * 3 * DIM * es);
-  w.ATT = take(T * DIM * es);
-  w.HID = take(T * MLP * es);
-  w.D1 = take(T * 4 * DEC * es);
+  w.pA = a_elems * es, w.pQKV = T * 3 * DIM * es, w.pATT = T * DIM * es, w.pHID = T * MLP * es, w.pD1 = T * 4 * DEC * es;
+  w.A = take(w.pA * planes);
+  w.QKV = take(w.pQKV * planes);
+  w.ATT = take(w.pATT * planes);
+  w.HID = take(w.pHID * planes);
+  w.D1 = take(w.pD1 * planes);
   w.D2 = take(T * 16 * DEC * es);
   w.total = off;
   return w;
@@ -383,6 +413,7 @@ extern "C" void ttk_vit_destroy(ttk_vit* h) {
   if (!h) return;
   cudaFree(h->f32_pool);
   cudaFree(h->bf16_pool);
+  cudaFree(h->x3_pool);
   delete h;
 }
 
@@ -504,11 +535,17 @@ static int vit_prepare(ttk_vit* h) {
   h->final_b = push(host(k + "final_layer.bias").data(), h->out_ch);
   cudaFree(h->f32_pool);
   cudaFree(h->bf16_pool);
+  cudaFree(h->x3_pool);
   h->f32_pool = nullptr;
   h->bf16_pool = nullptr;
+  h->x3_pool = nullptr;
+  h->pool_bytes = pool.size() * sizeof(float);
   TTK_CUDA(cudaMalloc((void**)&h->f32_pool, pool.size() * sizeof(float)));
   TTK_CUDA(cudaMalloc((void**)&h->bf16_pool, pool.size() * sizeof(__nv_bfloat16)));
   TTK_CUDA(cudaMemcpy(h->f32_pool, pool.data(), pool.size() * sizeof(float), cudaMemcpyHostToDevice));
+  TTK_CUDA(cudaMalloc((void**)&h->x3_pool, 2 * pool.size() * sizeof(float)));
+  split_pool_kernel<<<1024, 256>>>(h->f32_pool, h->x3_pool, h->x3_pool + pool.size(), pool.size());
+  TTK_LAUNCH_CHECK();
   f32_to_bf16_kernel<<<1024, 256>>>(h->f32_pool, h->bf16_pool, pool.size());
   TTK_LAUNCH_CHECK();
   TTK_CUDA(cudaDeviceSynchronize());
@@ -524,7 +561,7 @@ extern "C" size_t ttk_vit_workspace_bytes(const ttk_vit* h, int batch, int dtype
 extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dtype, float* heatmaps_dev, void* workspace_dev,
                                size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_vit_forward: null handle");
-  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16, "ttk_vit_forward: bad dtype %d", dtype);
+  TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32X3, "ttk_vit_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0, "ttk_vit_forward: bad batch");
   if (!h->ready) {
     const int rc = vit_prepare(h);
@@ -535,9 +572,10 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
   TTK_CHECK_ARG(x_dev && heatmaps_dev && workspace_dev, "ttk_vit_forward: null pointer");
   TTK_CHECK_ARG(workspace_bytes >= ttk_vit_workspace_bytes(h, batch, dtype), "ttk_vit_forward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const bool bf = dtype == TTK_BF16;
-  const size_t es = bf ? 2 : 4;
-  auto wptr = [&](size_t off) -> const void* { return bf ? (const void*)(h->bf16_pool + off) : (const void*)(h->f32_pool + off); };
+  const bool bf = dtype == TTK_BF16, x3 = dtype == TTK_TF32X3;
+  auto wptr = [&](size_t off) -> const void* {
+    return bf ? (const void*)(h->bf16_pool + off) : x3 ? (const void*)(h->x3_pool + off) : (const void*)(h->f32_pool + off);
+  };
   auto fptr = [&](size_t off) { return (const float*)(h->f32_pool + off); };
   const int hw_out = 16 * h->tokens;
 
@@ -546,11 +584,13 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
     const int T = n * h->tokens;
     Workspace w = carve(h, (char*)workspace_dev, std::min(batch, h->subbatch), dtype);
     const float* x = x_dev + (size_t)b0 * h->in_ch * h->height * h->width;
+    // a_plane / c_plane: plane distance of a split operand (TTK_TF32X3; c_plane != 0 makes the output a split pair)
     auto gemm = [&](const void* A, const ttk_vit::Lin& l, const float* R, void* C, int M, int act, int c_bf16, int up_h = 0, int up_w = 0,
-                    int py = 0, int px = 0) {
+                    int py = 0, int px = 0, size_t a_plane = 0, size_t c_plane = 0) {
       GemmArgs g;
       g.A = A, g.W = wptr(l.w_off), g.bias = fptr(l.b_off), g.R = R, g.C = C, g.M = M, g.N = l.n, g.K = l.k, g.act = act, g.c_bf16 = c_bf16;
       g.up_h = up_h, g.up_w = up_w, g.py = py, g.px = px;
+      if (x3) g.x3 = 1, g.a_plane = a_plane, g.w_plane = h->pool_bytes, g.c_split = c_plane != 0, g.c_plane = c_plane;
       return launch_gemm(h, g, dtype, st);
     };
     auto ln = [&](size_t wo, size_t bo) {
@@ -558,7 +598,7 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
       if (bf)
         layernorm_kernel<__nv_bfloat16><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(wo), fptr(bo), T, (__nv_bfloat16*)w.A);
       else
-        layernorm_kernel<float><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(wo), fptr(bo), T, (float*)w.A);
+        layernorm_kernel<float><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(wo), fptr(bo), T, (float*)w.A, x3 ? w.pA : 0);
     };
     int rc;
     // patch embedding (+ bias + position): the position table repeats per image and enters as a residual read modulo the token count
@@ -566,48 +606,54 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
     if (bf)
       patch_im2col_kernel<__nv_bfloat16><<<ttk_num_sms() * 8, 256, 0, st>>>(x, n, h->in_ch, h->height, h->width, h->hp, h->wp, (__nv_bfloat16*)w.A);
     else
-      patch_im2col_kernel<float><<<ttk_num_sms() * 8, 256, 0, st>>>(x, n, h->in_ch, h->height, h->width, h->hp, h->wp, (float*)w.A);
+      patch_im2col_kernel<float><<<ttk_num_sms() * 8, 256, 0, st>>>(x, n, h->in_ch, h->height, h->width, h->hp, h->wp, (float*)w.A, x3 ? w.pA : 0);
     TTK_LAUNCH_CHECK();
     {
       GemmArgs g;
       g.A = w.A, g.W = wptr(h->patch.w_off), g.bias = fptr(h->patch.b_off), g.R = fptr(h->pos_off), g.r_mod = h->tokens, g.C = w.X;
       g.M = T, g.N = h->patch.n, g.K = h->patch.k, g.act = VIT_ACT_NONE, g.c_bf16 = 0, g.up_h = g.up_w = g.py = g.px = 0;
+      if (x3) g.x3 = 1, g.a_plane = w.pA, g.w_plane = h->pool_bytes;
       if ((rc = launch_gemm(h, g, dtype, st)) != TTK_OK) return rc;
     }
     for (int i = 0; i < DEPTH; ++i) {
       const ttk_vit::Block& B = h->blocks[i];
       ln(B.ln1w, B.ln1b);
-      if ((rc = gemm(w.A, B.qkv, nullptr, w.QKV, T, VIT_ACT_NONE, bf)) != TTK_OK) return rc;
+      if ((rc = gemm(w.A, B.qkv, nullptr, w.QKV, T, VIT_ACT_NONE, bf, 0, 0, 0, 0, w.pA, x3 ? w.pQKV : 0)) != TTK_OK) return rc;
       ++h->launches;
       if (bf) {
         if ((rc = ttk_attention_umma((const __nv_bfloat16*)w.QKV, (__nv_bfloat16*)w.ATT, w.A, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
+      } else if (x3) {
+        if ((rc = ttk_attention3((const float*)w.QKV, w.pQKV, (float*)w.ATT, w.pATT, w.A, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
       } else {
         attention_f32_kernel<<<dim3(ttk_cdiv(h->tokens, 8), HEADS, n), 256, 0, st>>>((const float*)w.QKV, h->tokens, (float*)w.ATT);
       }
-      if ((rc = gemm(w.ATT, B.proj, w.X, w.X, T, VIT_ACT_NONE, 0)) != TTK_OK) return rc;
+      if ((rc = gemm(w.ATT, B.proj, w.X, w.X, T, VIT_ACT_NONE, 0, 0, 0, 0, 0, w.pATT)) != TTK_OK) return rc;
       ln(B.ln2w, B.ln2b);
-      if ((rc = gemm(w.A, B.fc1, nullptr, w.HID, T, VIT_ACT_GELU, bf)) != TTK_OK) return rc;
-      if ((rc = gemm(w.HID, B.fc2, w.X, w.X, T, VIT_ACT_NONE, 0)) != TTK_OK) return rc;
+      if ((rc = gemm(w.A, B.fc1, nullptr, w.HID, T, VIT_ACT_GELU, bf, 0, 0, 0, 0, w.pA, x3 ? w.pHID : 0)) != TTK_OK) return rc;
+      if ((rc = gemm(w.HID, B.fc2, w.X, w.X, T, VIT_ACT_NONE, 0, 0, 0, 0, 0, w.pHID)) != TTK_OK) return rc;
     }
     // last_norm: its output [T][384] is the NHWC feature map (n, hp, wp, 384) -- reuse ATT for it, A for the gathers
     ++h->launches;
     if (bf)
       layernorm_kernel<__nv_bfloat16><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(h->lnfw), fptr(h->lnfb), T, (__nv_bfloat16*)w.ATT);
     else
-      layernorm_kernel<float><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(h->lnfw), fptr(h->lnfb), T, (float*)w.ATT);
+      layernorm_kernel<float><<<ttk_cdiv(T, 8), 256, 0, st>>>(w.X, fptr(h->lnfw), fptr(h->lnfb), T, (float*)w.ATT, x3 ? w.pATT : 0);
     const char* feat = w.ATT;
     char* outs[2] = {w.D1, w.D2};
+    size_t feat_plane = w.pATT;
     int fh = h->hp, fw = h->wp, cin = DIM;
     for (int layer = 0; layer < 2; ++layer) {
       const int M = n * fh * fw;
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
-          if (bf) {
-            // tensor-core path: TMA gathers the 2x2 taps straight from the feature map (implicit GEMM, no materialised gather)
+          if (bf || x3) {
+            // tensor-core paths: TMA gathers the 2x2 taps straight from the feature map (implicit GEMM, no materialised gather)
             GemmArgs g;
             const ttk_vit::Lin& l = h->deconv[layer][py * 2 + px];
             g.A = feat, g.W = wptr(l.w_off), g.bias = fptr(l.b_off), g.R = nullptr, g.C = outs[layer], g.M = M, g.N = l.n, g.K = l.k;
-            g.act = VIT_ACT_RELU, g.c_bf16 = 1, g.up_h = fh, g.up_w = fw, g.py = py, g.px = px, g.implicit_c = cin;
+            g.act = VIT_ACT_RELU, g.c_bf16 = bf, g.up_h = fh, g.up_w = fw, g.py = py, g.px = px, g.implicit_c = cin;
+            // the first transposed convolution feeds the second (split pair), the second the float32 1x1 convolution
+            if (x3) g.x3 = 1, g.a_plane = feat_plane, g.w_plane = h->pool_bytes, g.c_split = layer == 0, g.c_plane = layer == 0 ? w.pD1 : 0;
             if ((rc = launch_gemm(h, g, dtype, st)) != TTK_OK) return rc;
             continue;
           }
@@ -616,6 +662,7 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
           if ((rc = gemm(w.A, h->deconv[layer][py * 2 + px], nullptr, outs[layer], M, VIT_ACT_RELU, bf, fh, fw, py, px)) != TTK_OK) return rc;
         }
       feat = outs[layer];
+      feat_plane = w.pD1;
       fh *= 2, fw *= 2, cin = DEC;
     }
     ++h->launches;
@@ -636,6 +683,11 @@ extern "C" int ttk_vit_debug_gemm(const void* a_dev, const void* w_dev, const fl
   GemmArgs g;
   g.A = a_dev, g.W = w_dev, g.bias = bias_dev, g.R = res_dev, g.C = c_dev, g.M = m, g.N = n, g.K = k, g.act = act, g.c_bf16 = c_bf16;
   g.up_h = up_h, g.up_w = up_w, g.py = py, g.px = px;
+  if (dtype == TTK_TF32X3) {        // split pairs [2][m][k], [2][n][k]; c_bf16 == 2: C is a split pair [2][rows][n] too
+    g.x3 = 1, g.a_plane = (size_t)m * k * 4, g.w_plane = (size_t)n * k * 4, g.c_split = c_bf16 == 2, g.c_bf16 = 0;
+    g.c_plane = (size_t)(up_w ? 4 : 1) * m * n * 4;
+    return ttk_gemm_umma(g, (cudaStream_t)stream);
+  }
   if (dtype == TTK_BF16) return ttk_gemm_umma(g, (cudaStream_t)stream);
   TTK_CHECK_ARG(n % 64 == 0 && k % 16 == 0 && !c_bf16, "ttk_vit_debug_gemm: the float32 kernel needs N %% 64 == 0 and K %% 16 == 0");
   gemm_f32_kernel<<<dim3(n / 64, ttk_cdiv(m, 64)), 256, 0, (cudaStream_t)stream>>>(g);
@@ -649,6 +701,12 @@ extern "C" int ttk_vit_debug_attention(const void* qkv_dev, void* out_dev, void*
   if (dtype == TTK_BF16) {
     TTK_CHECK_ARG(scratch_dev && scratch_bytes >= ttk_attention_umma_scratch_bytes(images, tokens, HEADS, HD), "ttk_vit_debug_attention: scratch too small");
     return ttk_attention_umma((const __nv_bfloat16*)qkv_dev, (__nv_bfloat16*)out_dev, scratch_dev, images, tokens, HEADS, HD, (cudaStream_t)stream);
+  }
+  if (dtype == TTK_TF32X3) {        // qkv [2][T][1152] / out [2][T][384] split pairs
+    TTK_CHECK_ARG(scratch_dev && scratch_bytes >= ttk_attention3_scratch_bytes(images, tokens, HEADS, HD), "ttk_vit_debug_attention: scratch too small");
+    const size_t T = (size_t)images * tokens;
+    return ttk_attention3((const float*)qkv_dev, T * 3 * DIM * 4, (float*)out_dev, T * DIM * 4, scratch_dev, images, tokens, HEADS, HD,
+                          (cudaStream_t)stream);
   }
   attention_f32_kernel<<<dim3(ttk_cdiv(tokens, 8), HEADS, images), 256, 0, (cudaStream_t)stream>>>((const float*)qkv_dev, tokens, (float*)out_dev);
   TTK_LAUNCH_CHECK();

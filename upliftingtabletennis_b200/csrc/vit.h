@@ -21,6 +21,11 @@ struct GemmArgs {
   int act;
   int c_bf16;             // output type
   int up_h, up_w, py, px; // up_w == 0: no scatter
+  // 3xTF32 mode (tcgen05 path, fp32-level results): A, W (and C when c_split) are pairs of float32 planes -- plane 0 = tf32(x), plane 1 =
+  // tf32(x - plane 0), *_plane bytes apart -- and every product is three kind::tf32 MMAs (hi*hi + lo*hi + hi*lo)
+  int x3 = 0;
+  int c_split = 0;        // x3 only: write C as such a pair (it feeds another x3 GEMM / the attention); 0: plain float32
+  size_t a_plane = 0, w_plane = 0, c_plane = 0;
   int implicit_c = 0;     // > 0 (tcgen05 path only): A is the NHWC feature map [img][up_h][up_w][implicit_c] itself and the 2x2 taps of the
                           // transposed convolution's output parity (py, px) are gathered by TMA (K = 4 taps x implicit_c), no materialised gather
 };
@@ -42,6 +47,8 @@ struct ttk_vit {
   // prepared device weights (float32 and bf16 copies of every GEMM operand)
   float* f32_pool = nullptr;
   __nv_bfloat16* bf16_pool = nullptr;
+  float* x3_pool = nullptr;      // [hi pool | lo pool]: tf32 split of f32_pool for the 3xTF32 path, planes pool_bytes apart
+  size_t pool_bytes = 0;
   struct Lin {
     size_t w_off, b_off;    // offsets (elements) into the pools; bias always float32
     int n, k;
@@ -63,7 +70,7 @@ struct ttk_vit {
   }
 };
 
-// gemm_umma.cu: bf16 operands through TMA, tcgen05.mma, fp32 accumulation in TMEM.  Returns TTK_ERR_UNSUPPORTED for shapes
+// gemm_umma.cu: bf16 (or, x3, split float32) operands through TMA, tcgen05.mma, fp32 accumulation in TMEM.  Returns TTK_ERR_UNSUPPORTED for shapes
 // it has no kernel for (the caller then reports the error; there is no silent fallback).
 int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st);
 // attn_umma.cu: softmax(q k^T / sqrt(32)) v per (image, head) on tensor cores.  qkv [T][3*dim] bf16, out [T][dim] bf16.
@@ -71,3 +78,8 @@ int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st);
 size_t ttk_attention_umma_scratch_bytes(int images, int tokens, int heads, int head_dim);
 int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_scratch, int images, int tokens, int heads, int head_dim,
                        cudaStream_t st);
+// attn3_umma.cu: the same attention with fp32-level results (3xTF32).  qkv / out are split float32 plane pairs ([2][T][3*dim],
+// [2][T][dim]; planes qkv_plane / out_plane bytes apart); vt_scratch: ttk_attention3_scratch_bytes(...) bytes.
+size_t ttk_attention3_scratch_bytes(int images, int tokens, int heads, int head_dim);
+int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_plane, void* vt_scratch, int images, int tokens, int heads,
+                   int head_dim, cudaStream_t st);

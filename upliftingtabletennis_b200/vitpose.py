@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import lib, check, ptr, stream_ptr
-from .precision import BF16, PrecisionMixin, lib_enum
+from .precision import BF16, FP32, TF32X3, PrecisionMixin, lib_enum
 from .detector import _attach
 
 
@@ -90,9 +90,11 @@ def state_dict_layout(in_ch, tokens, out_ch):
 
 
 class _VitModule(PrecisionMixin, nn.Module):
-    """``compute_dtype`` (constructor argument ``dtype``): 'bf16' (default: the tcgen05 tensor-core path of this architecture) or
-    'fp32' (SIMT kernels, strict parity with the CPU reference at 1e-4)."""
+    """``compute_dtype`` (constructor argument ``dtype``): 'bf16' (bf16 tensors on the tcgen05 tensor cores), 'tf32x3' (float32
+    tensors, three TF32 tensor-core products per term: float32-class results, the reference's arithmetic class for its Linear layers)
+    or 'fp32' (SIMT kernels, the strict parity path against the CPU reference at 1e-4)."""
     default_precision = BF16
+    supported_precisions = (BF16, TF32X3, FP32)
     input_layout = 'nchw'
 
     def __init__(self, in_ch, out_ch, resolution, dtype=None):

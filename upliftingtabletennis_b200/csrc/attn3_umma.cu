@@ -8,14 +8,16 @@
 // One CTA = one (image, head, 128-query tile); it walks the key tiles (64 keys) once:
 //   S   = Q K_j^T           3 x 4 tcgen05.mma 128 x 64 x 8; Q / K_j hi | lo tiles staged by TMA (128-byte rows = 32 floats), S in TMEM
 //   P_j = exp2(S*c - m)     two threads per query row (32 keys each): scores to registers, S is then free for the next Q K^T; running
-//                           maximum in registers, P_j split and written as float32 hi / lo K-major A operands (128-byte swizzle)
-//   O  += P_j V_j           3 x 8 tcgen05.mma 128 x 48 x 8; V staged TRANSPOSED ([dim][key] hi / lo planes from a small transpose
+//                           maximum in registers, P_j split and written to TENSOR MEMORY (tcgen05.st; hi and lo, 64 columns each): the
+//                           P V MMAs take their A operand from there, so P never crosses shared memory (a float32 P pair through
+//                           shared memory was 128 KB of traffic per tile and made the kernel shared-memory bound, 2990 clk / tile)
+//   O   = P_j V_j           per k8 step: P_hi x [V_hi ; V_lo] (N = 96, two accumulator blocks) and P_lo x V_hi (N = 48); V staged
+//                           TRANSPOSED ([dim][key] hi / lo planes from a small transpose
 //                           kernel) with a row of ones appended, so the row sums of P come out of the same MMAs.  Each key tile's
 //                           P_j V_j is a FRESH TMEM accumulation that the softmax threads add to register accumulators
 //                           (rescaled by 2^(m_old - m_new), round-to-nearest): the tensor core's float32 accumulate truncates, and
 //                           a chain over all 45 key tiles (1080 MMAs) measured 1.8e-5 relative error -- per tile it is 24 MMAs.
-// 128 x 64 tiles because the float32 P pair alone takes 64 KB of shared memory; 216 KB in all, one CTA per SM.  The tensor pipe
-// bounds it: thin MMAs (N = 64 / 48) take their ~45 clk floor each, 36 of them per tile against 512 clk of exponentials.
+// TMEM: S 64 + O 96 + P 128 columns (512 allocated, one CTA per SM); shared memory: Q pair + 4 K / V^T stages = 194 KB.
 #include "umma_prims.h"
 #include "vit.h"
 
@@ -23,18 +25,17 @@ namespace {
 
 using namespace umma;
 
-constexpr int HD = 32, BQ = 128, BKEY = 64, NST = 3, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
+constexpr int HD = 32, BQ = 128, BKEY = 64, NST = 4, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
 constexpr int Q_PLANE = BQ * 128, Q_BYTES = 2 * Q_PLANE;                 // hi | lo, 128-byte rows
 constexpr int K_PLANE = BKEY * 128, K_BYTES = 2 * K_PLANE;
 constexpr int VR = 48;                                 // rows of the staged V^T tile: 32 dims, a row of ones, 15 rows of zeros (N % 16 == 0)
 constexpr int V_CHUNK = VR * 128;                      // one 32-key chunk [48 rows][128 B]
 constexpr int V_PLANE = 2 * V_CHUNK, V_BYTES = 2 * V_PLANE;
 constexpr int KV_BYTES = K_BYTES + V_BYTES;            // 40 KB
-constexpr int P_CHUNK = BQ * 128;                      // one 32-key chunk [128 rows][128 B]
-constexpr int P_PLANE = 2 * P_CHUNK, P_BYTES = 2 * P_PLANE;      // 64 KB
 constexpr int X_BYTES = 4 * BQ * 4;                    // row maxima (2 parities x 2 halves) exchanged between partner warps
-constexpr int SMEM_BYTES = Q_BYTES + NST * KV_BYTES + P_BYTES + X_BYTES + 256;
-constexpr int TMEM_COLS = 128;                         // S: 64 columns, O: 48
+constexpr int SMEM_BYTES = Q_BYTES + NST * KV_BYTES + X_BYTES + 256;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_S = 0, COL_O = BKEY, COL_PH = COL_O + 2 * VR, COL_PL = COL_PH + BKEY;      // S | O_hi O_lo | P_hi | P_lo
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 __device__ __forceinline__ float ex2(float x) {
@@ -74,8 +75,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;
-  uint8_t* sP = sKV + NST * KV_BYTES;
-  uint8_t* sX = sP + P_BYTES;
+  uint8_t* sX = sKV + NST * KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + X_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
   const uint32_t bar_kv_full = smem_u32(bars), bar_kv_empty = bar_kv_full + 8 * NST, bar_q = bar_kv_empty + 8 * NST, bar_s_full = bar_q + 8,
@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
   if (warp == 8) {
     // TMA + MMA warp: all lanes walk the loop with warp-uniform values, one elected lane issues (see conv_umma.cu)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-    const uint32_t tS = tmem_u, tO = tmem_u + BKEY;
+    const uint32_t tS = tmem_u + COL_S, tO = tmem_u + COL_O, tPh = tmem_u + COL_PH, tPl = tmem_u + COL_PL;
     const bool leader = elect_one();
-    constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKEY), idesc_o = make_idesc_tf32(BQ, VR);
+    constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKEY), idesc_o = make_idesc_tf32(BQ, VR), idesc_o2 = make_idesc_tf32(BQ, 2 * VR);
     auto load_kv = [&](int j) {
       const uint32_t s = j % NST;
       if (leader) {
@@ -151,20 +151,17 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
         fence_after();
         issue_s(j + 1);
       }
-      mbar_wait(bar_p_full, j & 1);              // P_j is in shared memory (and O_{j-1} has been consumed)
+      mbar_wait(bar_p_full, j & 1);              // P_j is in tensor memory (and O_{j-1} has been consumed)
       fence_after();
       const uint32_t s = j % NST;
-      const uint32_t p0 = smem_u32(sP) >> 4, v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES) >> 4;
+      const uint32_t v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES) >> 4;
 #pragma unroll
       for (int k8 = 0; k8 < BKEY / 8; ++k8) {
-        // P: [plane][chunk][128 rows][128 B]; V^T: [chunk][plane][48 rows][128 B]
-        const uint32_t pc = (k8 >> 2) * (P_CHUNK / 16) + (k8 & 3) * 2, vc = (k8 >> 2) * (2 * V_CHUNK / 16) + (k8 & 3) * 2;
-        const uint64_t ph = make_desc16<1024, 2>(p0 + pc), pl = make_desc16<1024, 2>(p0 + P_PLANE / 16 + pc);
-        const uint64_t vh = make_desc16<1024, 2>(v0 + vc), vl = make_desc16<1024, 2>(v0 + V_CHUNK / 16 + vc);
+        // V^T: [chunk][plane][48 rows][128 B] -- the hi and lo rows of a chunk are one contiguous 96-row B operand
+        const uint64_t vb = make_desc16<1024, 2>(v0 + (k8 >> 2) * (2 * V_CHUNK / 16) + (k8 & 3) * 2);
         if (leader) {
-          mma_tf32(tO, pl, vh, idesc_o, k8 ? 1u : 0u);             // this tile's P V (and row sums); the softmax threads accumulate over tiles
-          mma_tf32(tO, ph, vl, idesc_o, 1u);
-          mma_tf32(tO, ph, vh, idesc_o, 1u);
+          mma_tf32_ts(tO, tPh + k8 * 8, vb, idesc_o2, k8 ? 1u : 0u);      // this tile's P_hi V_hi | P_hi V_lo (the softmax threads accumulate over tiles)
+          mma_tf32_ts(tO, tPl + k8 * 8, vb, idesc_o, 1u);                 // + P_lo V_hi
         }
       }
       if (leader) {
@@ -180,7 +177,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
   } else {
     // softmax warps 0..7: warp w and w+4 share TMEM lanes 32 (w % 4) .., i.e. the same 32 query rows; `half` picks the 32 key
     // columns (= one swizzled P chunk) and the 16 output dimensions a thread owns
-    const uint32_t tS = tmem, tO = tmem + BKEY;
+    const uint32_t tS = tmem + COL_S, tO = tmem + COL_O, tPh = tmem + COL_PH, tPl = tmem + COL_PL;
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;                  // query row of this thread = TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -189,15 +186,15 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
 #pragma unroll
     for (int d = 0; d < 16; ++d) o_acc[d] = 0.f;
     constexpr int HK = BKEY / 2;
-    const uint32_t p_row = smem_u32(sP) + half * P_CHUNK + row * 128;
     float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima
     auto take_o = [&](float scale) {                // (accumulators + the finished tile's P V) * scale
-      uint32_t v[16], w;
+      uint32_t v[16], v2[16], w;
       tmem_ld16(tO + lane_base + half * 16, v);
+      tmem_ld16(tO + lane_base + VR + half * 16, v2);                                                              // the P_hi V_lo block
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(w) : "r"(tO + lane_base + HD));      // column 32: sum_k P[row][k]
       tmem_wait_ld();
 #pragma unroll
-      for (int d = 0; d < 16; ++d) o_acc[d] = (o_acc[d] + __uint_as_float(v[d])) * scale;
+      for (int d = 0; d < 16; ++d) o_acc[d] = (o_acc[d] + (__uint_as_float(v[d]) + __uint_as_float(v2[d]))) * scale;
       l_acc = (l_acc + __uint_as_float(w)) * scale;
     };
     for (int j = 0; j < nk; ++j) {
@@ -237,18 +234,20 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
         fence_after();
         take_o(alpha);
       }
-      // P_j -> shared memory as hi / lo float32 planes (128-byte swizzle: 16-byte unit u of row r at u ^ (r & 7))
+      // P_j -> tensor memory as hi / lo float32 column blocks (lane = query row, column = key): the A operand of the P V MMAs
+      {
+        uint32_t ph[HK], pl[HK];
 #pragma unroll
-      for (int u = 0; u < HK / 4; ++u) {
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(p[4 * u + e], h[e], l[e]);
-        const uint32_t a = p_row + (((uint32_t)u ^ (row & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(h[0]), "f"(h[1]), "f"(h[2]), "f"(h[3]) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a + P_PLANE), "f"(l[0]), "f"(l[1]), "f"(l[2]), "f"(l[3]) : "memory");
+        for (int i = 0; i < HK; ++i) {
+          float h, l;
+          split_tf32(p[i], h, l);
+          ph[i] = __float_as_uint(h), pl[i] = __float_as_uint(l);
+        }
+        tmem_st32(tPh + lane_base + half * HK, ph);
+        tmem_st32(tPl + lane_base + half * HK, pl);
+        tmem_wait_st();
       }
-      fence_before();                                // the reads of O_{j-1} are ordered before the MMAs that overwrite it
-      fence_async_smem();                            // P_j visible to the tensor core (async proxy)
+      fence_before();                                // the reads of O_{j-1} and the writes of P_j are ordered before the MMAs that follow the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
     }

@@ -108,6 +108,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from tensor memory (lane = row of A, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // one lane of a converged warp (the same one on every call): the issuer of tcgen05.mma / commit
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

@@ -11,13 +11,13 @@
 //                           maximum in registers, P_j split and written to TENSOR MEMORY (tcgen05.st; hi and lo, 64 columns each): the
 //                           P V MMAs take their A operand from there, so P never crosses shared memory (a float32 P pair through
 //                           shared memory was 128 KB of traffic per tile and made the kernel shared-memory bound, 2990 clk / tile)
-//   O   = P_j V_j           per k8 step: P_hi x [V_hi ; V_lo] (N = 96, two accumulator blocks) and P_lo x V_hi (N = 48); V staged
-//                           TRANSPOSED ([dim][key] hi / lo planes from a small transpose
-//                           kernel) with a row of ones appended, so the row sums of P come out of the same MMAs.  Each key tile's
+//   O   = P_j V_j           per k8 step: P_hi x [V_hi ; V_lo] (N = 64, two accumulator blocks) and P_lo x V_hi (N = 32); V staged
+//                           TRANSPOSED ([dim][key] hi / lo planes from a small transpose kernel).  Each key tile's
 //                           P_j V_j is a FRESH TMEM accumulation that the softmax threads add to register accumulators
 //                           (rescaled by 2^(m_old - m_new), round-to-nearest): the tensor core's float32 accumulate truncates, and
 //                           a chain over all 45 key tiles (1080 MMAs) measured 1.8e-5 relative error -- per tile it is 24 MMAs.
-// TMEM: S 64 + O 96 + P 128 columns (512 allocated, one CTA per SM); shared memory: Q pair + 4 K / V^T stages = 194 KB.
+// TMEM: S 64 + O 64 + P 128 = 256 columns and 98 KB of shared memory (Q pair + 2 K / V^T stages), so TWO CTAs share an SM and one
+// CTA's softmax (exponentials, splits, TMEM round trips: a long dependent chain per tile) overlaps the other's MMAs.
 #include "umma_prims.h"
 #include "vit.h"
 
@@ -25,18 +25,18 @@ namespace {
 
 using namespace umma;
 
-constexpr int HD = 32, BQ = 128, BKEY = 64, NST = 4, THREADS = 288;      // 8 softmax warps + 1 TMA / MMA warp
+constexpr int HD = 32, BQ = 128, BKEY = 64, NST = 2, THREADS = 320;      // 8 softmax warps, MMA warp, TMA warp
 constexpr int Q_PLANE = BQ * 128, Q_BYTES = 2 * Q_PLANE;                 // hi | lo, 128-byte rows
 constexpr int K_PLANE = BKEY * 128, K_BYTES = 2 * K_PLANE;
-constexpr int VR = 48;                                 // rows of the staged V^T tile: 32 dims, a row of ones, 15 rows of zeros (N % 16 == 0)
-constexpr int V_CHUNK = VR * 128;                      // one 32-key chunk [48 rows][128 B]
+constexpr int VR = HD;                                 // rows of the staged V^T tile
+constexpr int V_CHUNK = VR * 128;                      // one 32-key chunk [32 rows][128 B]
 constexpr int V_PLANE = 2 * V_CHUNK, V_BYTES = 2 * V_PLANE;
-constexpr int KV_BYTES = K_BYTES + V_BYTES;            // 40 KB
+constexpr int KV_BYTES = K_BYTES + V_BYTES;            // 32 KB
 constexpr int X_BYTES = 4 * BQ * 4;                    // row maxima (2 parities x 2 halves) exchanged between partner warps
 constexpr int SMEM_BYTES = Q_BYTES + NST * KV_BYTES + X_BYTES + 256;
-constexpr int TMEM_COLS = 512;
+constexpr int TMEM_COLS = 256;
 constexpr int COL_S = 0, COL_O = BKEY, COL_PH = COL_O + 2 * VR, COL_PL = COL_PH + BKEY;      // S | O_hi O_lo | P_hi | P_lo
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(2 * (SMEM_BYTES + 1024) <= 233472 && COL_PL + BKEY <= TMEM_COLS, "two CTAs per SM");
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -47,11 +47,10 @@ __device__ __forceinline__ float ex2(float x) {
 struct Attn3Maps {
   CUtensorMap qkv;     // [2][images][tokens][3*dim] float32, box {32, rows, 1, 2}: one for Q (128 rows) ...
   CUtensorMap kk;      // ... one for K (64 rows)
-  CUtensorMap vt;      // [2][images][heads*48][tok_pad] float32, box {32, 48, 1, 2}
+  CUtensorMap vt;      // [2][images][heads*32][tok_pad] float32, box {32, 32, 1, 2}
 };
 
-// V^T planes with the extra rows: vt[p][img][head*48 + d][token] = v_p[img][token][head*32 + d] for d < 32; ones row (hi plane only) at
-// d == 32 for existing tokens; 0 elsewhere
+// V^T planes: vt[p][img][head*32 + d][token] = v_p[img][token][head*32 + d] (0 for the padding tokens)
 __global__ void __launch_bounds__(256) v_transpose3_kernel(const float* __restrict__ qkv, size_t qkv_plane, int tokens, int tok_pad, int dim,
                                                            float* __restrict__ vt, size_t vt_plane) {
   __shared__ float tile[2][64][HD + 1];
@@ -66,20 +65,24 @@ __global__ void __launch_bounds__(256) v_transpose3_kernel(const float* __restri
   for (int i = threadIdx.x; i < 2 * 64 * VR; i += 256) {
     const int p = i / (64 * VR), d = (i / 64) % VR, t = i % 64;
     float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(vt) + p * vt_plane) + ((size_t)img * heads + head) * VR * tok_pad;
-    if (t0 + t < tok_pad) base[(size_t)d * tok_pad + t0 + t] = d < HD ? tile[p][t][d] : (d == HD && p == 0 && t0 + t < tokens ? 1.f : 0.f);
+    if (t0 + t < tok_pad) base[(size_t)d * tok_pad + t0 + t] = tile[p][t][d];
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __grid_constant__ Attn3Maps maps, float* __restrict__ out,
+__global__ void __launch_bounds__(THREADS, 2) attention3_umma_kernel(const __grid_constant__ Attn3Maps maps, float* __restrict__ out,
                                                                      size_t out_plane, int tokens, int dim) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Q_BYTES;
   uint8_t* sX = sKV + NST * KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX + X_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 5);
-  const uint32_t bar_kv_full = smem_u32(bars), bar_kv_empty = bar_kv_full + 8 * NST, bar_q = bar_kv_empty + 8 * NST, bar_s_full = bar_q + 8,
-                 bar_s_empty = bar_s_full + 8, bar_p_full = bar_s_empty + 8, bar_o_full = bar_p_full + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 * NST + 5);
+  // K and V^T of a stage have their own full / empty barriers: K_j is free as soon as S_j has been computed (early), V_j only after
+  // P_j V_j, and the next K must arrive a tile ahead of the next V -- with one barrier pair per stage the softmax warps spent 27 %
+  // of their time waiting for S
+  const uint32_t bar_k_full = smem_u32(bars), bar_k_empty = bar_k_full + 8 * NST, bar_v_full = bar_k_empty + 8 * NST,
+                 bar_v_empty = bar_v_full + 8 * NST, bar_q = bar_v_empty + 8 * NST, bar_s_full = bar_q + 8, bar_s_empty = bar_s_full + 8,
+                 bar_p_full = bar_s_empty + 8, bar_o_full = bar_p_full + 8;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, head = blockIdx.y, img = blockIdx.z;
   const int nk = (tokens + BKEY - 1) / BKEY;
@@ -87,8 +90,10 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(bar_kv_full + 8 * s, 1);
-      mbar_init(bar_kv_empty + 8 * s, 1);
+      mbar_init(bar_k_full + 8 * s, 1);
+      mbar_init(bar_k_empty + 8 * s, 1);
+      mbar_init(bar_v_full + 8 * s, 1);
+      mbar_init(bar_v_empty + 8 * s, 1);
     }
     mbar_init(bar_q, 1);
     mbar_init(bar_s_full, 1);
@@ -103,27 +108,33 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
   fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
-    // TMA + MMA warp: all lanes walk the loop with warp-uniform values, one elected lane issues (see conv_umma.cu)
+  if (warp == 9) {
+    // TMA producer: Q once, then K_j / V^T_j in tile order into their 2-stage rings
+    if (lane == 0) {
+      mbar_expect_tx(bar_q, Q_BYTES);
+      tma_load_4d(smem_u32(sQ), &maps.qkv, bar_q, head * HD, q0, img, 0);
+      for (int j = 0; j < nk; ++j) {
+        const uint32_t s = j % NST, ph = ((j / NST) & 1) ^ 1;
+        const uint32_t dst = smem_u32(sKV + s * KV_BYTES);
+        mbar_wait(bar_k_empty + 8 * s, ph);
+        mbar_expect_tx(bar_k_full + 8 * s, K_BYTES);
+        tma_load_4d(dst, &maps.kk, bar_k_full + 8 * s, dim + head * HD, j * BKEY, img, 0);
+        mbar_wait(bar_v_empty + 8 * s, ph);
+        mbar_expect_tx(bar_v_full + 8 * s, V_BYTES);
+        // V^T: one box = one 32-key chunk of both planes, so the stage holds [chunk][plane][32 rows][128 B]
+        tma_load_4d(dst + K_BYTES, &maps.vt, bar_v_full + 8 * s, j * BKEY, head * VR, img, 0);
+        tma_load_4d(dst + K_BYTES + 2 * V_CHUNK, &maps.vt, bar_v_full + 8 * s, j * BKEY + 32, head * VR, img, 0);
+      }
+    }
+  } else if (warp == 8) {
+    // MMA warp: all lanes walk the loop with warp-uniform values, one elected lane issues (see conv_umma.cu)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t tS = tmem_u + COL_S, tO = tmem_u + COL_O, tPh = tmem_u + COL_PH, tPl = tmem_u + COL_PL;
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = make_idesc_tf32(BQ, BKEY), idesc_o = make_idesc_tf32(BQ, VR), idesc_o2 = make_idesc_tf32(BQ, 2 * VR);
-    auto load_kv = [&](int j) {
-      const uint32_t s = j % NST;
-      if (leader) {
-        mbar_expect_tx(bar_kv_full + 8 * s, KV_BYTES);
-        const uint32_t dst = smem_u32(sKV + s * KV_BYTES);
-        tma_load_4d(dst, &maps.kk, bar_kv_full + 8 * s, dim + head * HD, j * BKEY, img, 0);
-        // V^T chunks: [plane][chunk][48 rows][128 B]; a box brings one 32-key chunk of both planes -> strided destination, so
-        // one box per (plane, chunk) would need 4 loads; instead the planes are interleaved per chunk: [chunk][plane] (see issue_o)
-        tma_load_4d(dst + K_BYTES, &maps.vt, bar_kv_full + 8 * s, j * BKEY, head * VR, img, 0);
-        tma_load_4d(dst + K_BYTES + 2 * V_CHUNK, &maps.vt, bar_kv_full + 8 * s, j * BKEY + 32, head * VR, img, 0);
-      }
-    };
     auto issue_s = [&](int j) {
       const uint32_t s = j % NST;
-      mbar_wait(bar_kv_full + 8 * s, (j / NST) & 1);
+      mbar_wait(bar_k_full + 8 * s, (j / NST) & 1);
       fence_after();
       const uint32_t a0 = smem_u32(sQ) >> 4, b0 = smem_u32(sKV + s * KV_BYTES) >> 4;
 #pragma unroll
@@ -136,13 +147,11 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
           mma_tf32(tS, ah, bh, idesc_s, 1u);
         }
       }
-      if (leader) commit(bar_s_full);
+      if (leader) {
+        commit(bar_s_full);
+        commit(bar_k_empty + 8 * s);
+      }
     };
-    if (leader) {
-      mbar_expect_tx(bar_q, Q_BYTES);
-      tma_load_4d(smem_u32(sQ), &maps.qkv, bar_q, head * HD, q0, img, 0);
-    }
-    for (int j = 0; j < NST && j < nk; ++j) load_kv(j);
     mbar_wait(bar_q, 0);
     issue_s(0);
     for (int j = 0; j < nk; ++j) {
@@ -151,13 +160,14 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
         fence_after();
         issue_s(j + 1);
       }
+      const uint32_t s = j % NST;
+      mbar_wait(bar_v_full + 8 * s, (j / NST) & 1);
       mbar_wait(bar_p_full, j & 1);              // P_j is in tensor memory (and O_{j-1} has been consumed)
       fence_after();
-      const uint32_t s = j % NST;
       const uint32_t v0 = smem_u32(sKV + s * KV_BYTES + K_BYTES) >> 4;
 #pragma unroll
       for (int k8 = 0; k8 < BKEY / 8; ++k8) {
-        // V^T: [chunk][plane][48 rows][128 B] -- the hi and lo rows of a chunk are one contiguous 96-row B operand
+        // V^T: [chunk][plane][32 rows][128 B] -- the hi and lo rows of a chunk are one contiguous 64-row B operand
         const uint64_t vb = make_desc16<1024, 2>(v0 + (k8 >> 2) * (2 * V_CHUNK / 16) + (k8 & 3) * 2);
         if (leader) {
           mma_tf32_ts(tO, tPh + k8 * 8, vb, idesc_o2, k8 ? 1u : 0u);      // this tile's P_hi V_hi | P_hi V_lo (the softmax threads accumulate over tiles)
@@ -165,16 +175,13 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
         }
       }
       if (leader) {
-        commit(bar_kv_empty + 8 * s);
+        commit(bar_v_empty + 8 * s);
         commit(bar_o_full);
-      }
-      if (j + NST < nk) {                          // refill this stage once P_j V_j has read it
-        mbar_wait(bar_kv_empty + 8 * s, (j / NST) & 1);
-        load_kv(j + NST);
       }
       __syncwarp();
     }
   } else {
+    // (warps 8 and 9 fall through to the common exit)
     // softmax warps 0..7: warp w and w+4 share TMEM lanes 32 (w % 4) .., i.e. the same 32 query rows; `half` picks the 32 key
     // columns (= one swizzled P chunk) and the 16 output dimensions a thread owns
     const uint32_t tS = tmem + COL_S, tO = tmem + COL_O, tPh = tmem + COL_PH, tPl = tmem + COL_PL;
@@ -188,14 +195,12 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
     constexpr int HK = BKEY / 2;
     float* xch = reinterpret_cast<float*>(sX);      // [2 parities][2 halves][128 rows] row maxima
     auto take_o = [&](float scale) {                // (accumulators + the finished tile's P V) * scale
-      uint32_t v[16], v2[16], w;
+      uint32_t v[16], v2[16];
       tmem_ld16(tO + lane_base + half * 16, v);
       tmem_ld16(tO + lane_base + VR + half * 16, v2);                                                              // the P_hi V_lo block
-      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(w) : "r"(tO + lane_base + HD));      // column 32: sum_k P[row][k]
       tmem_wait_ld();
 #pragma unroll
       for (int d = 0; d < 16; ++d) o_acc[d] = (o_acc[d] + (__uint_as_float(v[d]) + __uint_as_float(v2[d]))) * scale;
-      l_acc = (l_acc + __uint_as_float(w)) * scale;
     };
     for (int j = 0; j < nk; ++j) {
       const int valid = min(BKEY, tokens - j * BKEY) - half * HK;        // keys of this thread's half that exist (may be <= 0)
@@ -229,24 +234,34 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
       float p[HK];
 #pragma unroll
       for (int i = 0; i < HK; ++i) p[i] = ex2(fmaf(__uint_as_float(sv[i]), sl2, -m_run));
+      {                                              // row sum of this thread's 32 keys (the partner's half joins at the end)
+        float s4[4] = {p[0], p[1], p[2], p[3]};
+#pragma unroll
+        for (int i = 4; i < HK; i += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) s4[k] += p[i + k];
+        }
+        l_acc = fmaf(l_acc, alpha, (s4[0] + s4[1]) + (s4[2] + s4[3]));
+      }
       if (j > 0) {                                   // P_{j-1} V_{j-1} has landed: into the register accumulators, on to this tile's scale
         mbar_wait(bar_o_full, (j - 1) & 1);
         fence_after();
         take_o(alpha);
       }
       // P_j -> tensor memory as hi / lo float32 column blocks (lane = query row, column = key): the A operand of the P V MMAs
-      {
-        uint32_t ph[HK], pl[HK];
 #pragma unroll
-        for (int i = 0; i < HK; ++i) {
+      for (int c = 0; c < HK; c += 16) {
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
           float h, l;
-          split_tf32(p[i], h, l);
+          split_tf32(p[c + i], h, l);
           ph[i] = __float_as_uint(h), pl[i] = __float_as_uint(l);
         }
-        tmem_st32(tPh + lane_base + half * HK, ph);
-        tmem_st32(tPl + lane_base + half * HK, pl);
-        tmem_wait_st();
+        tmem_st16(tPh + lane_base + half * HK + c, ph);
+        tmem_st16(tPl + lane_base + half * HK + c, pl);
       }
+      tmem_wait_st();
       fence_before();                                // the reads of O_{j-1} and the writes of P_j are ordered before the MMAs that follow the arrive
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full);
@@ -254,6 +269,11 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
     mbar_wait(bar_o_full, (nk - 1) & 1);
     fence_after();
     take_o(1.f);
+    // row sums of the two halves: through the exchange slots of the parity the last tile did NOT use (their last readers are
+    // behind that tile's bar.sync)
+    xch[((nk & 1) * 2 + half) * BQ + row] = l_acc;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    l_acc += xch[((nk & 1) * 2 + (half ^ 1)) * BQ + row];
     if (q0 + row < tokens) {
       const float inv = 1.f / l_acc;
       float* op = out + ((size_t)img * tokens + q0 + row) * dim + head * HD + half * 16;
@@ -278,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) attention3_umma_kernel(const __gri
 size_t ttk_attention3_scratch_bytes(int images, int tokens, int heads, int head_dim) {
   const size_t tok_pad = (size_t)(tokens + 7) / 8 * 8;
   (void)head_dim;
-  return 2 * (size_t)images * heads * VR * tok_pad * 4;
+  return 2 * (size_t)images * heads * VR * tok_pad * 4;      // (callers may pass more)
 }
 
 int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_plane, void* vt_scratch, int images, int tokens, int heads,

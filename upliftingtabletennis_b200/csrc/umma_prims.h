@@ -229,13 +229,12 @@ inline bool encode_f32(CUtensorMap* m, const void* base, int rank, const cuuint6
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-// the two terms of the 3xTF32 split of a float32 value: hi = tf32(x) (round to nearest), lo = tf32(x - hi)
+// the two terms of the 3xTF32 split of a float32 value: hi = tf32(x) (round to nearest), lo = x - hi
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-  lo = __uint_as_float(l);
+  // integer form of cvt.rna.tf32.f32 (round to nearest, ties away) without its special-case handling: 2 ALU ops; lo = x - hi is exact
+  // (13 significant bits) and is left unrounded -- kind::tf32 ignores its low bits (2^-22 of x)
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
 
 }  // namespace umma

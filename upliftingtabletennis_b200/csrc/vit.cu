@@ -24,11 +24,10 @@ constexpr int DIM = 384, DEPTH = 12, HEADS = 12, HD = 32, MLP = 1536, PATCH = 16
 
 // ---- im2col of the patch embedding: A[t][c*256 + ky*16 + kx] = x[b][c][ty*16 - 2 + ky][tx*16 - 2 + kx] ----------------
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
-  lo = __uint_as_float(l);
+  // integer form of cvt.rna.tf32.f32 (round to nearest, ties away) without its special-case handling: 2 ALU ops; lo = x - hi is exact
+  // (13 significant bits) and is left unrounded -- kind::tf32 ignores its low bits (2^-22 of x)
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
 }
 // store four float32 values, or (lo_plane != 0) their tf32 hi / lo split into two planes lo_plane bytes apart
 __device__ __forceinline__ void store4(float* o, size_t lo_plane, float a, float b, float c, float d) {

@@ -134,12 +134,16 @@ TTK_API int ttk_vit_tokens(const ttk_vit* h, int* hp, int* wp);
 TTK_API int ttk_vit_set_subbatch(ttk_vit* h, int images);
 TTK_API size_t ttk_vit_workspace_bytes(const ttk_vit* h, int batch, int dtype);
 /* x_dev: batch x in_ch x height x width float32 (NCHW, the reference's input tensor);
- * heatmaps_dev: batch x out_ch x 4hp x 4wp float32.  dtype TTK_F32: float32 SIMT kernels (parity with
- * the CPU reference); TTK_BF16: bf16 operands on tcgen05 tensor cores, float32 accumulate/residual. */
+ * heatmaps_dev: batch x out_ch x 4hp x 4wp float32.  dtype TTK_TF32X3: float32 tensors, every product as three
+ * TF32 tensor-core products of split operands (float32-class results: the arithmetic class of the reference's
+ * Linear layers and attention); TTK_F32: float32 SIMT kernels (strict parity with the CPU reference);
+ * TTK_BF16: bf16 operands on tcgen05 tensor cores, float32 accumulate/residual. */
 TTK_API int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dtype, float* heatmaps_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 TTK_API int ttk_vit_last_launches(const ttk_vit* h);
-/* Test hooks: the detector's two building blocks on caller buffers (dtype TTK_F32: float32 SIMT kernels, TTK_BF16: tcgen05).
+/* Test hooks: the detector's two building blocks on caller buffers (dtype TTK_F32: float32 SIMT kernels, TTK_BF16: tcgen05,
+ * TTK_TF32X3: tcgen05 with split float32 operands -- A, W, qkv (and C when c_bf16 == 2, and out) are then pairs of float32
+ * planes [2][rows][cols]: plane 0 = tf32(x), plane 1 = x - plane 0).
  * GEMM: C[m][n] = act(sum_k A[m][k] W[n][k] + bias[n]) (+ R[m][n]); act 0 none, 1 GELU (erf), 2 ReLU; A, W in `dtype`;
  * C bf16 when c_bf16 else float32; up_w > 0 scatters row (img, y, x) of an up_h x up_w grid to (img, 2y+py, 2x+px) of the 2x grid.
  * Attention: qkv [images*tokens][1152] in `dtype` -> out [images*tokens][384] (12 heads of 32), scratch for the bf16 path. */

@@ -112,7 +112,7 @@ def test_precision_classes_and_defaults(L):
     assert up.compute_dtype == 'fp32'
     with pytest.raises(NotImplementedError):
         up.compute_dtype = 'tf32'                      # the transformer has no single-product TF32 path
-    assert VitPose(in_frames=3, resolution=(96, 64)).compute_dtype == 'bf16'
+    assert VitPose(in_frames=3, resolution=(96, 64)).compute_dtype == 'tf32x3'
     with pytest.raises(NotImplementedError):
         VitPose(in_frames=3, resolution=(96, 64), dtype='tf32')
     # workspace of the tf32x3 path: a layer's activations live in HBM (x, q | k | v, o per table-token row)

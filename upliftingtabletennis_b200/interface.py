@@ -15,6 +15,7 @@ import torch
 
 from . import ops
 from .detector import MyHRNet, WASBNet
+from .precision import TF32, TF32X3, canonical
 from .vitpose import TableVitPose, VitPose
 from .uplift import get_model as get_uplifting_model
 
@@ -563,7 +564,11 @@ class TableTennisPipeline:
     detector objects are built (main and auxiliary never share one, even when they name the same model)."""
 
     def __init__(self, ball_model='vitpose', ball_model_aux='wasb', table_model='vitpose', table_model_aux='hrnet', dtype=None):
+        """dtype: None / 'tf32' / 'tf32x3' = every component on its reference-class tensor-core path (TF32 convolutions, 3xTF32
+        Linear layers and attention); 'bf16' or 'fp32' = every component on that path."""
         self.device = _device()
+        if dtype is not None and canonical(dtype) in (TF32, TF32X3):
+            dtype = None
         self.ball_detector = BallDetector(model_name=ball_model, dtype=dtype)
         self.ball_detector_aux = BallDetector(model_name=ball_model_aux, dtype=dtype)
         self.table_detector = TableDetector(model_name=table_model, dtype=dtype)

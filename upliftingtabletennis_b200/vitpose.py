@@ -90,10 +90,10 @@ def state_dict_layout(in_ch, tokens, out_ch):
 
 
 class _VitModule(PrecisionMixin, nn.Module):
-    """``compute_dtype`` (constructor argument ``dtype``): 'bf16' (bf16 tensors on the tcgen05 tensor cores), 'tf32x3' (float32
-    tensors, three TF32 tensor-core products per term: float32-class results, the reference's arithmetic class for its Linear layers)
-    or 'fp32' (SIMT kernels, the strict parity path against the CPU reference at 1e-4)."""
-    default_precision = BF16
+    """``compute_dtype`` (constructor argument ``dtype``): 'tf32x3' (default: float32 tensors, three TF32 tensor-core products per
+    term -- float32-class results, the arithmetic class of the reference's Linear layers and fp32 attention), 'bf16' (bf16 tensors on
+    the tensor cores, 2.3x faster, reported separately) or 'fp32' (SIMT kernels, the strict parity path against the CPU reference)."""
+    default_precision = TF32X3
     supported_precisions = (BF16, TF32X3, FP32)
     input_layout = 'nchw'
 

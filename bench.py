@@ -202,6 +202,23 @@ def gpu_eager_baseline(dev, steps=3, warmup=2, wasb_sub=8, uplift_batch=4096):
         except Exception as e:      # noqa: BLE001 - report, the leg is informative only
             up['bf16_sdpa_error'] = str(e)[:200]
         out['uplift_forward'] = {'unit': 'trajectories/s', **up, 'note': 'cuBLAS + SDPA + ATen elementwise, matmul TF32 off (torch default)'}
+        del usd, usd16, ua, ub16
+        from oracle import vitpose as ovp
+        hp, wp = ovp.tokens_hw(VIT_RES[1], VIT_RES[0])
+        vsd = {k: v.to(dev) for k, v in ovp.random_state_dict(5, 9, hp * wp, 1).items()}
+        vx = torch.randn((4, 9, VIT_RES[1], VIT_RES[0]), device=dev, generator=g)
+        vit = {'fp32_default': timed(lambda: ovp.vitpose_forward_native(vsd, vx), 4)}
+        torch.backends.cuda.matmul.allow_tf32 = True
+        vit['tf32_matmul_opt_in'] = timed(lambda: ovp.vitpose_forward_native(vsd, vx), 4)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        vsd16 = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in vsd.items()}
+        vx16 = vx.to(torch.bfloat16)
+        try:
+            vit['bf16'] = timed(lambda: ovp.vitpose_forward_native(vsd16, vx16), 4)
+        except Exception as e:      # noqa: BLE001 - informative leg
+            vit['bf16_error'] = str(e)[:200]
+        out['vitpose_forward'] = {'unit': 'stacks/s', 'sub_batch': 4, **vit,
+                                  'note': 'network only, %dx%d input; torch defaults = fp32 cuBLAS Linear layers + TF32 cuDNN convolutions' % VIT_RES}
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
     torch.cuda.empty_cache()
@@ -708,6 +725,13 @@ def main():
         if up_line is not None:
             eager['speedup_uplift'] = {'tf32x3_vs_torch_fp32_sdpa': up_line['value'] / world / eager['uplift_forward']['fp32_sdpa_b4096'],
                                        'fp32_simt_vs_torch_fp32_sdpa': up_line['fp32_simt']['value'] / world / eager['uplift_forward']['fp32_sdpa_b4096']}
+        if vit_line is not None and 'vitpose_forward' in eager:
+            ev = eager['vitpose_forward']
+            eager['speedup_vitpose'] = {'note': 'ours includes pre-processing and decode, the torch figures are the network alone',
+                                        'tf32x3_vs_torch_fp32_default': vit_line['value'] / world / ev['fp32_default'],
+                                        'tf32x3_vs_torch_tf32_matmul_opt_in': vit_line['value'] / world / ev['tf32_matmul_opt_in']}
+            if 'bf16' in ev:
+                eager['speedup_vitpose']['bf16_vs_torch_bf16'] = vit_line['bf16']['value'] / world / ev['bf16']
     cpu = None
     if not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())

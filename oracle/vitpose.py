@@ -147,3 +147,38 @@ def vitpose_forward(sd, x):
         f = deconv_bn_relu(sd, 3, f)
         w, b = sd['model.keypoint_head.final_layer.weight'], sd['model.keypoint_head.final_layer.bias']
         return torch.einsum('bchw,oc->bohw', f, w[:, :, 0, 0]) + b[None, :, None, None]
+
+
+def vitpose_forward_native(sd, x):
+    """The same network through torch's library modules' functional forms -- F.conv2d / F.layer_norm / F.linear / F.gelu /
+    F.conv_transpose2d / F.batch_norm, materialised attention as vit.py:160-176 -- on whatever device and dtype `sd` and `x` live on.
+    This is what the reference's nn.Modules execute; bench.py times it on the GPU as the stock-PyTorch baseline, and
+    tests/test_oracle_golden.py pins it against vitpose_forward on the CPU."""
+    F = torch.nn.functional
+    with torch.no_grad():
+        p = 'model.backbone.'
+        B = x.shape[0]
+        t = F.conv2d(x, sd[p + 'patch_embed.proj.weight'], sd[p + 'patch_embed.proj.bias'], stride=PATCH, padding=PAD)
+        hp, wp = t.shape[2], t.shape[3]
+        t = t.flatten(2).transpose(1, 2)
+        pe = sd[p + 'pos_embed']
+        t = t + pe[:, 1:] + pe[:, :1]
+        for i in range(DEPTH):
+            b = p + 'blocks.%d.' % i
+            h = F.layer_norm(t, (DIM,), sd[b + 'norm1.weight'], sd[b + 'norm1.bias'], LN_EPS)
+            qkv = F.linear(h, sd[b + 'attn.qkv.weight'], sd[b + 'attn.qkv.bias']).reshape(B, -1, 3, HEADS, DIM // HEADS).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv[0] * (DIM // HEADS) ** -0.5, qkv[1], qkv[2]
+            o = ((q @ k.transpose(-2, -1)).softmax(dim=-1) @ v).transpose(1, 2).reshape(B, -1, DIM)
+            t = t + F.linear(o, sd[b + 'attn.proj.weight'], sd[b + 'attn.proj.bias'])
+            h = F.layer_norm(t, (DIM,), sd[b + 'norm2.weight'], sd[b + 'norm2.bias'], LN_EPS)
+            h = F.gelu(F.linear(h, sd[b + 'mlp.fc1.weight'], sd[b + 'mlp.fc1.bias']))
+            t = t + F.linear(h, sd[b + 'mlp.fc2.weight'], sd[b + 'mlp.fc2.bias'])
+        t = F.layer_norm(t, (DIM,), sd[p + 'last_norm.weight'], sd[p + 'last_norm.bias'], LN_EPS)
+        f = t.permute(0, 2, 1).reshape(B, DIM, hp, wp)
+        k = 'model.keypoint_head.'
+        for j in (0, 3):
+            f = F.conv_transpose2d(f, sd[k + 'deconv_layers.%d.weight' % j], None, stride=2, padding=1)
+            bn = k + 'deconv_layers.%d.' % (j + 1)
+            f = F.relu(F.batch_norm(f, sd[bn + 'running_mean'], sd[bn + 'running_var'], sd[bn + 'weight'], sd[bn + 'bias'], False, 0.0, BN_EPS))
+        return F.conv2d(f, sd[k + 'final_layer.weight'], sd[k + 'final_layer.bias'])
+

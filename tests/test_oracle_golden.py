@@ -153,3 +153,15 @@ def test_dbscan_restatement_matches_sklearn():
         pts = rng.uniform(0, 60, (n, 2)) if trial % 2 else np.round(rng.uniform(0, 40, (n, 2)))   # integer grid: exact eps ties
         ref = sk.DBSCAN(eps=10, min_samples=3).fit(pts).labels_
         assert np.array_equal(otl.dbscan_labels(pts, 10, 3), ref), trial
+
+
+def test_vitpose_native_forward_matches_restatement(golden):
+    """oracle.vitpose.vitpose_forward_native (torch library ops, the stock-PyTorch baseline bench.py times on the GPU) against the
+    reference-generated golden heatmaps and the explicit restatement."""
+    from oracle import vitpose as ov
+    g = golden('vitpose')
+    sd = ov.random_state_dict(int(g['ball_seed']), 9, 24, 1)
+    x = torch.from_numpy(g['ball_x'])
+    y = ov.vitpose_forward_native(sd, x).numpy()
+    assert np.abs(y - g['ball_y']).max() <= 1e-5 * np.abs(g['ball_y']).max() + 1e-6
+    assert np.abs(y - ov.vitpose_forward(sd, g['ball_x']).numpy()).max() <= 1e-5 * np.abs(y).max() + 1e-6

@@ -302,7 +302,7 @@ size_t ttk_attention3_scratch_bytes(int images, int tokens, int heads, int head_
 }
 
 int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_plane, void* vt_scratch, int images, int tokens, int heads,
-                   int head_dim, cudaStream_t st) {
+                   int head_dim, cudaStream_t st, int v_transposed) {
   if (head_dim != HD || images <= 0 || tokens <= 0 || images > 65535 || qkv_plane % 16 || out_plane % 16) {
     ttk_set_error("ttk_attention3: unsupported shape (head_dim %d, tokens %d, images %d)", head_dim, tokens, images);
     return TTK_ERR_UNSUPPORTED;
@@ -315,8 +315,10 @@ int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_pl
   }
   float* vt = (float*)vt_scratch;
   const size_t vt_plane = (size_t)images * heads * VR * tok_pad * 4;
-  v_transpose3_kernel<<<dim3(ttk_cdiv(tok_pad, 64), heads, images), 256, 0, st>>>(qkv, qkv_plane, tokens, tok_pad, dim, vt, vt_plane);
-  TTK_LAUNCH_CHECK();
+  if (!v_transposed) {       // (the x3 qkv GEMM of vit.cu writes V^T itself)
+    v_transpose3_kernel<<<dim3(ttk_cdiv(tok_pad, 64), heads, images), 256, 0, st>>>(qkv, qkv_plane, tokens, tok_pad, dim, vt, vt_plane);
+    TTK_LAUNCH_CHECK();
+  }
   Attn3Maps maps;
   bool ok = true;
   {

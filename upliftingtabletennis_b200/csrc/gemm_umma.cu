@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
     const bool c_bf16 = g.c_bf16 != 0;
     const bool c_split = X3 && g.c_split != 0;
     const long long c_plane = (long long)g.c_plane;
+    float* const vt = X3 ? g.vt : nullptr;
+    const int vt_col0 = g.vt_col0, vt_tokens = g.vt_tokens, vt_tok_pad = g.vt_tok_pad;
+    const size_t vt_plane = g.vt_plane;
     const float* __restrict__ gR = g.R;
     const float* __restrict__ gBias = g.bias;
     uint8_t* const gC = (uint8_t*)g.C;
@@ -282,6 +285,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_umma_kernel(const __grid_cons
         if (gR && live) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += r[j];
+        }
+        if (X3 && vt && n >= vt_col0) {
+          // V columns of the qkv GEMM: written transposed ([dim][token], the attention's K-major B operand).  Lane = token, so the 32
+          // lanes of a warp store 32 consecutive floats of one [dim] row: coalesced without staging.
+          if (live) {
+            const int img = m / vt_tokens, t = m - img * vt_tokens;
+            float* dst = vt + ((size_t)img * (gN - vt_col0) + (n - vt_col0)) * vt_tok_pad + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float hi, lo;
+              split_tf32(f[j], hi, lo);
+              dst[(size_t)j * vt_tok_pad] = hi;
+              *reinterpret_cast<float*>(reinterpret_cast<char*>(dst + (size_t)j * vt_tok_pad) + vt_plane) = lo;
+            }
+          }
+          continue;
         }
         // stage 64-byte row pieces of the warp's 32 x 32 block in shared memory, then write them out row-contiguous (4 lanes per row,
         // full 32-byte sectors): bf16 = one piece of 32 columns, float32 = two pieces of 16 columns
@@ -408,7 +427,7 @@ int launch(const GemmArgs& g, cudaStream_t st) {      // the activation is a com
 int ttk_gemm_umma(const GemmArgs& g, cudaStream_t st) {
   const int BK = g.x3 ? 32 : 64;
   if (g.M <= 0 || g.K % BK != 0 || g.N % 128 != 0 || (g.R && g.c_bf16) || (g.x3 && g.c_bf16) || (g.c_split && !g.x3) ||
-      (g.x3 && (g.a_plane % 16 || g.w_plane % 16 || g.c_plane % 16)) ||
+      (g.x3 && (g.a_plane % 16 || g.w_plane % 16 || g.c_plane % 16)) || (g.vt && (!g.x3 || g.vt_col0 % 128 || g.vt_tokens <= 0 || g.up_w)) ||
       (g.implicit_c && (g.implicit_c % BK != 0 || g.K != 4 * g.implicit_c || g.up_w <= 0 || g.R))) {
     ttk_set_error("ttk_gemm_umma: unsupported shape M %d N %d K %d", g.M, g.N, g.K);
     return TTK_ERR_UNSUPPORTED;

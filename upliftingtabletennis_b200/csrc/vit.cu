@@ -617,12 +617,21 @@ extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dt
     for (int i = 0; i < DEPTH; ++i) {
       const ttk_vit::Block& B = h->blocks[i];
       ln(B.ln1w, B.ln1b);
-      if ((rc = gemm(w.A, B.qkv, nullptr, w.QKV, T, VIT_ACT_NONE, bf, 0, 0, 0, 0, w.pA, x3 ? w.pQKV : 0)) != TTK_OK) return rc;
+      if (x3) {
+        // the V third of the output goes straight to the attention's transposed B operand (in HID, free until fc1)
+        GemmArgs g;
+        g.A = w.A, g.W = wptr(B.qkv.w_off), g.bias = fptr(B.qkv.b_off), g.R = nullptr, g.C = w.QKV, g.M = T, g.N = B.qkv.n, g.K = B.qkv.k;
+        g.act = VIT_ACT_NONE, g.c_bf16 = 0, g.up_h = g.up_w = g.py = g.px = 0;
+        g.x3 = 1, g.a_plane = w.pA, g.w_plane = h->pool_bytes, g.c_split = 1, g.c_plane = w.pQKV;
+        const int tok_pad = (h->tokens + 7) / 8 * 8;
+        g.vt = (float*)w.HID, g.vt_plane = (size_t)n * DIM * tok_pad * 4, g.vt_col0 = 2 * DIM, g.vt_tokens = h->tokens, g.vt_tok_pad = tok_pad;
+        if ((rc = launch_gemm(h, g, dtype, st)) != TTK_OK) return rc;
+      } else if ((rc = gemm(w.A, B.qkv, nullptr, w.QKV, T, VIT_ACT_NONE, bf)) != TTK_OK) return rc;
       ++h->launches;
       if (bf) {
         if ((rc = ttk_attention_umma((const __nv_bfloat16*)w.QKV, (__nv_bfloat16*)w.ATT, w.A, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
       } else if (x3) {
-        if ((rc = ttk_attention3((const float*)w.QKV, w.pQKV, (float*)w.ATT, w.pATT, w.A, n, h->tokens, HEADS, HD, st)) != TTK_OK) return rc;
+        if ((rc = ttk_attention3((const float*)w.QKV, w.pQKV, (float*)w.ATT, w.pATT, w.HID, n, h->tokens, HEADS, HD, st, 1)) != TTK_OK) return rc;
       } else {
         attention_f32_kernel<<<dim3(ttk_cdiv(h->tokens, 8), HEADS, n), 256, 0, st>>>((const float*)w.QKV, h->tokens, (float*)w.ATT);
       }

@@ -26,6 +26,11 @@ struct GemmArgs {
   int x3 = 0;
   int c_split = 0;        // x3 only: write C as such a pair (it feeds another x3 GEMM / the attention); 0: plain float32
   size_t a_plane = 0, w_plane = 0, c_plane = 0;
+  // x3 qkv GEMM only: columns >= vt_col0 (the V third, one head per 32 columns) are written TRANSPOSED instead, as the attention's B
+  // operand: vt[plane][row / vt_tokens][(col - vt_col0)][row % vt_tokens] with rows vt_tok_pad floats long, planes vt_plane bytes apart
+  float* vt = nullptr;
+  size_t vt_plane = 0;
+  int vt_col0 = 0, vt_tokens = 0, vt_tok_pad = 0;
   int implicit_c = 0;     // > 0 (tcgen05 path only): A is the NHWC feature map [img][up_h][up_w][implicit_c] itself and the 2x2 taps of the
                           // transposed convolution's output parity (py, px) are gathered by TMA (K = 4 taps x implicit_c), no materialised gather
 };
@@ -81,5 +86,6 @@ int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_sc
 // attn3_umma.cu: the same attention with fp32-level results (3xTF32).  qkv / out are split float32 plane pairs ([2][T][3*dim],
 // [2][T][dim]; planes qkv_plane / out_plane bytes apart); vt_scratch: ttk_attention3_scratch_bytes(...) bytes.
 size_t ttk_attention3_scratch_bytes(int images, int tokens, int heads, int head_dim);
+// v_transposed: vt_scratch already holds V^T ([2][images][heads*32][tok_pad], tok_pad = tokens rounded up to 8) -- the qkv GEMM wrote it
 int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_plane, void* vt_scratch, int images, int tokens, int heads,
-                   int head_dim, cudaStream_t st);
+                   int head_dim, cudaStream_t st, int v_transposed = 0);

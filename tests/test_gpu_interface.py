@@ -93,6 +93,31 @@ def test_vitpose_detectors_predict(weights, golden):
     assert np.mean(err < 1e-3) >= 0.9, err
 
 
+def test_vitpose_api_default_is_reference_class(weights, golden):
+    """Without dtype= the ViTPose detectors run the tf32x3 tensor-core path, and that path meets the float32 bound against the
+    reference's own interface output; a pipeline-wide dtype of 'tf32' / 'tf32x3' keeps every component on its reference-class path."""
+    from oracle.gen_golden import write_vitpose_checkpoints
+    import hubconf
+    write_vitpose_checkpoints(weights)
+    g = golden('interface_vitpose')
+    frames = list(g['frames'])
+    bd = hubconf.ball_detection('vitpose')
+    assert bd.model.compute_dtype == 'tf32x3'
+    pos, hm = bd.predict([(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, 4)])
+    np.testing.assert_allclose(hm, g['ball_hm'], rtol=0, atol=1e-4 * np.abs(g['ball_hm']).max() + 1e-5)
+    np.testing.assert_allclose(pos[:, :2], g['ball_pos'][:, :2], rtol=0, atol=1e-3)
+    td = hubconf.table_detection('vitpose')
+    tpos, thm = td.predict(frames[:2])
+    np.testing.assert_allclose(thm, g['table_hm'], rtol=0, atol=1e-4 * np.abs(g['table_hm']).max() + 1e-5)
+    for dt, want in ((None, ('tf32x3', 'tf32', 'tf32x3', 'tf32', 'tf32x3')), ('tf32', ('tf32x3', 'tf32', 'tf32x3', 'tf32', 'tf32x3')),
+                     ('bf16', ('bf16',) * 5)):
+        pipe = hubconf.full_pipeline(dtype=dt)
+        got = tuple(m.model.compute_dtype for m in (pipe.ball_detector, pipe.ball_detector_aux, pipe.table_detector, pipe.table_detector_aux,
+                                                    pipe.uplifting_model))
+        assert got == want, (dt, got)
+        del pipe
+
+
 def test_uplifting_model_predict(weights, golden):
     from upliftingtabletennis_b200.interface import UpliftingModel
     g = golden('interface')

@@ -58,3 +58,38 @@ def test_two_ranks_nccl_gather_equals_single_rank(tmp_path, n):
         assert got.shape == (n, sharding.RECORD_FLOATS)
         # fp32 path: a trajectory's result does not depend on which other trajectories share its launch
         np.testing.assert_array_equal(got, expect)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs (gpurun --gpus 2)')
+def test_one_process_two_devices():
+    """One process driving two GPUs: per-device kernel attributes are set on each device, every model's weights live on the device it
+    first ran on, results agree bit for bit, and a handle refuses to run while another device is current."""
+    from oracle import hrnet as ohr, uplift as oup, vitpose as ovp
+    from upliftingtabletennis_b200 import synthetic
+    from upliftingtabletennis_b200.detector import WASBNet
+    from upliftingtabletennis_b200.uplift import get_model
+    from upliftingtabletennis_b200.vitpose import VitPose
+    sd_w = ohr.random_state_dict(9, 3, seed=3)
+    hp, wp = ovp.tokens_hw(64, 96)
+    sd_v = ovp.random_state_dict(4, 9, hp * wp, 1)
+    sd_u = oup.random_state_dict(5)
+    x_w = torch.randn(2, 9, 64, 96)
+    traj = [torch.from_numpy(a) for a in synthetic.trajectories(16, seed=2)]
+    outs = []
+    for d in (0, 1):
+        dev = torch.device('cuda', d)
+        with torch.cuda.device(d):
+            w = WASBNet(in_frames=3, resolution=(96, 64)).to(dev).eval()
+            w.load_state_dict(sd_w)
+            v = VitPose(in_frames=3, resolution=(96, 64)).to(dev).eval()
+            v.load_state_dict(sd_v)
+            u = get_model('connectstage', 'large', 'dynamic', 'new').to(dev).eval()
+            u.load_state_dict(sd_u)
+            outs.append((w(x_w.to(dev))[0].cpu(), v(x_w.to(dev))[0].cpu(), u(*(t.to(dev) for t in traj))[1].cpu()))
+            if d == 0:
+                first = (w, x_w.to(dev))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    with torch.cuda.device(1):                      # the cuda:0 model while device 1 is current
+        with pytest.raises(RuntimeError, match='device'):
+            first[0](first[1])

@@ -308,10 +308,9 @@ int ttk_attention3(const float* qkv, size_t qkv_plane, float* out, size_t out_pl
     return TTK_ERR_UNSUPPORTED;
   }
   const int dim = heads * HD, tok_pad = (tokens + 7) / 8 * 8;
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(attention3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
   }
   float* vt = (float*)vt_scratch;
   const size_t vt_plane = (size_t)images * heads * VR * tok_pad * 4;

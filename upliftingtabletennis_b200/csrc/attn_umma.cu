@@ -282,10 +282,9 @@ int ttk_attention_umma(const __nv_bfloat16* qkv, __nv_bfloat16* out, void* vt_sc
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
     return TTK_ERR_CUDA;
   }
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(attention_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
   }
   __nv_bfloat16* vt = (__nv_bfloat16*)vt_scratch;
   v_transpose_kernel<<<dim3(ttk_cdiv(tok_pad, 64), heads, images), 256, 0, st>>>(qkv, tokens, tok_pad, dim, vt);

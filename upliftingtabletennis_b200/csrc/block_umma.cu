@@ -337,10 +337,9 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
     return TTK_ERR_CUDA;
   }
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
-    attr = true;
   }
   CUtensorMap map;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};

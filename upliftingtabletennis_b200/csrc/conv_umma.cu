@@ -649,11 +649,10 @@ int launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
     return TTK_ERR_CUDA;
   }
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<KS, S, CIN, COUT, R, STAGES, RB, KCO, ESZ, HF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   C::SMEM_BYTES));
-    attr = true;
   }
   if (S == 2 && ((a.hin & 1) || (a.win & 1))) return TTK_ERR_UNSUPPORTED;
   // the input map's TFLOAT32 type makes TMA round fp32 to TF32 (nearest-even) while it fills shared memory
@@ -726,10 +725,9 @@ int launch_dual(const void* w_dual, const float* bias_dual, const ConvLaunch& a,
   using C = Cfg<1, 1, CINK, 128, R, STAGES, 0, 0, ESZ>;
   EncodeFn encode = get_encode();
   if (!encode) return TTK_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(conv_umma_kernel<1, 1, CINK, 128, R, STAGES, 0, 0, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr = true;
   }
   KMaps maps;
   cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)BW, (cuuint32_t)R, 1};

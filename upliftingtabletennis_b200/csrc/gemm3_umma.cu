@@ -294,10 +294,9 @@ int ttk_gemm3(const Gemm3Args& g, cudaStream_t st) {
     ttk_set_error("ttk_gemm3: unsupported shape M %d N %d (K is 128, N a multiple of 128; row statistics need N = 128)", g.M, g.N);
     return TTK_ERR_UNSUPPORTED;
   }
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(gemm3_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr = true;
   }
   G3Maps maps;
   if (!encode_f32_2d(&maps.a, g.A, (uint64_t)g.M, KD) || !encode_f32_2d(&maps.whi, g.W_hi, (uint64_t)g.N, KD) ||

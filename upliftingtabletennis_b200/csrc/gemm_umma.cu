@@ -361,10 +361,9 @@ template <int BN, bool WRES, int ACT, bool X3>
 int launch_act(const GemmArgs& g, cudaStream_t st) {
   using C = GCfg<BN, WRES, X3>;
   constexpr int BK = C::BK;
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(gemm_umma_kernel<BN, WRES, ACT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr = true;
   }
   GemmMaps maps;
   bool ok_a, ok_w;

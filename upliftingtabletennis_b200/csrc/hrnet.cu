@@ -814,6 +814,7 @@ extern "C" int ttk_hrnet_conv_info(const ttk_hrnet* h, int i, char* name, char* 
 extern "C" int ttk_hrnet_set_conv(ttk_hrnet* h, int i, const float* w_host, const float* b_host) {
   TTK_CHECK_ARG(h && i >= 0 && i < (int)h->convs.size(), "ttk_hrnet_set_conv: bad index %d", i);
   TTK_CHECK_ARG(w_host && b_host, "ttk_hrnet_set_conv: null pointer");
+  if (int rc = ttk_bind_device(&h->device, "ttk_hrnet_set_conv")) return rc;
   TtkConv& c = h->convs[i];
   const int kk = c.k * c.k;
   if (i == (int)h->convs.size() - 1) {
@@ -865,6 +866,7 @@ extern "C" size_t ttk_hrnet_workspace_bytes(const ttk_hrnet* h, int batch, int h
 extern "C" int ttk_hrnet_forward(ttk_hrnet* h, const void* x_dev, int batch, int height, int width, int dtype,
                                  float* heatmaps_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_hrnet_forward: null handle");
+  if (int rc = ttk_bind_device(&h->device, "ttk_hrnet_forward")) return rc;
   TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32, "ttk_hrnet_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0 && height > 0 && width > 0 && height % 8 == 0 && width % 8 == 0,
                 "ttk_hrnet_forward: height and width must be positive multiples of 8 (got %dx%d)", height, width);

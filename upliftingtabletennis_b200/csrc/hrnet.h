@@ -53,6 +53,7 @@ struct ConvLaunch {
 
 struct ttk_hrnet {
   int in_ch, out_ch, out_first, out_count;
+  int device = -1;              // device of the packed weights (ttk_bind_device)
   std::vector<TtkConv> convs;
   std::vector<TtkTensor> tensors;
   std::vector<TtkOp> ops;

@@ -527,6 +527,7 @@ extern "C" int ttk_uplift_set_param(ttk_uplift* h, int i, const float* data_host
   TTK_CHECK_ARG(h && i >= 0 && i < (int)h->params.size(), "ttk_uplift_set_param: bad index %d", i);
   UpliftParam& p = h->params[i];
   TTK_CHECK_ARG(data_host && numel == p.numel, "ttk_uplift_set_param: %s expects %d elements, got %d", p.name.c_str(), p.numel, numel);
+  if (int rc = ttk_bind_device(&h->device, "ttk_uplift_set_param")) return rc;
   if (!p.dev) TTK_CUDA(cudaMalloc((void**)&p.dev, (size_t)numel * sizeof(float)));
   TTK_CUDA(cudaMemcpy(p.dev, data_host, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
   p.set = true;
@@ -554,6 +555,7 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
                                   const float* times_dev, int batch, int seq_len, int dtype, float* rot_out_dev,
                                   float* pos_out_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_uplift_forward: null handle");
+  if (int rc = ttk_bind_device(&h->device, "ttk_uplift_forward")) return rc;
   TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32X3, "ttk_uplift_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0 && seq_len >= 2 && seq_len + 1 <= MT, "ttk_uplift_forward: seq_len must be in [2, %d] (got %d)", MT - 1, seq_len);
   for (const UpliftParam& p : h->params)
@@ -570,14 +572,13 @@ extern "C" int ttk_uplift_forward(ttk_uplift* h, const float* ball_dev, const fl
     int rc = finalize_layers(h);
     if (rc) return rc;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static TtkPerDevice attr_done;
+  if (attr_done.first()) {
     TTK_CUDA(cudaFuncSetAttribute(uplift_stack_kernel<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     TTK_CUDA(cudaFuncSetAttribute(uplift_stack_kernel<MODE_TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     TTK_CUDA(cudaFuncSetAttribute(uplift_stack_kernel<MODE_SECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     TTK_CUDA(cudaFuncSetAttribute(embed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     TTK_CUDA(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEAD_SMEM_BYTES));
-    attr_done = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int T = seq_len;

@@ -22,6 +22,7 @@ struct UpliftParam {
 
 struct ttk_uplift {
   int dim, heads, depth, skip;
+  int device = -1;                 // device of the parameters (ttk_bind_device)
   std::vector<UpliftParam> params;
   LayerW* layers_dev = nullptr;    // [4 pos + (depth-4) temporal + 4 second]
   bool layers_ready = false;

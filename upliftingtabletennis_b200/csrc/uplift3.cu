@@ -272,15 +272,14 @@ size_t ttk_uplift3_workspace_bytes(const ttk_uplift* h, int batch, int T) {
 // One stage.  POS: io.X (ball embeddings [batch T][128]) and io.table_emb -> io.X (ball tokens after the table-token layers);
 // TEMPORAL: io.X in place; SECOND: cls + (io.X or io.second_emb) -> io.table_emb[0 .. batch) (the cls rows, input of the rotation head).
 int ttk_uplift3_stage(ttk_uplift* h, int mode, const UpliftIO& io, void* ws, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_POS, NTAB + 1, 2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(32)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_POS, NTAB + 1, 2, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(32)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_TEMPORAL, 52, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_TEMPORAL, 64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_SECOND, 52, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
     TTK_CUDA(cudaFuncSetAttribute(attention3_kernel<MODE_SECOND, 64, 1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem(64)));
-    attr = true;
   }
   const int T = io.T, batch = io.batch;
   const long long ntok = (long long)batch * T;

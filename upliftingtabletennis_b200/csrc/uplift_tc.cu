@@ -705,12 +705,11 @@ int ttk_uplift_tc_stage(ttk_uplift* h, int mode, const UpliftIO& io, cudaStream_
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
     return TTK_ERR_CUDA;
   }
-  static bool attr = false;
-  if (!attr) {
+  static TtkPerDevice attr;
+  if (attr.first()) {
     TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_TEMPORAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     TTK_CUDA(cudaFuncSetAttribute(uplift_tc_kernel<MODE_SECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    attr = true;
   }
   const int n_layers_total = h->depth + 4;
   CUtensorMap wmap;

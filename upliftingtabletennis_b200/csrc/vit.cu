@@ -560,6 +560,7 @@ extern "C" size_t ttk_vit_workspace_bytes(const ttk_vit* h, int batch, int dtype
 extern "C" int ttk_vit_forward(ttk_vit* h, const float* x_dev, int batch, int dtype, float* heatmaps_dev, void* workspace_dev,
                                size_t workspace_bytes, void* stream) {
   TTK_CHECK_ARG(h, "ttk_vit_forward: null handle");
+  if (int rc = ttk_bind_device(&h->device, "ttk_vit_forward")) return rc;
   TTK_CHECK_ARG(dtype == TTK_F32 || dtype == TTK_BF16 || dtype == TTK_TF32X3, "ttk_vit_forward: bad dtype %d", dtype);
   TTK_CHECK_ARG(batch >= 0, "ttk_vit_forward: bad batch");
   if (!h->ready) {

@@ -47,6 +47,7 @@ struct ttk_vit {
   int in_ch, out_ch, height, width, hp, wp, tokens;
   std::vector<VitParam> params;
   bool ready = false;
+  int device = -1;          // device of the packed weights (ttk_bind_device)
   int launches = 0;
   int subbatch = 16;
   // prepared device weights (float32 and bf16 copies of every GEMM operand)

@@ -204,3 +204,24 @@ def test_process_trajectory_seams(weights, golden):
     bm.compute_dtype = 'tf32'
     bpos_tf = iu.process_trajectory_ball(bm, torch.from_numpy(ball))
     assert bpos_tf.shape == bpos.shape and np.isfinite(bpos_tf).all()      # output parity of this path: tests/test_gpu_output_parity.py
+
+
+def test_predict_segments_long_inputs(weights, golden):
+    """predict() uploads at most `segment` stacks at a time; the concatenated result equals the one-upload result."""
+    import hubconf
+    g = golden('interface')
+    frames = list(g['frames'])
+    triples = [(frames[i - 1], frames[i], frames[i + 1]) for i in range(1, len(frames) - 1)]
+    bd = hubconf.ball_detection('wasb')
+    pos, hm = bd.predict(triples)
+    bd.segment = 2
+    pos2, hm2 = bd.predict(triples)
+    assert pos2.shape == pos.shape and hm2.shape == hm.shape
+    np.testing.assert_array_equal(pos2, pos)
+    np.testing.assert_array_equal(hm2, hm)
+    td = hubconf.table_detection('hrnet')
+    tpos, thm = td.predict(frames)
+    td.segment = 3
+    tpos2, thm2 = td.predict(frames)
+    np.testing.assert_array_equal(tpos2, tpos)
+    np.testing.assert_array_equal(thm2, thm)

@@ -349,6 +349,18 @@ class _Detector:
         return bounds
 
     stage_slots = 16               # pinned staging ring for numpy frames: 16 x 6.2 MB at 1080p, whatever the clip length
+    segment = 512                  # stacks per upload of predict(): bounds device and pinned memory for arbitrarily long inputs
+                                   # (514 1080p frames = 3.2 GB on the device; the reference streams frame by frame)
+
+    def _predict_segments(self, images, return_heatmaps):
+        """predict() over at most `segment` stacks at a time; the numpy results are concatenated."""
+        pos, hms = [], []
+        for s0 in range(0, max(len(images), 1), self.segment):
+            p, hm = self.predict_device(images[s0:s0 + self.segment], return_heatmaps, heatmaps_to_host=True)
+            pos.append(p.cpu().numpy())
+            if return_heatmaps:
+                hms.append(hm.numpy())          # (a view of the pinned block; the array keeps it alive)
+        return (pos[0] if len(pos) == 1 else np.concatenate(pos)), ((hms[0] if len(hms) == 1 else np.concatenate(hms)) if return_heatmaps else None)
 
     def _upload(self, images, dev):
         """Upload each distinct frame once, asynchronously on a copy stream.  numpy frames (pageable memory, what cv2 delivers) go
@@ -455,8 +467,7 @@ class BallDetector(_Detector):
     def predict(self, images, return_heatmaps=True):
         """images: list (length B) of (prev, curr, next) HWC uint8 BGR frames.
         Returns pred_pos (B, 3) float64 [x, y, 1.0] and the heatmaps (B, 1, h, w) float32 (None if return_heatmaps=False)."""
-        pos, hm = self.predict_device(images, return_heatmaps, heatmaps_to_host=True)
-        return pos.cpu().numpy(), (hm.numpy() if return_heatmaps else None)
+        return self._predict_segments(images, return_heatmaps)
 
     def predict_device(self, images, return_heatmaps=False, heatmaps_to_host=False):
         """predict() without the device->host copy: positions (B, 3) float64 and heatmaps stay CUDA tensors."""
@@ -493,8 +504,8 @@ class TableDetector(_Detector):
 
     def predict(self, images, return_heatmaps=True):
         """images: list of HWC uint8 BGR frames -> pred_pos (B, 13, 3) float64, heatmaps (B, 1, 13, h, w)."""
-        pos, hm = self.predict_device(images, return_heatmaps, heatmaps_to_host=True)
-        return pos.cpu().numpy(), (hm[:, None].numpy() if return_heatmaps else None)
+        pos, hm = self._predict_segments(images, return_heatmaps)
+        return pos, (hm[:, None] if return_heatmaps else None)
 
     def predict_device(self, images, return_heatmaps=False, heatmaps_to_host=False):
         frames, order, ready = self._upload(list(images), self.device)

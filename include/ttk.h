@@ -37,6 +37,8 @@ enum { TTK_LAYOUT_NCHW_F32 = 0, TTK_LAYOUT_NHWC16 = 1 };
 
 TTK_API int ttk_version(void);
 TTK_API const char* ttk_last_error(void);
+/* Host helper of the plugin side (interface.py: numpy frames -> pinned staging ring): memcpy with non-temporal stores. */
+TTK_API int ttk_host_copy_stream(void* dst, const void* src, size_t bytes);
 /* 1 when a CUDA device with compute capability 10.x is present, else 0 (never raises). */
 TTK_API int ttk_device_ok(void);
 

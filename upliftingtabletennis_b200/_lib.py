@@ -26,6 +26,7 @@ def _load():
     sig = {
         'ttk_version': (i32, []),
         'ttk_last_error': (C.c_char_p, []),
+        'ttk_host_copy_stream': (i32, [vp, vp, sz]),
         'ttk_device_ok': (i32, []),
         'ttk_preprocess_stacks': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
         'ttk_hrnet_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),

@@ -1,5 +1,10 @@
-// libttk: version, error state, device probe.
+// libttk: version, error state, device probe, host staging copy.
 #include "ttk_internal.h"
+
+#include <string.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 static thread_local char g_err[512] = "";
 
@@ -33,4 +38,34 @@ extern "C" int ttk_device_ok(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10 ? 1 : 0;
+}
+
+// Host copy of one frame into a pinned staging slot with non-temporal stores: the slot is read next by the DMA engine, not by a
+// core, so the stores bypass the cache and skip the read-for-ownership of the destination lines (2 instead of 3 memory transfers
+// per byte).  Called from Python worker threads through ctypes (which drops the GIL).
+extern "C" int ttk_host_copy_stream(void* dst, const void* src, size_t bytes) {
+  if (!dst || !src) {
+    ttk_set_error("ttk_host_copy_stream: null pointer");
+    return TTK_ERR_ARG;
+  }
+#if defined(__x86_64__)
+  if (((uintptr_t)dst & 15) == 0 && bytes >= 4096) {
+    const __m128i* s = (const __m128i*)src;
+    __m128i* d = (__m128i*)dst;
+    const size_t lines = bytes / 64;
+    for (size_t i = 0; i < lines; ++i) {
+      const __m128i a = _mm_loadu_si128(s + 4 * i), b = _mm_loadu_si128(s + 4 * i + 1), c = _mm_loadu_si128(s + 4 * i + 2),
+                    e = _mm_loadu_si128(s + 4 * i + 3);
+      _mm_stream_si128(d + 4 * i, a);
+      _mm_stream_si128(d + 4 * i + 1, b);
+      _mm_stream_si128(d + 4 * i + 2, c);
+      _mm_stream_si128(d + 4 * i + 3, e);
+    }
+    _mm_sfence();
+    memcpy((char*)dst + lines * 64, (const char*)src + lines * 64, bytes - lines * 64);
+    return TTK_OK;
+  }
+#endif
+  memcpy(dst, src, bytes);
+  return TTK_OK;
 }

@@ -13,7 +13,7 @@ import zipfile
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .detector import MyHRNet, WASBNet
 from .precision import TF32, TF32X3, canonical
 from .vitpose import TableVitPose, VitPose
@@ -416,6 +416,7 @@ class _Detector:
             stage = self._stage = torch.empty((ns,) + fshape, dtype=torch.uint8).pin_memory()
             self._stage_ev = [None] * ns
         view, slot_ev = stage.numpy(), self._stage_ev
+        slot_ptr = [stage[k].data_ptr() for k in range(ns)]
         marks = _ReadyMarks([i for i in range(n) if i % 2 == 1 or i == n - 1])      # an event every other frame: the first pass (4 stacks) starts after 6 frames
         out.record_stream(copy_stream)
         dev_index = torch.cuda.current_device()
@@ -424,7 +425,11 @@ class _Detector:
             if ev is not None:
                 ev.synchronize()            # the transfer that last read this slot (possibly of an earlier call) has finished
             u = uniq[i]
-            view[i % ns] = u.numpy() if isinstance(u, torch.Tensor) else u
+            u = u.numpy() if isinstance(u, torch.Tensor) else u
+            if u.flags['C_CONTIGUOUS']:     # non-temporal stores: 11.5 instead of 8.7 GB/s per thread (tools/host_staging_probe.py)
+                _lib.check(_lib.lib.ttk_host_copy_stream(slot_ptr[i % ns], u.ctypes.data, u.nbytes))
+            else:
+                view[i % ns] = u
 
         def run():
             try:

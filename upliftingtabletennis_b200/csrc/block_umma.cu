@@ -33,6 +33,7 @@ struct BCfg {
   static constexpr int ROWB = ESZ * C;                 // bytes per pixel row of a tile (32 or 64)
   static constexpr int R1 = R + 2, RX = R + 4;         // intermediate rows, input rows
   static constexpr int NX = SLOTS + 1;                 // input tile ring: one tile per slot in flight plus one being loaded
+  static constexpr int NSG = SLOTS == 1 ? 2 : 1;       // epilogue warp groups per slot: with one slot both groups drain it, half the rows each
   static constexpr int X_BYTES = RX * TW * ROWB, X_AL = al1024(X_BYTES);
   static constexpr int T_BYTES = R1 * TW * ROWB, T_AL = al1024(T_BYTES);
   static constexpr int W_BYTES = 9 * C * ROWB, W_AL = al1024(W_BYTES);
@@ -122,14 +123,14 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < K::NX; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_xempty + 8 * s, 4);
+      mbar_init(bar_xempty + 8 * s, 4 * K::NSG);
     }
     for (int k = 0; k < SLOTS; ++k) {
       mbar_init(bar_m1 + 8 * k, 1);
-      mbar_init(bar_st + 8 * k, 4);
+      mbar_init(bar_st + 8 * k, 4 * K::NSG);
       mbar_init(bar_m2 + 8 * k, 1);
     }
-    mbar_init(bar_init, 4 * SLOTS);
+    mbar_init(bar_init, 4 * SLOTS * K::NSG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();                                  // weights / zeros: generic-proxy writes -> async proxy (tensor core)
@@ -186,16 +187,26 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
         }
       }
     }
-  } else if (warp - 2 < 4 * SLOTS) {
-    // epilogue group k = (warp - 2) / 4 serves slot k; TMEM lane quarter q = warp % 4, thread = pixel of a tile row.
-    // Rows are drained G at a time (64 accumulator columns per TMEM wait) so that the load latency is paid once per group.
-    const int q = warp & 3, k = (warp - 2) >> 2;
+  } else {
+    // epilogue group (warp - 2) / 4 serves slot k (two slots), or half the rows of the only slot; TMEM lane quarter q = warp % 4,
+    // thread = pixel of a tile row.  Rows are drained G at a time (64 accumulator columns per TMEM wait) so that the load latency is
+    // paid once per group.
+    const int q = warp & 3, ge = (warp - 2) >> 2;
+    const int k = SLOTS == 1 ? 0 : ge, sg = SLOTS == 1 ? ge : 0;
+    constexpr int E1_ROWS = K::R1 / K::NSG, E2_ROWS = R / K::NSG;
+    static_assert(K::R1 % K::NSG == 0 && R % K::NSG == 0, "rows split evenly between the epilogue groups");
+    const int e1_lo = sg * E1_ROWS, e1_hi = e1_lo + E1_ROWS, e2_lo = sg * E2_ROWS, e2_hi = e2_lo + E2_ROWS;
     const int m = q * 32 + lane;                       // pixel within the tile row = TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t acc1 = tmem + k * K::ACC, acc2 = acc1 + K::ACC1;
     constexpr int G = 64 / C;                          // rows per group
-    for (int c = 0; c < K::ACC; c += 16) tmem_zero16(acc1 + lane_base + c);
+    for (int c = sg * 16; c < K::ACC; c += 16 * K::NSG) tmem_zero16(acc1 + lane_base + c);
     tmem_wait_st();
+    float b1r[C], b2r[C];                               // biases in registers (TF32 instantiation; the bf16 ones read shared memory)
+    if (ESZ == 4) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) b1r[j] = sB1[j], b2r[j] = sB2[j];
+    }
     fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_init);
@@ -211,25 +222,25 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       const int ix = x0 - 1 + m;
       const bool col_in = ix >= 0 && ix < a.w;
 #pragma unroll 1
-      for (int r0 = 0; r0 < K::R1; r0 += G) {
+      for (int r0 = e1_lo; r0 < e1_hi; r0 += G) {
         uint32_t v[G][C];
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          if (r0 + g < K::R1) {
+          if (r0 + g < e1_hi) {
 #pragma unroll
             for (int c = 0; c < C; c += 16) tmem_ld16(acc1 + lane_base + (K::R1 - 1 - (r0 + g)) * C + c, v[g] + c);
           }
         tmem_wait_ld();
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          if (r0 + g < K::R1) {
+          if (r0 + g < e1_hi) {
 #pragma unroll
             for (int c = 0; c < C; c += 16) tmem_zero16(acc1 + lane_base + (K::R1 - 1 - (r0 + g)) * C + c);
           }
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const int ri = r0 + g;
-          if (ri < K::R1) {
+          if (ri < e1_hi) {
             const int iy = y0 - 1 + ri;
             const bool inside = col_in && iy >= 0 && iy < a.h;
             uint32_t pk[C * ESZ / 4];
@@ -242,11 +253,12 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
                 pk[j] = *reinterpret_cast<uint32_t*>(&b2);
               }
             } else {
-              // the intermediate is an operand of kind::tf32, which truncates: round it here like TMA rounds the tensors it loads
+              // the intermediate is an operand of kind::tf32, which truncates: round it here (to nearest; the integer form of
+              // cvt.rna.tf32.f32, exact for these non-negative finite values and a quarter of its instructions)
 #pragma unroll
               for (int j = 0; j < C; ++j) {
-                const float f0 = inside ? fmaxf(__uint_as_float(v[g][j]) + sB1[j], 0.f) : 0.f;
-                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(pk[j]) : "f"(f0));
+                const float f0 = inside ? fmaxf(__uint_as_float(v[g][j]) + b1r[j], 0.f) : 0.f;
+                pk[j] = (__float_as_uint(f0) + 0x1000u) & 0xFFFFE000u;
               }
             }
             const uint32_t row_ad = st_base + (ri * TW + m) * K::ROWB;
@@ -271,11 +283,11 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       const bool col_ok = m < WO && ox < a.w;
       const uint32_t sx_base = smem_u32(sX + s * K::X_AL);
 #pragma unroll 1
-      for (int r0 = 0; r0 < R; r0 += G) {
+      for (int r0 = e2_lo; r0 < e2_hi; r0 += G) {
         uint32_t v[G][C], rv[G][C * ESZ / 4];
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          if (r0 + g < R) {
+          if (r0 + g < e2_hi) {
 #pragma unroll
             for (int c = 0; c < C; c += 16) tmem_ld16(acc2 + lane_base + (R - 1 - (r0 + g)) * C + c, v[g] + c);
             const uint32_t row_ad = sx_base + ((r0 + g + 2) * TW + (m + 2)) * K::ROWB;
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
         tmem_wait_ld();
 #pragma unroll
         for (int g = 0; g < G; ++g)
-          if (r0 + g < R) {
+          if (r0 + g < e2_hi) {
 #pragma unroll
             for (int c = 0; c < C; c += 16) tmem_zero16(acc2 + lane_base + (R - 1 - (r0 + g)) * C + c);
           }
@@ -297,7 +309,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
         for (int g = 0; g < G; ++g) {
           const int r = r0 + g;
           const int oy = y0 + r;
-          if (r < R && col_ok && oy < a.h) {
+          if (r < e2_hi && col_ok && oy < a.h) {
             uint32_t o[C * ESZ / 4];
             if (ESZ == 2) {
 #pragma unroll
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
             } else {
               // the residual is the staged input tile, i.e. x as TMA rounded it to TF32 (2^-12 relative: inside the path's class)
 #pragma unroll
-              for (int j = 0; j < C; ++j) o[j] = __float_as_uint(fmaxf(__uint_as_float(v[g][j]) + sB2[j] + __uint_as_float(rv[g][j]), 0.f));
+              for (int j = 0; j < C; ++j) o[j] = __float_as_uint(fmaxf(__uint_as_float(v[g][j]) + b2r[j] + __uint_as_float(rv[g][j]), 0.f));
             }
             uint4* op = reinterpret_cast<uint4*>((char*)a.out + (((size_t)img * a.h + oy) * a.w + ox) * C * ESZ);
 #pragma unroll

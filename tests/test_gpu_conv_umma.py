@@ -150,16 +150,18 @@ def test_network_block_fusion_on_off(net):
     assert np.linalg.norm((y_on - y_off).cpu().numpy()) / np.linalg.norm(ref) < 2e-2
 
 
-def test_network_block_fusion_tf32(net):
-    """TF32 path: the six BasicBlocks of the 16-channel full-resolution branch as fused kernels against the conv-by-conv plan.  The fused
-    kernel rounds the intermediate with cvt.rna (TMA rounds to even) and takes the residual from the TF32-rounded staged tile, so the two
-    plans agree to TF32 resolution, not bit for bit."""
+@pytest.mark.parametrize('mode', [2, 3])
+def test_network_block_fusion_tf32(net, mode):
+    """TF32 path: the six BasicBlocks of the 16-channel full-resolution branch as fused kernels against the conv-by-conv plan.
+    mode 2: blockhf_umma.cu (horizontal tap fusion, fp32 residual from global memory); mode 3: block_umma.cu (one MMA per tap, residual
+    from the TF32-rounded staged tile).  The fused kernels round the intermediate to nearest (TMA rounds to even), so the plans agree to
+    TF32 resolution, not bit for bit.  The image is 264 pixels wide: three 124- / 126-pixel tiles with a ragged last one."""
     from upliftingtabletennis_b200._lib import lib
     m, sd = net
     x = torch.from_numpy(np.random.default_rng(3).standard_normal((2, 9, 72, 264)).astype(np.float32)).cuda()
     m.compute_dtype = 'tf32'
     try:
-        lib.ttk_hrnet_set_block_fusion(m.engine.h, 2)          # 2 = also the TF32 blocks (off by default: slower than conv by conv, hrnet.cu)
+        lib.ttk_hrnet_set_block_fusion(m.engine.h, mode)
         y_on, _ = m(x)
         n_on = m.engine.last_launches()
         lib.ttk_hrnet_set_block_fusion(m.engine.h, 0)

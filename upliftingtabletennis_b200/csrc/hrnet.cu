@@ -621,7 +621,7 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
     // TF32: the fused kernel exists (16 channels, one tile in flight: 227 KB do not hold a second slot of fp32 tiles) and is parity-green,
     // but M1 -> E1 -> M2 -> E2 of a single tile run back to back: 2.19 ms per block against 1.50 ms for the two HBM-bound convolutions, so
     // it is used only when asked for (use_block_fusion == 2)
-    if (umma && is_basic_block(h, oi) && ((esz == 2 && h->use_block_fusion) || (esz == 4 && h->use_block_fusion == 2 && h->convs[op.conv].cin_p == 16))) {
+    if (umma && is_basic_block(h, oi) && ((esz == 2 && h->use_block_fusion) || (esz == 4 && h->use_block_fusion >= 2 && h->convs[op.conv].cin_p == 16))) {
       const TtkOp& op2 = h->ops[oi + 1];
       const TtkTensor& ti = h->tensors[op.in];
       auto p2 = [&](int t) -> void* { return t == h->input_tensor ? const_cast<void*>(x) : (void*)(ws + h->tensors[t].offset); };
@@ -635,7 +635,10 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
         r.flops += 2.0 * opix * c2.cin * c2.cout * 9;
         r.bytes = 2.0 * opix * ti.c * sizeof(T) + 2.0 * 9 * ti.c * ti.c * sizeof(T);
       }
-      const int rc = ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st, esz);
+      // TF32: mode 2 = horizontal tap fusion (blockhf_umma.cu), mode 3 = the per-tap kernel of block_umma.cu
+      const int rc = esz == 4 && h->use_block_fusion == 2
+                         ? ttk_blockhf_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st)
+                         : ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st, esz);
       if (rc == TTK_OK) {
         h->launches++;
         ++oi;                                      // conv2 is done as well

@@ -107,7 +107,9 @@ TTK_API int ttk_hrnet_debug_conv(ttk_hrnet* h, int conv_index, const void* in_de
                          int relu, int path, void* out_dev, void* stream);
 /* Test hook: one BasicBlock (convs conv_index and conv_index + 1, 16 or 32 padded channels) through the fused tcgen05 kernel:
  * out = relu(conv2(relu(conv1(in))) + in), NHWC bf16.  ttk_hrnet_set_block_fusion: 0 runs the blocks conv by conv (A/B, cross-check),
- * 1 (default) fuses the bf16 blocks of the 16- and 32-channel branches, 2 also the TF32 16-channel blocks (measured slower). */
+ * 1 (default) fuses the bf16 blocks of the 16- and 32-channel branches, 2 / 3 also the TF32 16-channel blocks (two 3-row tiles in flight
+ * with the fp32 residual from global memory / one 4-row tile with the residual from the staged tile; measured no faster than conv by
+ * conv). */
 TTK_API int ttk_hrnet_debug_block(ttk_hrnet* h, int conv_index, const void* in_dev, int n, int hin, int win, void* out_dev, void* stream);
 TTK_API int ttk_hrnet_set_block_fusion(ttk_hrnet* h, int enable);
 TTK_API int ttk_hrnet_set_profile(ttk_hrnet* h, int enable);

@@ -153,9 +153,9 @@ def test_network_block_fusion_on_off(net):
 @pytest.mark.parametrize('mode', [2, 3])
 def test_network_block_fusion_tf32(net, mode):
     """TF32 path: the six BasicBlocks of the 16-channel full-resolution branch as fused kernels against the conv-by-conv plan.
-    mode 2: blockhf_umma.cu (horizontal tap fusion, fp32 residual from global memory); mode 3: block_umma.cu (one MMA per tap, residual
-    from the TF32-rounded staged tile).  The fused kernels round the intermediate to nearest (TMA rounds to even), so the plans agree to
-    TF32 resolution, not bit for bit.  The image is 264 pixels wide: three 124- / 126-pixel tiles with a ragged last one."""
+    mode 2: two 3-row tiles in flight, fp32 residual from global memory; mode 3: one 4-row tile, residual from the TF32-rounded staged
+    tile.  The fused kernels round the intermediate to nearest (TMA rounds to even), so the plans agree to TF32 resolution, not bit for
+    bit.  The image is 264 pixels wide (three 126-pixel tiles with a ragged last one) and 72 high (24 / 18 row tiles)."""
     from upliftingtabletennis_b200._lib import lib
     m, sd = net
     x = torch.from_numpy(np.random.default_rng(3).standard_normal((2, 9, 72, 264)).astype(np.float32)).cuda()

@@ -28,11 +28,14 @@ constexpr int BW = 128, WO = 126, TW = 130, THREADS = 320;      // TMA warp, MMA
 constexpr int al1024(int b) { return (b + 1023) & ~1023; }
 
 
-template <int C, int R, int SLOTS, int ESZ = 2>
+// GRES (TF32): the residual x is read from global memory (L2: TMA fetched the same lines a moment ago) in fp32 instead of from the
+// staged tile, which TMA rounded to TF32 -- the block then computes what the two separate convolutions compute -- and the input tile is
+// free as soon as conv1 has read it, so two buffers serve two slots.
+template <int C, int R, int SLOTS, int ESZ = 2, int GRES = 0>
 struct BCfg {
   static constexpr int ROWB = ESZ * C;                 // bytes per pixel row of a tile (32 or 64)
   static constexpr int R1 = R + 2, RX = R + 4;         // intermediate rows, input rows
-  static constexpr int NX = SLOTS + 1;                 // input tile ring: one tile per slot in flight plus one being loaded
+  static constexpr int NX = GRES ? 2 : SLOTS + 1;      // input tile ring: one tile per slot in flight plus one being loaded
   static constexpr int NSG = SLOTS == 1 ? 2 : 1;       // epilogue warp groups per slot: with one slot both groups drain it, half the rows each
   static constexpr int X_BYTES = RX * TW * ROWB, X_AL = al1024(X_BYTES);
   static constexpr int T_BYTES = R1 * TW * ROWB, T_AL = al1024(T_BYTES);
@@ -50,6 +53,7 @@ struct BCfg {
 struct BlockArgs {
   const void *w1, *w2;               // packed like ttk_conv_umma_pack (fused 3x3: [kx][ky][cout][cin])
   const float *b1, *b2;
+  const void* x;                     // the block's input (GRES: residual source)
   void* out;
   int n, h, w;
   int tiles_x, tiles_y, total;
@@ -86,9 +90,9 @@ __device__ __forceinline__ void issue_conv(uint32_t abase, uint32_t wbase, uint3
 // Tiles of a CTA are numbered t = 0, 1, 2, ... in the order it takes them; tile t lives in input buffer t % NX and in slot t % SLOTS
 // (slot = its own accumulators and intermediate tile, served by its own group of four epilogue warps), so with two slots the MMAs of
 // one tile run under the epilogues of the other.
-template <int C, int R, int SLOTS, int ESZ = 2>
+template <int C, int R, int SLOTS, int ESZ = 2, int GRES = 0>
 __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_constant__ CUtensorMap xmap, const BlockArgs a) {
-  using K = BCfg<C, R, SLOTS, ESZ>;
+  using K = BCfg<C, R, SLOTS, ESZ, GRES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW1 = smem;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < K::NX; ++s) {
       mbar_init(bar_xfull + 8 * s, 1);
-      mbar_init(bar_xempty + 8 * s, 4 * K::NSG);
+      mbar_init(bar_xempty + 8 * s, GRES ? 1 : 4 * K::NSG);
     }
     for (int k = 0; k < SLOTS; ++k) {
       mbar_init(bar_m1 + 8 * k, 1);
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
             fence_after();
             issue_conv<C, K::R1, K::LAYOUT, ESZ>(smem_u32(sX + s * K::X_AL), smem_u32(sW1), acc1, leader);
             if (leader) commit(bar_m1 + 8 * k);
+            if (GRES && leader) commit(bar_xempty + 8 * s);      // nothing else reads the input tile
             __syncwarp();
             stage[k] = 1;
           } else {
@@ -277,25 +282,42 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_st + 8 * k);
       // ---- E2: output pixel (y0 + r, x0 + m), residual from the staged input tile at (r + 2, m + 2) ----
-      mbar_wait(bar_m2 + 8 * k, tp);
-      fence_after();
       const int ox = x0 + m;
       const bool col_ok = m < WO && ox < a.w;
       const uint32_t sx_base = smem_u32(sX + s * K::X_AL);
+      // GRES: the fp32 residual rows are requested from global memory (L2) BEFORE the wait for conv2, whose ~1400 clk cover the latency
+      // (one row group holds all of E2's rows: R <= G)
+      static_assert(!GRES || E2_ROWS <= G, "one residual prefetch per tile");
+      uint32_t rv[G][C * ESZ / 4];
+      if (GRES) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int oy = y0 + e2_lo + g;
+          if (g < E2_ROWS && col_ok && oy < a.h) {
+            const char* rp = (const char*)a.x + (((size_t)img * a.h + oy) * a.w + ox) * C * ESZ;
+#pragma unroll
+            for (int u = 0; u < K::ROWB / 32; ++u) ldg256(rp + 32 * u, rv[g] + 8 * u);
+          }
+        }
+      }
+      mbar_wait(bar_m2 + 8 * k, tp);
+      fence_after();
 #pragma unroll 1
       for (int r0 = e2_lo; r0 < e2_hi; r0 += G) {
-        uint32_t v[G][C], rv[G][C * ESZ / 4];
+        uint32_t v[G][C];
 #pragma unroll
         for (int g = 0; g < G; ++g)
           if (r0 + g < e2_hi) {
 #pragma unroll
             for (int c = 0; c < C; c += 16) tmem_ld16(acc2 + lane_base + (R - 1 - (r0 + g)) * C + c, v[g] + c);
-            const uint32_t row_ad = sx_base + ((r0 + g + 2) * TW + (m + 2)) * K::ROWB;
+            if (!GRES) {
+              const uint32_t row_ad = sx_base + ((r0 + g + 2) * TW + (m + 2)) * K::ROWB;
 #pragma unroll
-            for (int u = 0; u < K::ROWB / 16; ++u) {
-              uint32_t ad = row_ad + u * 16;
-              ad ^= ((ad >> 7) & K::SWZ) << 4;
-              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[g][4 * u]), "=r"(rv[g][4 * u + 1]), "=r"(rv[g][4 * u + 2]), "=r"(rv[g][4 * u + 3]) : "r"(ad));
+              for (int u = 0; u < K::ROWB / 16; ++u) {
+                uint32_t ad = row_ad + u * 16;
+                ad ^= ((ad >> 7) & K::SWZ) << 4;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rv[g][4 * u]), "=r"(rv[g][4 * u + 1]), "=r"(rv[g][4 * u + 2]), "=r"(rv[g][4 * u + 3]) : "r"(ad));
+              }
             }
           }
         tmem_wait_ld();
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
       tmem_wait_st();
       fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_xempty + 8 * s);  // the input tile (residual source) is free
+      if (!GRES && lane == 0) mbar_arrive(bar_xempty + 8 * s);  // the input tile (residual source) is free
     }
   }
   fence_before();
@@ -341,9 +363,9 @@ __global__ void __launch_bounds__(THREADS, 1) block_umma_kernel(const __grid_con
   if (warp == 2) tmem_dealloc(tmem, K::TMEM_COLS);
 }
 
-template <int C, int R, int SLOTS, int ESZ = 2>
+template <int C, int R, int SLOTS, int ESZ = 2, int GRES = 0>
 int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st) {
-  using K = BCfg<C, R, SLOTS, ESZ>;
+  using K = BCfg<C, R, SLOTS, ESZ, GRES>;
   EncodeFn encode = get_encode();
   if (!encode) {
     ttk_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -351,7 +373,7 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
   }
   static TtkPerDevice attr;
   if (attr.first()) {
-    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS, ESZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
+    TTK_CUDA(cudaFuncSetAttribute(block_umma_kernel<C, R, SLOTS, ESZ, GRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES));
   }
   CUtensorMap map;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -366,12 +388,12 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
   }
   BlockArgs a;
   a.w1 = ESZ == 2 ? (const void*)c1.w_umma : (const void*)c1.w_umma32, a.w2 = ESZ == 2 ? (const void*)c2.w_umma : (const void*)c2.w_umma32;
-  a.b1 = c1.bias, a.b2 = c2.bias, a.out = y;
+  a.b1 = c1.bias, a.b2 = c2.bias, a.x = x, a.out = y;
   a.n = n, a.h = h, a.w = w;
   a.tiles_x = ttk_cdiv(w, WO), a.tiles_y = ttk_cdiv(h, R);
   a.total = a.tiles_x * a.tiles_y * n;
   const int grid = std::max(1, std::min(a.total, ttk_num_sms()));
-  block_umma_kernel<C, R, SLOTS, ESZ><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
+  block_umma_kernel<C, R, SLOTS, ESZ, GRES><<<grid, THREADS, K::SMEM_BYTES, st>>>(map, a);
   TTK_LAUNCH_CHECK();
   return TTK_OK;
 }
@@ -383,7 +405,10 @@ int launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, 
 int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st, int esz) {
   if (c1.k != 3 || c2.k != 3 || c1.stride != 1 || c2.stride != 1 || c1.cin_p != c1.cout_p || c2.cin_p != c1.cin_p || c2.cout_p != c1.cin_p)
     return TTK_ERR_UNSUPPORTED;
-  if (esz == 4) return c1.cin_p == 16 ? launch<16, 4, 1, 4>(c1, c2, x, y, n, h, w, st) : TTK_ERR_UNSUPPORTED;      // 64-byte rows, one slot
+  // TF32 (64-byte rows): two 3-row tiles in flight with the fp32 residual from global memory (esz 4), or one 4-row tile with the residual
+  // from the staged tile (esz 5: the first version, kept for comparison)
+  if (esz == 4) return c1.cin_p == 16 ? launch<16, 3, 2, 4, 1>(c1, c2, x, y, n, h, w, st) : TTK_ERR_UNSUPPORTED;
+  if (esz == 5) return c1.cin_p == 16 ? launch<16, 4, 1, 4, 0>(c1, c2, x, y, n, h, w, st) : TTK_ERR_UNSUPPORTED;
   if (c1.cin_p == 16) return launch<16, 6, 2>(c1, c2, x, y, n, h, w, st);      // two tiles in flight (2 x 224 TMEM columns)
   if (c1.cin_p == 32) return launch<32, 4, 1>(c1, c2, x, y, n, h, w, st);      // 320 TMEM columns per tile: one slot
   return TTK_ERR_UNSUPPORTED;

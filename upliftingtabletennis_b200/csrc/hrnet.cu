@@ -618,9 +618,8 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
   bool dual_skipped = false;
   for (size_t oi = 0; oi < h->ops.size(); ++oi) {
     const TtkOp& op = h->ops[oi];
-    // TF32: the fused kernel exists (16 channels, one tile in flight: 227 KB do not hold a second slot of fp32 tiles) and is parity-green,
-    // but M1 -> E1 -> M2 -> E2 of a single tile run back to back: 2.19 ms per block against 1.50 ms for the two HBM-bound convolutions, so
-    // it is used only when asked for (use_block_fusion == 2)
+    // TF32: the fused kernels exist (16 channels) and are parity-green, but the thin MMAs of a 16-channel convolution keep them at or
+    // above the time of the two HBM-bound convolutions, so they run only when asked for (use_block_fusion 2 / 3)
     if (umma && is_basic_block(h, oi) && ((esz == 2 && h->use_block_fusion) || (esz == 4 && h->use_block_fusion >= 2 && h->convs[op.conv].cin_p == 16))) {
       const TtkOp& op2 = h->ops[oi + 1];
       const TtkTensor& ti = h->tensors[op.in];
@@ -635,10 +634,9 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
         r.flops += 2.0 * opix * c2.cin * c2.cout * 9;
         r.bytes = 2.0 * opix * ti.c * sizeof(T) + 2.0 * 9 * ti.c * ti.c * sizeof(T);
       }
-      // TF32: mode 2 = horizontal tap fusion (blockhf_umma.cu), mode 3 = the per-tap kernel of block_umma.cu
-      const int rc = esz == 4 && h->use_block_fusion == 2
-                         ? ttk_blockhf_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st)
-                         : ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st, esz);
+      // TF32: mode 2 = two 3-row tiles in flight (fp32 residual from global memory), mode 3 = one 4-row tile (residual from the staged tile)
+      const int rc = ttk_block_umma_launch(h->convs[op.conv], h->convs[op2.conv], p2(op.in), p2(op2.out), bs, H >> ti.shift, W >> ti.shift, st,
+                                           esz == 4 && h->use_block_fusion == 3 ? 5 : esz);
       if (rc == TTK_OK) {
         h->launches++;
         ++oi;                                      // conv2 is done as well
@@ -983,7 +981,7 @@ extern "C" int ttk_hrnet_debug_block(ttk_hrnet* h, int conv_index, const void* i
 
 extern "C" int ttk_hrnet_set_block_fusion(ttk_hrnet* h, int enable) {
   TTK_CHECK_ARG(h, "ttk_hrnet_set_block_fusion: null handle");
-  h->use_block_fusion = enable;          // 0 off, 1 bf16 blocks (default), 2 also the TF32 16-channel blocks
+  h->use_block_fusion = enable;          // 0 off, 1 bf16 blocks (default), 2 / 3 also the TF32 16-channel blocks (two 3-row tiles / one 4-row tile)
   return TTK_OK;
 }
 

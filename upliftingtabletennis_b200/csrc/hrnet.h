@@ -94,5 +94,3 @@ void ttk_conv_umma_pack_dual(const float* w3, const float* wd, int esz, std::vec
 
 // block_umma.cu: y = relu(conv2(relu(conv1(x))) + x) for the 3x3 stride-1 pairs of a BasicBlock with 16 or 32 (padded) channels.
 int ttk_block_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st, int esz = 2);
-// blockhf_umma.cu: the same block for 16 fp32 channels (TF32 products) with horizontal tap fusion and an fp32 residual
-int ttk_blockhf_umma_launch(const TtkConv& c1, const TtkConv& c2, const void* x, void* y, int n, int h, int w, cudaStream_t st);

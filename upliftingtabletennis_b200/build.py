@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libttk.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-         '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden'] + os.environ.get('TTK_NVCC_FLAGS', '').split()
 
 
 def sources():

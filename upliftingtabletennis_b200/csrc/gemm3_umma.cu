@@ -25,7 +25,10 @@ namespace {
 using namespace umma;
 
 constexpr int BM = 128, BN = 128, KD = 128, KC = 32, NKC = KD / KC;
-constexpr int STAGES = 3;
+#ifndef TTK_GEMM3_STAGES
+#define TTK_GEMM3_STAGES 3      // tools/run_sanitizer.sh builds a 2-stage variant for synccheck, whose own bookkeeping needs shared memory
+#endif
+constexpr int STAGES = TTK_GEMM3_STAGES;
 constexpr int CHUNK_BYTES = BM * KC * 4;                 // 16 KB: 128 rows x 128 bytes
 constexpr int W_BYTES = 2 * NKC * CHUNK_BYTES;           // hi | lo, four chunks each
 constexpr int STAGE_BYTES = 2 * CHUNK_BYTES;             // raw -> hi (in place) | lo

@@ -325,6 +325,13 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     from upliftingtabletennis_b200 import _lib, ops, sharding, synthetic
+    # several ranks on one host: waiting host threads sleep instead of spin, so that the cores go to the threads that stage frames
+    # (2 cores per GPU on this pool's boxes).  TTK_HOST_SYNC=spin keeps CUDA's default.
+    host_sync = 'spin'
+    if int(os.environ.get('LOCAL_WORLD_SIZE', world) or 1) > 1 and os.environ.get('TTK_HOST_SYNC', 'blocking') == 'blocking':
+        _lib.host_blocking_sync(local)
+        host_sync = 'blocking'
+
     from upliftingtabletennis_b200._lib import lib
     from upliftingtabletennis_b200.precision import storage_dtype
     hub = tempfile.mkdtemp(prefix='ttk_bench_hub_')
@@ -759,7 +766,9 @@ def main():
         'ms_per_step': head['ms_dev'] / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': args.dtype, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'api_default_dtype': api_default,
-                   'parallelism': 'clip-sharded x%d, NCCL all_gather of (x,y,v) records' % world, 'l2': 'inputs (211 MB of frames) and activations exceed the 126 MB L2',
+                   'parallelism': 'clip-sharded x%d, NCCL all_gather of (x,y,v) records' % world,
+                   'host_sync': host_sync + (' (cudaDeviceScheduleBlockingSync: several ranks share the host cores)' if host_sync == 'blocking' else ' (CUDA default)'),
+                   'l2': 'inputs (211 MB of frames) and activations exceed the 126 MB L2',
                    'weights': 'seeded synthetic (synthetic.hrnet_blob_state_dict: random, BN folded; the frames\' bright blob survives to the heatmap so that peaks are genuine)'},
         'e2e': dict(e2e_entry(head['ms_copy_hm'], args.steps, "hubconf.ball_detection('wasb').predict(triples): 32 (prev, cur, next) triples of numpy frames in pageable host memory, every "
                               "frame a separate .copy() as interface.py:275 builds them (96 frames cross PCIe), heatmaps returned as numpy like the reference's default call",

@@ -39,6 +39,9 @@ TTK_API int ttk_version(void);
 TTK_API const char* ttk_last_error(void);
 /* Host helper of the plugin side (interface.py: numpy frames -> pinned staging ring): memcpy with non-temporal stores. */
 TTK_API int ttk_host_copy_stream(void* dst, const void* src, size_t bytes);
+/* Host threads waiting for `device` sleep instead of spin (cudaDeviceScheduleBlockingSync; process-global for that device): for hosts
+ * that run one rank per GPU with few cores per GPU.  old_flags (may be NULL) receives the previous device flags. */
+TTK_API int ttk_host_blocking_sync(int device, unsigned* old_flags);
 /* 1 when a CUDA device with compute capability 10.x is present, else 0 (never raises). */
 TTK_API int ttk_device_ok(void);
 

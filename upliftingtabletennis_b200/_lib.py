@@ -27,6 +27,7 @@ def _load():
         'ttk_version': (i32, []),
         'ttk_last_error': (C.c_char_p, []),
         'ttk_host_copy_stream': (i32, [vp, vp, sz]),
+        'ttk_host_blocking_sync': (i32, [i32, C.POINTER(C.c_uint)]),
         'ttk_device_ok': (i32, []),
         'ttk_preprocess_stacks': (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
         'ttk_hrnet_create': (i32, [i32, i32, i32, i32, C.POINTER(vp)]),
@@ -96,6 +97,16 @@ def check(rc):
 def require_device():
     if not lib.ttk_device_ok():
         raise TtkError('libttk needs an sm_100 (B200) CUDA device; none is visible and there is no CPU fallback')
+
+
+def host_blocking_sync(device=None):
+    """Host threads waiting for `device` (default: the current one) sleep instead of spin.  For hosts that run one rank per GPU with few
+    cores per GPU, where spinning waiters take the cores from the frame-staging threads; process-global for the device.  Returns the
+    previous device flags."""
+    import torch
+    old = C.c_uint(0)
+    check(lib.ttk_host_blocking_sync(torch.cuda.current_device() if device is None else int(device), C.byref(old)))
+    return old.value
 
 
 def stream_ptr(stream=None):

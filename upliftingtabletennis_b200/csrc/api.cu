@@ -69,3 +69,24 @@ extern "C" int ttk_host_copy_stream(void* dst, const void* src, size_t bytes) {
   memcpy(dst, src, bytes);
   return TTK_OK;
 }
+
+// Make host threads that wait for this device (stream / event synchronisation, blocking copies) sleep instead of spin.  CUDA's default
+// spins when there are no more contexts than cores; with one rank per GPU on a host that has two cores per GPU, every rank's waiting
+// threads then burn the cores its frame-staging threads need (bench.py at eight ranks: DESIGN.md section 5).  Process-global for the
+// device; returns the previous flags in *old_flags (may be null).
+extern "C" int ttk_host_blocking_sync(int device, unsigned* old_flags) {
+  int cur = 0;
+  TTK_CUDA(cudaGetDevice(&cur));
+  TTK_CUDA(cudaSetDevice(device));
+  unsigned flags = 0;
+  TTK_CUDA(cudaGetDeviceFlags(&flags));
+  if (old_flags) *old_flags = flags;
+  const cudaError_t e = cudaSetDeviceFlags((flags & ~(unsigned)cudaDeviceScheduleMask) | cudaDeviceScheduleBlockingSync);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ttk_set_error("ttk_host_blocking_sync: cudaSetDeviceFlags -> %s", cudaGetErrorString(e));
+    return TTK_ERR_CUDA;
+  }
+  return TTK_OK;
+}

@@ -256,7 +256,8 @@ def _staging_pool():
         from concurrent.futures import ThreadPoolExecutor
         # host threads that copy numpy frames into the pinned staging ring: up to 8, sharing the cores with the other ranks of the node
         ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 8) // ranks)), thread_name_prefix='ttk-stage')
+        n = int(os.environ.get('TTK_STAGE_THREADS', '0') or 0) or max(2, min(8, (os.cpu_count() or 8) // ranks))
+        _POOL = ThreadPoolExecutor(max_workers=n, thread_name_prefix='ttk-stage')
     return _POOL
 
 

@@ -86,7 +86,15 @@ struct Cfg {
   static constexpr int RES_BYTES = RB ? 2 * NRB * RBOX_BYTES : 0;
   static constexpr uint32_t RSWZ = RROWB == 32 ? 1u : RROWB == 64 ? 3u : 7u;
   static constexpr int XCH_BYTES = HF ? 4 * 2 * R * COUT * 4 : 0;      // HF: edge-lane exchange between the four epilogue warps
-  static constexpr int SMEM_BYTES = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + RES_BYTES + COUT * 4 + XCH_BYTES + 256;
+  static constexpr int SMEM_BASE = 1024 + W_BYTES_AL + STAGES * STAGE_BYTES + RES_BYTES + COUT * 4 + XCH_BYTES + 256;
+  // STG (fp32 layers with >= 32 output channels per CTA, where shared memory allows): a column group (32 channels = 128 contiguous
+  // bytes of a pixel) is staged per warp in shared memory and written out row-contiguous -- 8 pixels x 128 bytes per store
+  // instruction instead of 32 pixels x 32 bytes, a quarter of the L1 wavefronts.  The wide layers' epilogues are bound by exactly
+  // those: stem conv1 ran at 64 % of the HBM rate with l1tex 95 % busy.
+  static constexpr int STG_WARP_BYTES = 32 * 128;
+  static constexpr bool STG_WANTED = S == 1 && !RB && !HF && ESZ == 4 && COUT % 32 == 0 && R * COUT >= 64;
+  static constexpr bool STG = STG_WANTED && SMEM_BASE + 128 + 4 * STG_WARP_BYTES <= 232448;
+  static constexpr int SMEM_BYTES = SMEM_BASE + (STG ? 128 + 4 * STG_WARP_BYTES : 0);
   static constexpr uint32_t LAYOUT = ROWB == 32 ? 6u : ROWB == 64 ? 4u : 2u;     // SWIZZLE_32B / 64B / 128B
   static constexpr uint32_t SWZ = ROWB == 32 ? 1u : ROWB == 64 ? 3u : 7u;
   static_assert(S == 1 || KS == 3, "stride 2 is implemented for 3x3 only");
@@ -137,6 +145,8 @@ __global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel
   float* sXch = sBias + COUT;                           // HF: [warp][set 0 of lane 31 | set 2 of lane 0][R][COUT]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sXch + C::XCH_BYTES / 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+  // STG: per-warp staging rows of 128 bytes, 128-byte aligned (behind the barriers' 256 bytes)
+  uint8_t* sStage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars) + 256 + 127) & ~(uintptr_t)127);
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * STAGES, bar_tfull = bar_empty + 8 * STAGES,
                  bar_tempty = bar_tfull + 16, bar_rfull = bar_tempty + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -461,6 +471,42 @@ __global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (g + 1 < G) fetch(g + 1, v[(g + 1) & 1], rv[(g + 1) & 1]);
+          if constexpr (C::STG) {
+            // the group's 32 channels of this lane's pixel -> staging row `lane` (16-byte chunk c at slot c ^ (lane & 7): conflict free),
+            // then 4 store instructions of 8 pixels x 128 contiguous bytes each (lane = pixel it * 8 + lane / 4, 32-byte piece lane % 4)
+            const int col = g * GCOLS, r = R - 1 - col / COUT, c0 = col % COUT;
+            const int oy = ty * R + r;
+            const uint32_t srow = smem_u32(sStage) + (warp - 2) * C::STG_WARP_BYTES;
+#pragma unroll
+            for (int sb = 0; sb < NSUB; ++sb) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[g & 1][sb][j]) + sBias[c0 + sb * 16 + j];
+              if (nres > 0) add_words(f, rv[g & 1][sb]);
+              if (a.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(srow + lane * 128 + (((sb * 4 + u) ^ (lane & 7)) << 4)), "f"(f[4 * u]),
+                             "f"(f[4 * u + 1]), "f"(f[4 * u + 2]), "f"(f[4 * u + 3])
+                             : "memory");
+            }
+            __syncwarp();
+            const int pq = lane & 3;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int p = it * 8 + (lane >> 2);
+              uint32_t o[8];
+              lds128(srow + p * 128 + (((2 * pq) ^ (p & 7)) << 4), o);
+              lds128(srow + p * 128 + (((2 * pq + 1) ^ (p & 7)) << 4), o + 4);
+              const int oxp = tx * BW + (warp & 3) * 32 + p;
+              if (oxp < a.w_img && oy < a.h)
+                stg256((char*)a.out + ((((size_t)img * a.h + oy) * a.w_img + oxp) * a.cout_total + n_off + c0) * 4 + pq * 32, o);
+            }
+            __syncwarp();
+          } else
 #pragma unroll
           for (int sb = 0; sb < NSUB; ++sb) {
             const int col = g * GCOLS + sb * 16, r = R - 1 - col / COUT, c0 = col % COUT;
@@ -872,7 +918,7 @@ int ttk_conv_umma_launch(const TtkConv& cv, const ConvLaunch& a, cudaStream_t st
   if (k == KS_ && s == S_ && ci == CI_ && co == CO_) return launch<KS_, S_, CI_, CO_, R_, ST_, RB_, KC_, 4>(cv, a, st);
   // 3x3 stride 1
   TTK_UMMA32(3, 1, 16, 64, 4, 3, 0, 16)      // stem conv1
-  TTK_UMMA32(3, 1, 64, 64, 4, 3, 0, 8)       // stem conv2, quarter-resolution branch: 147 KB of weights + three 25 KB boxes
+  TTK_UMMA32(3, 1, 64, 64, 4, 3, 0, 8)       // stem conv2, quarter-resolution branch: 147 KB of weights + three 25 KB boxes (no room for store staging; two boxes + staging measured slower: 3.80 vs 3.66 ms)
   if (k == 3 && s == 1 && ci == 32 && co == 32 && a.nres == 0) return launch<3, 1, 32, 32, 8, 2, 0, 16, 4>(cv, a, st);
   TTK_UMMA32(3, 1, 32, 32, 4, 3, 0, 16)      // half-resolution branch (residual read from global memory: no room for staged tiles)
   if (k == 3 && s == 1 && ci == 16 && co == 16 && a.nres == 0) return launch<3, 1, 16, 16, 8, 2, 0, 16, 4>(cv, a, st);     // taller tile (R = 4 with four stages: 0.77 vs 0.66 ms)

@@ -442,74 +442,78 @@ int launch_conv_simt(const TtkConv& cv, const ConvLaunch& a, bool rounded_weight
 }
 
 // out = act(in + sum_r res_r[y >> s_r, x >> s_r])   (full-resolution fuse of a HighResolutionModule)
-// 16 bytes per thread per access (8 bf16 / 4 fp32 channels), two independent items in flight per thread.  One grid row per
-// image row and shifts for the channel-vector split (c / V is a power of two), so no thread divides: the first version
-// decomposed a flat 64-bit index with three divisions per item and ran at half the HBM rate because of them.
+// 32 bytes per thread per access (16 bf16 / 8 fp32 channels, 256-bit loads and stores), two independent items in flight per thread.
+// One grid row per image row and shifts for the channel-vector split (c / V is a power of two), so no thread divides: the first
+// version decomposed a flat 64-bit index with three divisions per item and ran at half the HBM rate because of them.
+__device__ __forceinline__ void sum_ld256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
 template <typename T>
 __global__ void __launch_bounds__(256) sum_kernel(const T* __restrict__ in, T* __restrict__ out, const T* __restrict__ res0,
                                                   const T* __restrict__ res1, const T* __restrict__ res2, int rs0, int rs1,
                                                   int rs2, int nres, int h, int w, int c, int cv_shift, int relu) {
-  constexpr int V = 16 / sizeof(T);                 // channels per 16-byte vector
+  constexpr int V = 32 / sizeof(T);                 // channels per 32-byte item
   const T* rp[3] = {res0, res1, res2};
   const int rsh[3] = {rs0, rs1, rs2};
   const int y = blockIdx.y, b = blockIdx.z;
   const int row_items = w << cv_shift;
-  const size_t row0 = ((size_t)b * h + y) * (size_t)row_items;      // in 16-byte items
+  const size_t row0 = ((size_t)b * h + y) * (size_t)row_items;      // in 32-byte items
   const int e0 = blockIdx.x * 512 + threadIdx.x;
   float v[2][V];
-  uint4 raw[2];
+  uint32_t raw[2][8];
   bool live[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int e = e0 + u * 256;
     live[u] = e < row_items;
-    if (live[u]) raw[u] = *reinterpret_cast<const uint4*>(in + (row0 + e) * V);
+    if (live[u]) sum_ld256(in + (row0 + e) * V, raw[u]);
   }
+  auto widen = [](const uint32_t* q, float* f, bool add) {
+    if (sizeof(T) == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float lo = __uint_as_float(q[j] << 16), hi = __uint_as_float(q[j] & 0xffff0000u);
+        f[2 * j % V] = add ? f[2 * j % V] + lo : lo;
+        f[(2 * j + 1) % V] = add ? f[(2 * j + 1) % V] + hi : hi;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j % V] = add ? f[j % V] + __uint_as_float(q[j]) : __uint_as_float(q[j]);
+    }
+  };
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     if (!live[u]) continue;
     const int e = e0 + u * 256;
-    if (sizeof(T) == 2) {
-      const uint32_t wv[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[u][2 * j] = __uint_as_float(wv[j] << 16);
-        v[u][2 * j + 1] = __uint_as_float(wv[j] & 0xffff0000u);
-      }
-    } else {
-      v[u][0] = __uint_as_float(raw[u].x); v[u][1] = __uint_as_float(raw[u].y);
-      v[u][2] = __uint_as_float(raw[u].z); v[u][3] = __uint_as_float(raw[u].w);
-    }
+    widen(raw[u], v[u], false);
     const int x = e >> cv_shift, ci = e & ((1 << cv_shift) - 1);
     for (int r = 0; r < nres; ++r) {
       const int sh = rsh[r];
-      const uint4 q = *reinterpret_cast<const uint4*>(rp[r] + (((size_t)b * (h >> sh) + (y >> sh)) * (w >> sh) + (x >> sh)) * c + ci * V);
-      if (sizeof(T) == 2) {
-        const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[u][2 * j] += __uint_as_float(wv[j] << 16);
-          v[u][2 * j + 1] += __uint_as_float(wv[j] & 0xffff0000u);
-        }
-      } else {
-        v[u][0] += __uint_as_float(q.x); v[u][1] += __uint_as_float(q.y);
-        v[u][2] += __uint_as_float(q.z); v[u][3] += __uint_as_float(q.w);
-      }
+      uint32_t q[8];
+      sum_ld256(rp[r] + (((size_t)b * (h >> sh) + (y >> sh)) * (w >> sh) + (x >> sh)) * c + ci * V, q);
+      widen(q, v[u], true);
     }
     if (relu) {
 #pragma unroll
       for (int j = 0; j < V; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
     }
-    uint4 o;
+    uint32_t o[8];
     if (sizeof(T) == 2) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[u][0], v[u][1]), p1 = __floats2bfloat162_rn(v[u][2], v[u][3]);
-      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][4 % V], v[u][5 % V]), p3 = __floats2bfloat162_rn(v[u][6 % V], v[u][7 % V]);
-      o = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1), *reinterpret_cast<uint32_t*>(&p2),
-                     *reinterpret_cast<uint32_t*>(&p3));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[u][2 * j % V], v[u][(2 * j + 1) % V]);
+        o[j] = *reinterpret_cast<uint32_t*>(&p2);
+      }
     } else {
-      o = make_uint4(__float_as_uint(v[u][0]), __float_as_uint(v[u][1]), __float_as_uint(v[u][2]), __float_as_uint(v[u][3]));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(v[u][j % V]);
     }
-    *reinterpret_cast<uint4*>(out + (row0 + e) * V) = o;
+    T* op = out + (row0 + e) * V;
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]),
+                 "r"(o[6]), "r"(o[7])
+                 : "memory");
   }
 }
 
@@ -713,7 +717,7 @@ int run_plan(ttk_hrnet* h, const void* x, int bs, int H, int W, float* heat, cha
     } else if (op.type == OP_SUM) {
       const TtkTensor& to = h->tensors[op.out];
       const int hh = H >> to.shift, ww = W >> to.shift;
-      const int cv = to.c / (16 / (int)sizeof(T));
+      const int cv = to.c / (32 / (int)sizeof(T));          // 32-byte items per pixel
       int cv_shift = 0;
       while ((1 << cv_shift) < cv) ++cv_shift;
       if ((1 << cv_shift) != cv || bs > 65535 || hh > 65535) {

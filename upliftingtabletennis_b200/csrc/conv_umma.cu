@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(HF ? THREADS_HF : THREADS, 1) conv_umma_kernel
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           if (g + 1 < G) fetch(g + 1, v[(g + 1) & 1], rv[(g + 1) & 1]);
-          if constexpr (C::STG) {
+          if (C::STG && nres == 0) {         // (with a residual the staged form measured slower: 0.74 vs 0.60 ms for the half-resolution conv2 layers)
             // the group's 32 channels of this lane's pixel -> staging row `lane` (16-byte chunk c at slot c ^ (lane & 7): conflict free),
             // then 4 store instructions of 8 pixels x 128 contiguous bytes each (lane = pixel it * 8 + lane / 4, 32-byte piece lane % 4)
             const int col = g * GCOLS, r = R - 1 - col / COUT, c0 = col % COUT;
